@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Headline benchmark: EGConv forward+backward edges/s on synthetic arxiv-/mag-shaped graphs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|mag|cifar|zinc] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one EGConv layer forward + backward over the whole synthetic graph (BASELINE.json
+configs[1] at N=1: EGC-M symnorm+max+std, H4 B4, 128->128 on an ogbn-arxiv-shaped graph, structure
+cached as in the reference's full-graph training).  Rank 0 prints ONE JSON line.
+`value` = aggregated nnz (after symmetrisation + self-loops) per second with inputs resident in HBM,
+`e2e` = same through the public `EGConv` API with the step's features arriving from pinned host
+memory and the loss read back; `roofline` is for the dominant kernel, `cpu_baseline` is the oracle
+port of the reference path timed on this box's host cores.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: nodes, raw directed edges, F_in, F_out, heads, bases, aggregators, input kind, zipf exponent
+    "arxiv": dict(n=169_343, e0=1_166_243, f_in=128, f_out=128, heads=4, bases=4,
+                  aggrs=["symnorm", "max", "std"], kind="edge_index", zipf=0.75,
+                  desc="EGC-M (symnorm+max+std, H4 B4) 128->128, ogbn-arxiv-shaped, 1 layer fwd+bwd"),
+    "mag": dict(n=736_389, e0=5_416_271, f_in=128, f_out=128, heads=8, bases=4,
+                aggrs=["symnorm"], kind="adj_t", zipf=0.70,
+                desc="EGC-S (symnorm, H8 B4) 128->128, ogbn-mag-shaped paper graph, 1 layer fwd+bwd"),
+}
+L2_BYTES = 126e6
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic graphs (seeded; shapes from SURVEY.md section 8)
+# ------------------------------------------------------------------------------------------------
+def synth_graph(kind: str, seed: int = 0, p_intra: float = 0.0, blocks: int = 8):
+    """(num_nodes, edge_index int64 [2, E]) - power-law in-degree (Zipf over a random node order),
+    near-uniform out-degree, symmetrised + de-duplicated like `to_undirected` / `to_symmetric`
+    (ref experiments/arxiv/configs.py:100, experiments/mag/configs.py:84-85).
+    p_intra: probability that an edge stays inside its target's contiguous id block (locality knob
+    for row-partitioned runs)."""
+    w = WORKLOADS[kind]
+    n, e0 = w["n"], w["e0"]
+    rng = np.random.default_rng(seed)
+    rank = rng.permutation(n)
+    p = 1.0 / np.power(np.arange(1, n + 1, dtype=np.float64), w["zipf"])
+    p /= p.sum()
+    dst = rank[rng.choice(n, size=e0, p=p)]
+    src = rng.integers(0, n, size=e0)
+    if p_intra > 0:
+        bs = (n + blocks - 1) // blocks
+        local = rng.random(e0) < p_intra
+        lo = (dst // bs) * bs
+        src = np.where(local, np.minimum(lo + rng.integers(0, bs, size=e0), n - 1), src)
+    key = np.unique(np.concatenate([src * n + dst, dst * n + src]))
+    ei = np.stack([key // n, key % n])
+    return n, torch.from_numpy(ei.astype(np.int64))
+
+
+def to_adj_t(edge_index, n):
+    """rows = targets, sorted by (target, source) (ref experiments/utils.py:93,107-109)."""
+    perm = (edge_index[1] * n + edge_index[0]).argsort(stable=True)
+    src, dst = edge_index[0][perm], edge_index[1][perm]
+    rowptr = torch.zeros(n + 1, dtype=torch.long)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    return rowptr, src
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic (unique) bytes - SURVEY.md section 8(d) / BASELINE.md section 2
+# ------------------------------------------------------------------------------------------------
+def stream_counts(aggrs):
+    sym = int("symnorm" in aggrs)
+    lin = int(any(a in ("sum", "mean", "var", "std") for a in aggrs))
+    sq = int(any(a in ("var", "std") for a in aggrs))
+    n_arg = sum(a in ("max", "min") for a in aggrs)
+    return sym, lin, sq, n_arg
+
+
+def algorithmic_bytes(n, e, f_in, heads, bases, dim, aggrs):
+    a, bd, f_out = len(aggrs), bases * dim, heads * dim
+    hab = heads * a * bases
+    sym, lin, sq, n_arg = stream_counts(aggrs)
+    L = sym + lin + sq
+    bf = 4 * n * (f_in + 2 * bd + 2 * hab + f_out + n_arg * bd) + 4 * (e + n + 1) + 4 * n * sym
+    bb = 4 * n * (f_out + hab + bd + n_arg * bd + 2 * hab + 2 * L * bd + 2 * bd + 2 * f_in) + 8 * (e + n + 1) + 4 * n * sym
+    return bf, bb
+
+
+def kernel_algorithmic_bytes(n, e, f_in, heads, bases, dim, aggrs):
+    """Unique bytes each kernel of the step must move (DESIGN.md 'kernels'); same accounting as above."""
+    a, bd, f_out = len(aggrs), bases * dim, heads * dim
+    hab = heads * a * bases
+    sym, lin, sq, n_arg = stream_counts(aggrs)
+    L = sym + lin + sq
+    csr = 4 * (e + n + 1)
+    return {
+        "k_gemm_f32": None,   # several launches of different shapes; reported through the step total
+        "k_aggregate_fwd": 4 * n * (bd + hab + f_out) + csr + 4 * n * sym,
+        "k_aggregate_bwd": 4 * n * (bd + hab + f_out + hab + L * bd) + csr + 4 * n * sym,
+        "k_scatter_bwd": 4 * n * (L * bd + bd + (bd if sq else 0) + (bd if n_arg else 0)) + csr,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (recipe in /opt/skills/guides/B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path of the reference (oracle port), used by --impl reference and by the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(w, n, edge_index, frac, seed=0):
+    """Builds a closure running one fwd+bwd of the reference path on the host for the targets < frac*n.
+    Returns (step_fn, nnz_aggregated, description)."""
+    from oracle import restatement as R
+    torch.manual_seed(seed)
+    ei = edge_index
+    if frac < 1.0:
+        keep = ei[1] < int(frac * n)
+        ei = ei[:, keep]
+    layer = R.EGConvOracle(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"],
+                           cached=True)
+    x = torch.randn(n, w["f_in"], requires_grad=True)
+    go = torch.randn(n, w["f_out"])
+    graph_in = ei if w["kind"] == "edge_index" else to_adj_t(ei, n) + (None,)
+    g = layer.prepare(x, graph_in)      # cached structure, like the reference's full-graph runs
+
+    def step():
+        for p_ in layer.parameters():
+            p_.grad = None
+        x.grad = None
+        out = layer(x, graph_in)
+        out.backward(go)
+        return out
+
+    return step, g.nnz, f"targets < {frac:.3f}*N of the {w['kind']} graph ({g.nnz} nnz incl. self-loops), full x"
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_reference_arm(args, w, n, edge_index):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # calibrate on a 1/16 sample, then size the sample so the whole run stays within ~150 s
+    step_small, nnz_small, _ = cpu_reference_step_factory(w, n, edge_index, 1 / 16)
+    t_small = time_cpu(step_small, 1, 1)
+    t_full_est = t_small * 16
+    budget = 150.0
+    frac = min(1.0, budget / max(t_full_est * (args.steps + args.warmup), 1e-9))
+    frac = max(frac, 1 / 64)
+    step, nnz, sample = cpu_reference_step_factory(w, n, edge_index, frac)
+    t = time_cpu(step, args.steps, args.warmup)
+    value = nnz / t
+    line = {
+        "impl": "reference", "metric": "EGConv fwd+bwd edges/s", "value": value, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "nodes": n, "nnz": nnz, "sample": sample,
+                   "path": "oracle port of the reference's PyG path (pure-torch leaf ops), host CPU"},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def run_single_gpu(args, w, n, edge_index):
+    import egc_b200
+    from egc_b200 import _lib
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    conv = egc_b200.EGConv(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"],
+                           cached=True).to(dev)
+    x_host = torch.randn(n, w["f_in"]).pin_memory()
+    go = torch.randn(n, w["f_out"], device=dev)
+    if w["kind"] == "edge_index":
+        graph_in = edge_index.to(dev)
+    else:
+        rowptr, col = to_adj_t(edge_index, n)
+        graph_in = egc_b200.SparseTensor(rowptr=rowptr.to(dev), col=col.to(dev), sparse_sizes=(n, n), is_sorted=True)
+    x = x_host.to(dev).requires_grad_(True)
+    params = list(conv.parameters())
+
+    def step():
+        out = conv(x, graph_in)
+        torch.autograd.grad(out, [x] + params, go)
+        return out
+
+    def step_e2e():
+        xs = x_host.to(dev, non_blocking=True).requires_grad_(True)
+        out = conv(xs, graph_in)
+        loss = (out * go).sum()
+        torch.autograd.grad(loss, [xs] + params)
+        return float(loss.item())
+
+    step()                                              # builds + caches the graph structure (CSR, CSC, plans)
+    graph = conv._cached_edge_index if w["kind"] == "edge_index" else conv._cached_adj_t
+    nnz = graph.nnz
+    dim = w["f_out"] // w["heads"]
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launch_count()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps, _lib.launch_count() - launches0
+
+    with ClockSampler(dev.index or 0) as clocks:
+        ms, launches = timed(step, args.steps, args.warmup)
+        ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    # per-kernel times (CUDA events around every launch of the library, same steps, separate pass)
+    _lib.profile_enable(True)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+
+    peak, peak_src = load_peaks()
+    bf, bb = algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], dim, w["aggrs"])
+    kbytes = kernel_algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], dim, w["aggrs"])
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t / args.steps} for k, (c, t) in prof.items()}
+    cand = [k for k in kernels if kbytes.get(k)]
+    dom = max(cand, key=lambda k: kernels[k]["ms_per_step"]) if cand else None
+    roofline = None
+    if dom:
+        per_launch_ms = prof[dom][1] / prof[dom][0]
+        achieved = kbytes[dom] / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kbytes[dom], "ms_per_launch": per_launch_ms}
+    step_gbs = (bf + bb) / (ms * 1e-3) / 1e9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        frac = 1.0 if args.workload == "arxiv" else 0.25
+        cstep, cnnz, sample = cpu_reference_step_factory(w, n, edge_index, frac)
+        t_cpu = time_cpu(cstep, 2, 1)
+        cpu = {"value": cnnz / t_cpu, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": f"{sample}; 1 warm-up + 2 timed fwd+bwd steps, {t_cpu:.2f} s/step"}
+
+    line = {
+        "metric": "EGConv fwd+bwd edges/s", "value": nnz / (ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "nodes": n, "raw_directed_edges": w["e0"], "nnz": nnz,
+                   "input": w["kind"], "structure": "cached (graph prepared once, as the reference's cached=True)",
+                   "l2": f"no flush: per-step working set {(bf + bb) / 1e9:.2f} GB >> {L2_BYTES / 1e6:.0f} MB L2",
+                   "algorithmic_bytes_per_step": bf + bb, "bytes_per_edge": (bf + bb) / nnz},
+        "clocks": clocks.summary(),
+        "e2e": {"value": nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "step_roofline": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "kernels": kernels,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    w = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n, ei = synth_graph(args.workload, args.seed)
+        run_reference_arm(args, w, n, ei)
+        return
+
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        from egc_b200 import dist_bench
+        dist_bench.run(args, w)
+        return
+    n, ei = synth_graph(args.workload, args.seed)
+    run_single_gpu(args, w, n, ei)
+
+
+if __name__ == "__main__":
+    main()

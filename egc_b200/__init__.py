@@ -1,0 +1,16 @@
+"""egc_b200 - B200 (sm_100a) implementation of the EGConv message-passing hot path of shyam196/egc.
+
+Public surface (mirrors the reference operator API, /root/reference/experiments/optimized_layers.py):
+    EGConv            drop-in layer
+    SparseTensor      minimal `torch_sparse.SparseTensor` container accepted by EGConv.forward
+    GraphStructure    prepared device graph (CSR / CSC / symnorm weights / long-row plan)
+    egconv            functional form on a prepared graph
+    build / load      compile / load libegc_b200.so (C ABI in include/egc_b200.h)
+"""
+from ._lib import (BWD_DETERMINISTIC, GEMM_3XTF32, GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, EGCError, build,  # noqa: F401
+                   load)
+from .conv import EGConv  # noqa: F401
+from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
+from .graph import GraphStructure, SparseTensor  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,138 @@
+"""Autograd boundary between PyTorch and the C-ABI kernels of `libegc_b200.so`.
+
+`egconv(x, graph, bases_weight, comb_weight, comb_bias, bias, ...)` computes what
+/root/reference/experiments/optimized_layers.py:177-210 computes after graph preparation
+(projections -> multi-aggregator message passing -> per-head combination -> bias) and its backward is
+the hand-written one (CSR pass, atomic-free CSC pass, projection gradients).  PyTorch only owns
+the memory and the stream.
+"""
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import LayerDesc, check, ptr
+from .graph import GraphStructure, _stream, _ws
+
+
+def make_desc(graph: GraphStructure, heads: int, bases: int, dim: int, aggrs: Sequence[str], sigmoid: bool) -> LayerDesc:
+    if len(aggrs) < 1 or len(aggrs) > _lib.EGC_MAX_AGGR:
+        raise ValueError(f"between 1 and {_lib.EGC_MAX_AGGR} aggregators are supported, got {len(aggrs)}")
+    d = LayerDesc()
+    d.n_dst, d.n_src = graph.n_dst, graph.n_src
+    d.heads, d.bases, d.dim = heads, bases, dim
+    d.n_aggr = len(aggrs)
+    for i, a in enumerate(aggrs):
+        if a not in _lib.AGGR_CODES:
+            raise ValueError(f'Unknown aggregator "{a}".')           # ref :246
+        d.aggr[i] = _lib.AGGR_CODES[a]
+    d.sigmoid = int(bool(sigmoid))
+    return d
+
+
+def _require_cuda_f32(name: str, t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"egc_b200: `{name}` must be a CUDA tensor - this library has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"egc_b200: `{name}` must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def project(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor], sigmoid: bool,
+            algo: int = _lib.GEMM_AUTO):
+    """bases = x @ W_b ; weightings = act(x @ W_c^T + b_c)   (ref :180-184)"""
+    lib = _lib.load()
+    n, f_in = x.shape
+    bd, hab = bases_weight.shape[1], comb_weight.shape[0]
+    bases = torch.empty((n, bd), dtype=torch.float32, device=x.device)
+    weightings = torch.empty((n, hab), dtype=torch.float32, device=x.device)
+    if n > 0:
+        check(lib.egc_project_fwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(comb_bias), n, f_in, bd, hab,
+                                  int(sigmoid), ptr(bases), ptr(weightings), algo, _stream()), "egc_project_fwd")
+    return bases, weightings
+
+
+def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Optional[Tensor],
+                      bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False):
+    """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg); unrequested ones are None."""
+    lib = _lib.load()
+    dev = bases.device
+    n, bd, hd = desc.n_dst, desc.bases * desc.dim, desc.heads * desc.dim
+    out = torch.empty((n, hd), dtype=torch.float32, device=dev) if want_out else None
+    agg = torch.empty((n, desc.n_aggr, bd), dtype=torch.float32, device=dev) if want_agg else None
+    arg = torch.empty((n, desc.n_aggr, bd), dtype=torch.int32, device=dev) if want_arg else None
+    plan = graph.plan.struct
+    nbytes = lib.egc_aggregate_fwd_workspace_bytes(desc, plan)
+    ws = _ws(nbytes, dev)
+    check(lib.egc_aggregate_fwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin), plan,
+                                ptr(bases), ptr(weightings), ptr(bias), ptr(out), ptr(agg), ptr(arg), ptr(ws), nbytes,
+                                _stream()), "egc_aggregate_fwd")
+    return out, agg, arg
+
+
+class _EGConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, graph, heads, num_bases, aggrs, sigmoid, algo,
+                bwd_flags):
+        x = _require_cuda_f32("x", x)
+        bases_weight = _require_cuda_f32("bases_weight", bases_weight)
+        comb_weight = _require_cuda_f32("comb_weight.weight", comb_weight)
+        comb_bias = _require_cuda_f32("comb_weight.bias", comb_bias)
+        bias = _require_cuda_f32("bias", bias)
+        if x.dim() != 2 or x.size(0) != graph.n_src or graph.n_src != graph.n_dst:
+            raise ValueError(f"x must be [num_nodes, in_channels] with num_nodes == {graph.n_src}")
+        dim = bases_weight.size(1) // num_bases
+        desc = make_desc(graph, heads, num_bases, dim, aggrs, sigmoid)
+        with torch.cuda.device(x.device):
+            bases, weightings = project(x, bases_weight, comb_weight, comb_bias, sigmoid, algo)
+            out, _, _ = aggregate_combine(desc, graph, bases, weightings, bias)
+        ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings)
+        ctx.graph, ctx.desc, ctx.algo, ctx.bwd_flags = graph, desc, algo, bwd_flags
+        ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, bases_weight, comb_weight, bases, weightings = ctx.saved_tensors
+        graph, desc = ctx.graph, ctx.desc
+        lib = _lib.load()
+        dev = x.device
+        grad_out = _require_cuda_f32("grad_out", grad_out)
+        n, f_in = x.shape
+        bd, hab = bases_weight.shape[1], comb_weight.shape[0]
+        need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
+        with torch.cuda.device(dev):
+            graph.ensure_csc()
+            d_w = torch.empty((n, hab), dtype=torch.float32, device=dev)
+            d_bases = torch.empty((graph.n_src, bd), dtype=torch.float32, device=dev)
+            d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if (need_b and ctx.has_bias) else None
+            nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.nnz, graph.plan.struct, graph.csc_plan.struct,
+                                                           ctx.bwd_flags)
+            ws = _ws(nbytes, dev)
+            check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin),
+                                        graph.plan.struct, ptr(graph.colptr), ptr(graph.rowidx), ptr(graph.csr2csc),
+                                        ptr(graph.csc_val_sym), ptr(graph.csc_val_lin), graph.csc_plan.struct,
+                                        ptr(bases), ptr(weightings), ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias),
+                                        ctx.bwd_flags, ptr(ws), nbytes, _stream()), "egc_aggregate_bwd")
+            del ws
+            d_x = torch.empty_like(x) if need_x else None
+            d_wb = torch.empty_like(bases_weight) if need_wb else None
+            d_wc = torch.empty_like(comb_weight) if need_wc else None
+            d_bc = torch.empty(hab, dtype=torch.float32, device=dev) if (need_bc and ctx.has_comb_bias) else None
+            nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
+            ws = _ws(nbytes, dev)
+            check(lib.egc_project_bwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(d_bases), ptr(d_w), n, f_in, bd,
+                                      hab, ptr(d_x), ptr(d_wb), ptr(d_wc), ptr(d_bc), ctx.algo, ptr(ws), nbytes,
+                                      _stream()), "egc_project_bwd")
+        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None
+
+
+def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
+           bias: Optional[Tensor], num_heads: int, num_bases: int, aggrs: Sequence[str], sigmoid: bool = False,
+           algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0) -> Tensor:
+    """Differentiable EGConv layer body on a prepared graph."""
+    return _EGConvFunction.apply(x, bases_weight, comb_weight, comb_bias, bias, graph, num_heads, num_bases,
+                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags))

@@ -1,0 +1,228 @@
+/*
+ * egc_b200.h - C ABI of libegc_b200.so: the B200 (sm_100a) implementation of the EGConv
+ * message-passing hot path of shyam196/egc.
+ *
+ * Every entry point is what a binding of the reference's hot path would call instead of the
+ * torch / torch_scatter / torch_sparse / torch_geometric leaf ops.  "ref" citations are
+ * relative to /root/reference/ (experiments/optimized_layers.py unless another file is named).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked host;
+ *   - every function returns 0 (EGC_OK) or a negative egc_status; the message of the last
+ *     failure on the calling thread is available from egc_last_error_string();
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing here
+ *     allocates or frees caller-visible memory or synchronises the device; scratch space is
+ *     a caller-owned workspace whose size comes from the matching *_workspace_bytes();
+ *   - features are fp32, row-major, contiguous; graph indices are int32 on the device
+ *     (the reference's int64 edge_index / rowptr / col are narrowed by the build functions);
+ *   - target-major CSR: row i lists the sources j of the messages node i receives
+ *     (= the reference's `adj_t`, ref experiments/utils.py:107-109).
+ */
+#ifndef EGC_B200_H_
+#define EGC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGC_ABI_VERSION 1
+#define EGC_MAX_AGGR 8          /* len(aggrs) accepted by one layer */
+#define EGC_CHUNK_EDGES 256     /* rows longer than this are split into chunks of this many nnz */
+
+typedef enum egc_status {
+  EGC_OK = 0,
+  EGC_ERR_INVALID_ARGUMENT = -1,
+  EGC_ERR_CUDA = -2,
+  EGC_ERR_UNSUPPORTED = -3,
+  EGC_ERR_WORKSPACE = -4
+} egc_status;
+
+/* Aggregator codes, ref :93 {"sum","mean","symnorm","min","max","var","std"}. */
+typedef enum egc_aggr {
+  EGC_AGGR_SUM = 0,
+  EGC_AGGR_MEAN = 1,
+  EGC_AGGR_SYMNORM = 2,
+  EGC_AGGR_MIN = 3,
+  EGC_AGGR_MAX = 4,
+  EGC_AGGR_VAR = 5,
+  EGC_AGGR_STD = 6
+} egc_aggr;
+
+/* Shape of one EGConv layer invocation (ref :96-108, :195-202). */
+typedef struct egc_layer_desc {
+  int32_t n_dst;                 /* target nodes = CSR rows = rows of weightings / out            */
+  int32_t n_src;                 /* source nodes = rows of bases (== n_dst for EGConv)            */
+  int32_t heads;                 /* H                                                             */
+  int32_t bases;                 /* B                                                             */
+  int32_t dim;                   /* D = out_channels / H; a basis row has B*D floats              */
+  int32_t n_aggr;                /* A = len(aggrs), 1..EGC_MAX_AGGR                               */
+  int32_t aggr[EGC_MAX_AGGR];    /* egc_aggr codes in the order given to the constructor          */
+  int32_t sigmoid;               /* weightings went through sigmoid (ref :183-184)                */
+} egc_layer_desc;
+
+/* Row plan: how long rows of a CSR (or columns of its CSC) are split into chunks so that no
+ * warp walks more than EGC_CHUNK_EDGES nnz.  Built once per graph by egc_plan_build(). */
+typedef struct egc_row_plan {
+  int32_t n_long;                /* rows with more than EGC_CHUNK_EDGES nnz                       */
+  int32_t n_chunks;              /* total chunks over those rows                                  */
+  const int32_t* long_rows;      /* [n_long]    row id                                            */
+  const int32_t* long_chunk_ptr; /* [n_long+1]  first chunk of each long row                      */
+  const int32_t* chunk_row;      /* [n_chunks]  row id of the chunk                               */
+  const int32_t* chunk_begin;    /* [n_chunks]  first nnz of the chunk; it ends at min(begin+EGC_CHUNK_EDGES, row end) */
+} egc_row_plan;
+
+int egc_abi_version(void);
+const char* egc_last_error_string(void);      /* host string, valid until the thread's next failing call */
+/* compile-time facts of the loaded binary, for INTEGRATION / smoke checks */
+const char* egc_build_info(void);
+
+/* Launch accounting / tracing (the reference has no tracing at all).
+ * egc_launch_count(): kernels launched by this library in this process (always counted).
+ * egc_profile_enable(1): from now on every kernel launch is bracketed by CUDA events on its stream;
+ * egc_profile_collect() synchronises those events and writes one "name,launches,total_ms\n" line per
+ * kernel name into buf (returns the number of bytes written, negative on error) and clears the table. */
+uint64_t egc_launch_count(void);
+int egc_profile_enable(int32_t on);
+int egc_profile_collect(char* buf /* host */, size_t capacity);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph preparation (bit-exact integer work)
+ * ---------------------------------------------------------------------------------------- */
+
+/* meta[] slots written (device int32[8]) by the graph builders */
+#define EGC_META_NNZ 0          /* nnz of the produced CSR                                        */
+#define EGC_META_MAX_DEG 1      /* longest row                                                    */
+#define EGC_META_N_LONG 2       /* rows longer than EGC_CHUNK_EDGES                               */
+#define EGC_META_N_CHUNKS 3     /* chunks over those rows                                         */
+#define EGC_META_N_LOOPS 4      /* self-loops appended                                            */
+#define EGC_META_SLOTS 8
+
+/* loops: how self-loops are handled for an edge_index input */
+#define EGC_LOOPS_NONE 0        /* add_self_loops=False: graph used untouched                     */
+#define EGC_LOOPS_ALL_NODES 1   /* gcn_norm(..., num_nodes=N) -> add_remaining_self_loops, ref :131-137 */
+#define EGC_LOOPS_UP_TO_MAX_ID 2/* add_remaining_self_loops(edge_index) without num_nodes, ref :164:
+                                   only nodes <= edge_index.max() get a loop                      */
+
+size_t egc_csr_from_edges_workspace_bytes(int64_t n_edges, int32_t n_nodes);
+/* edge_index (int64, row 0 = source j, row 1 = target i; ref :128-141 / :159-166) -> target-major CSR.
+ * Existing self-loops are dropped and one loop per node is appended AFTER all other edges
+ * (PyG add_remaining_self_loops); rows keep the edge order of the input (stable sort by target), so
+ * "first element wins" ties of min/max resolve as in torch_scatter.
+ * Outputs: rowptr[n_nodes+1], col[capacity n_edges + n_nodes] (first meta[NNZ] valid), meta[8]. */
+int egc_csr_from_edges(const int64_t* src, const int64_t* dst, int64_t n_edges, int32_t n_nodes,
+                       int32_t loops, int32_t* rowptr, int32_t* col, int32_t* meta,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* SparseTensor input (ref :143-156, :168-175; torch_sparse fill_diag): narrows an int64 CSR to int32
+ * and, if fill_diag != 0, removes every diagonal entry and inserts one per i < min(n_dst, n_src) at
+ * its sorted position (diagonal value 1.0 when the matrix carries values).
+ * value_in may be NULL.  Outputs: rowptr[n_dst+1], col / value_out [capacity nnz_in + min(n_dst,n_src)], meta[8]. */
+size_t egc_csr_fill_diag_workspace_bytes(int32_t n_dst);
+int egc_csr_fill_diag(const int64_t* rowptr_in, const int64_t* col_in, const float* value_in,
+                      int32_t n_dst, int32_t n_src, int32_t fill_diag, int32_t* rowptr, int32_t* col,
+                      float* value_out, int32_t* meta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* gcn_norm (ref :131-137, :146-152): deg[i] = sum of row i's values (nnz count when value == NULL),
+ * dis = deg^-1/2 with inf -> 0, val_sym[e] = (value[e] * dis[row(e)]) * dis[col(e)].
+ * Requires n_src == n_dst when called for EGConv.  deg / dis may be NULL if not wanted. */
+int egc_symnorm_weights(const int32_t* rowptr, const int32_t* col, const float* value, int32_t n_dst,
+                        float* deg, float* dis, float* val_sym, void* stream);
+
+/* CSC view used by the backward pass (the reference caches torch_sparse's csr2csc,
+ * ref experiments/utils.py:111-113): colptr[n_src+1], rowidx[nnz] (target of each entry),
+ * csr2csc[nnz] (CSR position of each CSC entry; stable, i.e. targets ascending inside a column). */
+size_t egc_csr_transpose_workspace_bytes(int32_t nnz, int32_t n_dst, int32_t n_src);
+int egc_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t nnz, int32_t n_dst, int32_t n_src,
+                      int32_t* colptr, int32_t* rowidx, int32_t* csr2csc, int32_t* meta,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[k] = in[perm[k]] for fp32 per-nnz values (CSR order -> CSC order). */
+int egc_permute_f32(const float* in, const int32_t* perm, int32_t n, float* out, void* stream);
+
+/* Chunk plan of the long rows of a CSR (meta[N_LONG], meta[N_CHUNKS] give the array sizes). */
+int egc_plan_build(const int32_t* rowptr, int32_t n_rows, int32_t n_long, int32_t n_chunks,
+                   int32_t* long_rows, int32_t* long_chunk_ptr, int32_t* chunk_row, int32_t* chunk_begin,
+                   void* workspace, size_t workspace_bytes, void* stream);
+size_t egc_plan_build_workspace_bytes(int32_t n_rows);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections  (ref :180 `torch.matmul(x, bases_weight)`, :182-184 `comb_weight(x)` [+ sigmoid])
+ * ---------------------------------------------------------------------------------------- */
+
+#define EGC_GEMM_AUTO 0         /* tcgen05 3xTF32 when the shape allows, else fp32 FFMA            */
+#define EGC_GEMM_FP32_SIMT 1    /* exact fp32 FFMA tiles (any shape)                               */
+#define EGC_GEMM_3XTF32 2       /* tcgen05 kind::tf32, 3-term split: fp32-level accuracy           */
+#define EGC_GEMM_TF32 3         /* tcgen05 kind::tf32, single pass (~1e-3 relative)                */
+
+/* bases[n, bd] = x[n, f_in] . w_bases[f_in, bd]
+ * weightings[n, hab] = act(x . w_comb[hab, f_in]^T + b_comb[hab]),  act = sigmoid if `sigmoid`. */
+int egc_project_fwd(const float* x, const float* w_bases, const float* w_comb, const float* b_comb,
+                    int32_t n, int32_t f_in, int32_t bd, int32_t hab, int32_t sigmoid,
+                    float* bases, float* weightings, int32_t algo, void* stream);
+
+/* Autograd of the two projections (ref: implicit backward of :180-182).  d_lin is the gradient
+ * w.r.t. the pre-activation of comb_weight (sigmoid' already applied by egc_aggregate_bwd).
+ *   d_x[n,f_in]       = d_bases . w_bases^T + d_lin . w_comb        (d_x may be NULL)
+ *   d_w_bases[f_in,bd] = x^T . d_bases ; d_w_comb[hab,f_in] = d_lin^T . x ; d_b_comb[hab] = colsum(d_lin)
+ * Parameter gradients are OVERWRITTEN (not accumulated). */
+size_t egc_project_bwd_workspace_bytes(int32_t n, int32_t f_in, int32_t bd, int32_t hab);
+int egc_project_bwd(const float* x, const float* w_bases, const float* w_comb,
+                    const float* d_bases, const float* d_lin, int32_t n, int32_t f_in, int32_t bd, int32_t hab,
+                    float* d_x, float* d_w_bases, float* d_w_comb, float* d_b_comb,
+                    int32_t algo, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-aggregator CSR SpMM + per-node/per-head combination
+ * (ref :191 propagate -> :215-249 aggregate / :251-278 message_and_aggregate, :195-208 combine + bias)
+ * ---------------------------------------------------------------------------------------- */
+
+/* out[i, h*D+d] = bias[h*D+d] + sum_{a,b} weightings[i, h*A*B + a*B + b] * agg_a(i)[b*D + d]
+ * where agg_a(i) reduces bases[j, :] over the nnz of CSR row i with aggregator a:
+ *   sum / mean (divide by nnz count, min 1) / symnorm (weights val_sym) / min / max (empty row -> 0,
+ *   first nnz wins ties) / var = mean(x^2) - mean(x)^2 / std = sqrt(relu(var) + 1e-5).
+ * val_sym: per-nnz weights for symnorm (required iff symnorm is requested).
+ * val_lin: per-nnz weights applied by every other aggregator (NULL = unweighted; only a valued
+ *          SparseTensor without symnorm produces them, ref :256-258).
+ * bias may be NULL.  Optional debug/inspection outputs (NULL to skip):
+ *   agg_out[n_dst, A, B*D]  the aggregated bases before combination (ref :249 / :278)
+ *   arg_out[n_dst, A, B*D]  int32 nnz position of the winning element for min/max slots (-1: empty row,
+ *                           other slots -1); source id = col[arg]. */
+size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* plan);
+int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
+                      const float* val_sym, const float* val_lin, const egc_row_plan* plan,
+                      const float* bases, const float* weightings, const float* bias,
+                      float* out, float* agg_out, int32_t* arg_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (ref: autograd of :191-208; torch_sparse spmm backward over the cached CSC).
+ * Pass 1 (CSR, per target): recomputes the aggregates, writes d_weightings (times sigmoid' when
+ * desc->sigmoid; = gradient w.r.t. the Linear output) and the target-side streams; min/max gradients are
+ * routed to the single winning source.  Pass 2 (CSC, per source, atomic-free):
+ *   d_bases[j] = sum_e val_sym[e] t_sym[i_e] + val_lin[e] (t_lin[i_e] + 2 bases[j] t_sq[i_e]) + routed.
+ * csc_val_sym / csc_val_lin are val_sym / val_lin in CSC order (NULL like their CSR twins).
+ * d_bias (may be NULL) = column sums of grad_out.  flags: EGC_BWD_* bits. */
+#define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients through the CSC pass (no fp32 atomics) */
+size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, int32_t nnz, const egc_row_plan* csr_plan,
+                                         const egc_row_plan* csc_plan, int32_t flags);
+int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
+                      const float* val_sym, const float* val_lin, const egc_row_plan* csr_plan,
+                      const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc,
+                      const float* csc_val_sym, const float* csc_val_lin, const egc_row_plan* csc_plan,
+                      const float* bases, const float* weightings, const float* grad_out,
+                      float* d_weightings, float* d_bases, float* d_bias, int32_t flags,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row exchange for row-partitioned graphs (no reference counterpart; see DESIGN.md "multi-GPU")
+ * ---------------------------------------------------------------------------------------- */
+
+/* dst[k, :] = src[index[k], :]  (pack halo rows before a send / all-gather), width floats per row */
+int egc_gather_rows(const float* src, const int32_t* index, int32_t n_index, int32_t width, float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGC_B200_H_ */

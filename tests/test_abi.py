@@ -1,0 +1,80 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and the Python operator mirrors the reference constructor contract.  No compute calls."""
+import os
+import re
+
+import pytest
+import torch
+
+import egc_b200
+from egc_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "egc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(egc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = egc_b200.load()
+    names = header_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/egc_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in egc_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_build_info():
+    lib = egc_b200.load()
+    assert lib.egc_abi_version() == 1
+    info = lib.egc_build_info().decode()
+    assert "sm_100a" in info and "chunk_edges=256" in info
+
+
+def test_struct_layouts_match_header():
+    assert _lib.LayerDesc.aggr.offset == 24 and _lib.LayerDesc.sigmoid.offset == 24 + 4 * 8
+    import ctypes
+    assert ctypes.sizeof(_lib.LayerDesc) == 60
+    assert ctypes.sizeof(_lib.RowPlan) == 8 + 4 * 8
+
+
+def test_constructor_contract_matches_reference():
+    # ref optimized_layers.py:89-94 error behaviour, :105-113 parameter shapes, :280-286 repr
+    with pytest.raises(ValueError, match="divisible"):
+        egc_b200.EGConv(16, 100, num_heads=8)
+    with pytest.raises(ValueError, match="Unsupported aggregator"):
+        egc_b200.EGConv(16, 32, aggrs=["symadd"])
+    conv = egc_b200.EGConv(128, 128, aggrs=["symnorm", "max", "std"], num_heads=4, num_bases=4)
+    sd = conv.state_dict()
+    assert list(sd) == ["bases_weight", "bias", "comb_weight.weight", "comb_weight.bias"]
+    assert sd["bases_weight"].shape == (128, 128) and sd["comb_weight.weight"].shape == (48, 128)
+    assert sd["comb_weight.bias"].shape == (48,) and sd["bias"].shape == (128,)
+    assert repr(conv) == "EGConv(128, 128, ['symnorm', 'max', 'std'])"
+    assert float(sd["bias"].abs().max()) == 0.0
+    bound = (6.0 / (128 + 128)) ** 0.5
+    assert float(sd["bases_weight"].abs().max()) <= bound
+    assert egc_b200.EGConv(8, 16, bias=False).bias is None
+    # known-answer parameter count: one ZINC EGC-S layer (hidden 168, H8 B4) = 19 688
+    # (4 layers = 78 752 of the 102 861 printed at output/pretrained.txt:41)
+    zinc = egc_b200.EGConv(168, 168, aggrs=["symnorm"], num_heads=8, num_bases=4)
+    assert sum(p.numel() for p in zinc.parameters()) == 19688
+
+
+def test_no_cpu_fallback():
+    conv = egc_b200.EGConv(8, 16, num_heads=4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        conv(torch.randn(4, 8), torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        egc_b200.GraphStructure.from_edge_index(torch.zeros(2, 3, dtype=torch.long), 4, True, True)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "egc_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, f"egc_b200/{fn} mentions the oracle"

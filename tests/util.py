@@ -1,0 +1,47 @@
+"""Shared helpers for the test-suite (graph generators, fixtures, comparisons)."""
+import glob
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+def random_graph(n, e, seed, hub=0, isolated=2, self_loops=5, dups=20):
+    """edge_index [2, E'] with a few self-loops, duplicated edges, trailing isolated nodes, optional hubs."""
+    gen = torch.Generator().manual_seed(seed)
+    hi = max(n - isolated, 1)
+    src = torch.randint(0, hi, (e,), generator=gen)
+    dst = torch.randint(0, hi, (e,), generator=gen)
+    src[:self_loops] = dst[:self_loops]
+    src = torch.cat([src, src[self_loops:self_loops + dups]])
+    dst = torch.cat([dst, dst[self_loops:self_loops + dups]])
+    if hub:
+        others = torch.randperm(hi, generator=gen)[:hub]
+        src = torch.cat([src, others, torch.full((others.numel(),), 3)])
+        dst = torch.cat([dst, torch.full((others.numel(),), 7), others])
+    return torch.stack([src, dst])
+
+
+def to_adj_csr(edge_index, n, value=None):
+    """(rowptr, col, value) of adj_t: rows = targets, sorted by (target, source) - experiments/utils.py:93."""
+    perm = (edge_index[1] * n + edge_index[0]).argsort(stable=True)
+    src, dst = edge_index[0][perm], edge_index[1][perm]
+    rowptr = torch.zeros(n + 1, dtype=torch.long)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    return rowptr, src, (value[perm] if value is not None else None)
+
+
+def rel_err(a, b):
+    """max |a-b| relative to max |b| (the 1e-5 bar of BASELINE.json is on this quantity)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    denom = b.abs().max().clamp(min=1e-30)
+    return ((a - b).abs().max() / denom).item()
