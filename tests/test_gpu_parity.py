@@ -31,30 +31,46 @@ def oracle_and_cuda(f_in, f_out, aggrs, h, b, loops=True, sigmoid=False, bias=Tr
     return o, c.to(DEV)
 
 
-def run_both(o, c, x, graph_cpu, graph_gpu, grad_out, dtype=torch.float64):
-    """fp64 oracle on CPU vs fp32 kernels on GPU; returns dict name -> (cuda, oracle)."""
+def _oracle_run(o, x, graph_cpu, grad_out, dtype):
     od = R.EGConvOracle(o.in_channels, o.out_channels, aggrs=o.aggregators, num_heads=o.num_heads,
                         num_bases=o.num_bases, add_self_loops=o.add_self_loops, bias=o.bias is not None,
                         sigmoid=o.sigmoid).to(dtype)
     od.load_state_dict({k: v.to(dtype) for k, v in o.state_dict().items()})
     xo = x.to(dtype).requires_grad_(True)
+    if not isinstance(graph_cpu, torch.Tensor) and graph_cpu[2] is not None:
+        graph_cpu = (graph_cpu[0], graph_cpu[1], graph_cpu[2].to(dtype))
     out_o = od(xo, graph_cpu)
     po = list(od.named_parameters())
     go = torch.autograd.grad(out_o, [xo] + [p for _, p in po], grad_out.to(dtype))
+    return out_o, po, go
+
+
+def run_both(o, c, x, graph_cpu, graph_gpu, grad_out):
+    """fp32 kernels on the GPU vs the oracle on the CPU.  Returns name -> (cuda, oracle fp64, oracle fp32):
+    the fp64 run is the truth, the fp32 run shows how much rounding noise the reference's own fp32
+    arithmetic carries on this input (std's var = E[x^2] - E[x]^2 cancels catastrophically, so its
+    gradient can be off by 1e-4 in fp32 on BOTH sides)."""
+    out_o, po, go = _oracle_run(o, x, graph_cpu, grad_out, torch.float64)
+    out_s, _, gs = _oracle_run(o, x, graph_cpu, grad_out, torch.float32)
     xc = x.to(DEV).requires_grad_(True)
     out_c = c(xc, graph_gpu)
     pc = dict(c.named_parameters())
     gc = torch.autograd.grad(out_c, [xc] + [pc[n] for n, _ in po], grad_out.to(DEV))
-    res = {"out": (out_c, out_o), "grad_x": (gc[0], go[0])}
-    for (n, _), a, bb in zip(po, gc[1:], go[1:]):
-        res["grad_" + n] = (a, bb)
+    res = {"out": (out_c, out_o, out_s), "grad_x": (gc[0], go[0], gs[0])}
+    for (n, _), a, bb, cc in zip(po, gc[1:], go[1:], gs[1:]):
+        res["grad_" + n] = (a, bb, cc)
     return res
 
 
-def assert_close(res, tol=TOL):
-    for k, (a, b) in res.items():
-        e = rel_err(a, b)
-        assert e < tol, f"{k}: relative error {e:.3e} >= {tol}"
+def tolerance(ref32, ref64):
+    """1e-5 relative, or twice the reference's own fp32-vs-fp64 rounding error where that is larger."""
+    return max(TOL, 2.0 * rel_err(ref32, ref64))
+
+
+def assert_close(res):
+    for k, (a, b64, b32) in res.items():
+        e, tol = rel_err(a, b64), tolerance(b32, b64)
+        assert e < tol, f"{k}: relative error {e:.3e} >= {tol:.3e}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,9 +196,9 @@ def test_degree_properties_full_arxiv_size():
         assert torch.equal(agg[:, k], torch.ones_like(agg[:, k]))
     assert float(agg[:, 5].abs().max()) == 0.0
     assert torch.allclose(agg[:, 6], torch.full_like(agg[:, 6], 1e-5 ** 0.5))
-    rowsum = torch.zeros(n, device=DEV).index_add_(0, torch.repeat_interleave(
-        torch.arange(n, device=DEV), (g.rowptr[1:] - g.rowptr[:-1]).long()), g.val_sym)
-    assert rel_err(agg[:, 2, 0], rowsum) < 1e-6
+    rowsum = torch.zeros(n, device=DEV, dtype=torch.float64).index_add_(0, torch.repeat_interleave(
+        torch.arange(n, device=DEV), (g.rowptr[1:] - g.rowptr[:-1]).long()), g.val_sym.double())
+    assert rel_err(agg[:, 2, 0], rowsum) < TOL
     # linearity of the sum aggregator at full size
     torch.manual_seed(0)
     xa, xb = torch.randn(n, 128, device=DEV), torch.randn(n, 128, device=DEV)
@@ -241,10 +257,10 @@ def test_layer_matches_reference_golden(name):
     out = c(x, gi)
     names = [n for n, _ in c.named_parameters()]
     grads = torch.autograd.grad(out, [x] + list(c.parameters()), rec["grad_out"].to(DEV))
-    assert rel_err(out, rec["out_f64"]) < TOL
-    assert rel_err(grads[0], rec["grad_x_f64"]) < TOL
+    assert rel_err(out, rec["out_f64"]) < tolerance(rec["out_f32"], rec["out_f64"])
+    assert rel_err(grads[0], rec["grad_x_f64"]) < tolerance(rec["grad_x_f32"], rec["grad_x_f64"])
     for pn, g in zip(names, grads[1:]):
-        assert rel_err(g, rec[f"grad_{pn}_f64"]) < TOL, pn
+        assert rel_err(g, rec[f"grad_{pn}_f64"]) < tolerance(rec[f"grad_{pn}_f32"], rec[f"grad_{pn}_f64"]), pn
 
 
 CONFIGS = [  # f_in, f_out, aggrs, heads, bases
@@ -294,7 +310,7 @@ def test_weighted_adjacency_without_symnorm():
     adj = egc_b200.SparseTensor(rowptr=rowptr.to(DEV), col=col.to(DEV), value=v.to(DEV), sparse_sizes=(n, n),
                                 is_sorted=True)
     torch.manual_seed(5)
-    assert_close(run_both(o, c, torch.randn(n, 24), (rowptr, col, v.double()), adj, torch.randn(n, 32)))
+    assert_close(run_both(o, c, torch.randn(n, 24), (rowptr, col, v), adj, torch.randn(n, 32)))
 
 
 def test_empty_and_tiny_graphs():
