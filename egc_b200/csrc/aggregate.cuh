@@ -6,6 +6,10 @@
 // 32*VEC floats the warp's 32/G groups walk different neighbours in parallel and are merged with
 // xor-shuffles at the end.  All requested aggregators are produced from ONE gather of each
 // neighbour row: primitives sum / symnorm-sum / sum of squares / max(+arg) / min(+arg).
+//
+// The gather loop is branch-free: a batch of kGatherUnroll neighbours is always issued; slots past
+// the end of the row re-read the row's last neighbour (harmless for max/min, which keep the first
+// winner) and carry weight 0 into the sums.
 #pragma once
 
 #include <float.h>
@@ -22,7 +26,7 @@ constexpr int kGatherUnroll = 8;      // independent 128-bit gathers in flight p
 constexpr float kStdEps = 1e-5f;      // ref optimized_layers.py:244,273
 
 struct AggParams {
-  // target-major CSR (or the CSC when used by the scatter pass)
+  // target-major CSR
   const int32_t* rowptr;
   const int32_t* col;
   const float* val_sym;
@@ -40,25 +44,23 @@ struct AggParams {
   const float* bases;        // [n_src, BD]
   const float* weightings;   // [n_rows, HAB]
   const float* bias;         // [HD] or null
-  float* out;                // [n_rows, HD]
-  float* agg_out;            // [n_rows, A, BD] or null
+  float* out;                // [n_rows, HD] or null
+  float* agg_out;            // [n_rows, A, BD] or null   (reference `aggregated`)
   int32_t* arg_out;          // [n_rows, A, BD] or null
-  // backward (pass 1)
-  const float* grad_out;     // [n_rows, HD]
-  float* d_weightings;       // [n_rows, HAB]
-  float* tstreams;           // [n_rows, n_ts, BD]
-  float* d_bases;            // [n_src, BD], pre-zeroed when min/max gradients are routed atomically
-  int n_ts, ts_sym, ts_lin, ts_sq;   // stream slots (-1: absent)
+  float* saved;              // [n_rows, S, BD] or null   (training: what the backward needs)
+  int32_t* saved_arg;        // [n_rows, n_arg, BD] or null
+  int n_saved, n_arg;        // S = A (+1 mean slot when var/std present); n_arg = # of min/max slots
   // shape
   int H, B, D, A, BD, HD, AB, HAB;
   int aggr[EGC_MAX_AGGR];
+  int arg_slot[EGC_MAX_AGGR];   // index into saved_arg for min/max aggregators, else -1
   int sigmoid;
   // lane geometry
   int nvec;      // VEC-wide pieces per basis row
   int G;         // lanes per group (power of two, <= 32)
   int n_pass;    // passes of 32 pieces when nvec > 32
   // per-warp shared memory layout (float offsets)
-  int sm_agg, sm_w, sm_g, sm_mean, sm_var, sm_amx, sm_amn, sm_per_warp;
+  int sm_agg, sm_w, sm_per_warp;
   int mode;      // 0: chunk tasks then row tasks, 1: merge tasks (one per long row)
 };
 
@@ -97,16 +99,31 @@ __device__ __forceinline__ void st_row(float* p, const float (&v)[VEC]) {
   }
 }
 
-__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src) {
+// streaming (evict-first) store: outputs that are not re-read by this kernel
+template <int VEC>
+__device__ __forceinline__ void st_stream(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) __stcs(p + k, v[k]);
+  }
+}
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
   unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // accumulator of the aggregation primitives for VEC features
 // ---------------------------------------------------------------------------------------------
-template <int MASK, int VEC, bool LINW>
+template <int MASK, int VEC, bool LINW, bool ARG>
 struct Acc {
   float sum[VEC], sym[VEC], sq[VEC], mx[VEC], mn[VEC];
   int amx[VEC], amn[VEC];
@@ -120,30 +137,46 @@ struct Acc {
     }
   }
 
-  // one neighbour; e = nnz position (for first-wins arg tracking).  Products and sums are rounded
-  // separately (no FMA contraction) so a sequential walk reproduces the reference's fp32 results.
-  __device__ __forceinline__ void add(const float (&x)[VEC], float vs, float vl, int e) {
+  // One neighbour.  m = 1 for a real neighbour, 0 for a padding slot (which re-reads the last real one);
+  // vs = its symnorm weight (0 for padding); vl = its linear weight (LINW only); e = nnz position.
+  // Products and sums are rounded separately (no FMA contraction of x*w + s), so a sequential walk
+  // reproduces the reference's fp32 results bit for bit.
+  __device__ __forceinline__ void add(const float (&x)[VEC], float m, float vs, float vl, int e) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const float xl = LINW ? __fmul_rn(x[k], vl) : x[k];
-      if constexpr (MASK & P_SUM) sum[k] = __fadd_rn(sum[k], xl);
-      if constexpr (MASK & P_SYM) sym[k] = __fadd_rn(sym[k], __fmul_rn(x[k], vs));
+      const float msg = LINW ? __fmul_rn(x[k], vl) : x[k];          // message seen by sum/mean/min/max/var
+      if constexpr (MASK & P_SUM) sum[k] = fmaf(msg, m, sum[k]);     // exact: m is 0 or 1
       if constexpr (MASK & P_SQ) {
         float s = __fmul_rn(x[k], x[k]);
         if (LINW) s = __fmul_rn(s, vl);
-        sq[k] = __fadd_rn(sq[k], s);
+        sq[k] = fmaf(s, m, sq[k]);
       }
-      if constexpr (MASK & P_MAX) { if (xl > mx[k]) { mx[k] = xl; amx[k] = e; } }
-      if constexpr (MASK & P_MIN) { if (xl < mn[k]) { mn[k] = xl; amn[k] = e; } }
+      if constexpr (MASK & P_SYM) sym[k] = __fadd_rn(sym[k], __fmul_rn(x[k], vs));
+      if constexpr (MASK & P_MAX) {
+        if constexpr (ARG) { if (msg > mx[k]) { mx[k] = msg; amx[k] = e; } }
+        else mx[k] = fmaxf(mx[k], msg);
+      }
+      if constexpr (MASK & P_MIN) {
+        if constexpr (ARG) { if (msg < mn[k]) { mn[k] = msg; amn[k] = e; } }
+        else mn[k] = fminf(mn[k], msg);
+      }
     }
   }
 
   // ties between partial results: the smaller nnz position wins (-1 = empty compares as +inf)
   __device__ __forceinline__ void merge_max(int k, float o, int oa) {
-    if (o > mx[k] || (o == mx[k] && static_cast<unsigned>(oa) < static_cast<unsigned>(amx[k]))) { mx[k] = o; amx[k] = oa; }
+    if constexpr (ARG) {
+      if (o > mx[k] || (o == mx[k] && static_cast<unsigned>(oa) < static_cast<unsigned>(amx[k]))) { mx[k] = o; amx[k] = oa; }
+    } else {
+      mx[k] = fmaxf(mx[k], o);
+    }
   }
   __device__ __forceinline__ void merge_min(int k, float o, int oa) {
-    if (o < mn[k] || (o == mn[k] && static_cast<unsigned>(oa) < static_cast<unsigned>(amn[k]))) { mn[k] = o; amn[k] = oa; }
+    if constexpr (ARG) {
+      if (o < mn[k] || (o == mn[k] && static_cast<unsigned>(oa) < static_cast<unsigned>(amn[k]))) { mn[k] = o; amn[k] = oa; }
+    } else {
+      mn[k] = fminf(mn[k], o);
+    }
   }
 
   __device__ __forceinline__ void merge_xor(int off) {
@@ -154,23 +187,19 @@ struct Acc {
       if constexpr (MASK & P_SQ) sq[k] = __fadd_rn(sq[k], __shfl_xor_sync(kFull, sq[k], off));
       if constexpr (MASK & P_MAX) {
         float o = __shfl_xor_sync(kFull, mx[k], off);
-        int oa = __shfl_xor_sync(kFull, amx[k], off);
+        int oa = ARG ? __shfl_xor_sync(kFull, amx[k], off) : 0;
         merge_max(k, o, oa);
       }
       if constexpr (MASK & P_MIN) {
         float o = __shfl_xor_sync(kFull, mn[k], off);
-        int oa = __shfl_xor_sync(kFull, amn[k], off);
+        int oa = ARG ? __shfl_xor_sync(kFull, amn[k], off) : 0;
         merge_min(k, o, oa);
       }
     }
   }
 
-  static constexpr int n_slots() {
-    return ((MASK & P_SUM) ? 1 : 0) + ((MASK & P_SYM) ? 1 : 0) + ((MASK & P_SQ) ? 1 : 0) +
-           ((MASK & P_MAX) ? 2 : 0) + ((MASK & P_MIN) ? 2 : 0);
-  }
-
-  // partial <-> scratch; `p` points at slot 0 of this lane's features, slots are BD floats apart
+  // partial <-> scratch; `p` points at slot 0 of this lane's features, slots are BD floats apart.
+  // Slot order: SUM, SYM, SQ, MAX, AMAX, MIN, AMIN (arg slots always reserved, see n_slots_of_mask).
   __device__ __forceinline__ void store(float* p, int BD) const {
     int s = 0;
     if constexpr (MASK & P_SUM) { st_row<VEC>(p + s * BD, sum); ++s; }
@@ -178,17 +207,23 @@ struct Acc {
     if constexpr (MASK & P_SQ) { st_row<VEC>(p + s * BD, sq); ++s; }
     if constexpr (MASK & P_MAX) {
       st_row<VEC>(p + s * BD, mx); ++s;
-      float t[VEC];
+      if constexpr (ARG) {
+        float t[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) t[k] = __int_as_float(amx[k]);
-      st_row<VEC>(p + s * BD, t); ++s;
+        for (int k = 0; k < VEC; ++k) t[k] = __int_as_float(amx[k]);
+        st_row<VEC>(p + s * BD, t);
+      }
+      ++s;
     }
     if constexpr (MASK & P_MIN) {
       st_row<VEC>(p + s * BD, mn); ++s;
-      float t[VEC];
+      if constexpr (ARG) {
+        float t[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) t[k] = __int_as_float(amn[k]);
-      st_row<VEC>(p + s * BD, t); ++s;
+        for (int k = 0; k < VEC; ++k) t[k] = __int_as_float(amn[k]);
+        st_row<VEC>(p + s * BD, t);
+      }
+      ++s;
     }
   }
 
@@ -212,13 +247,19 @@ struct Acc {
     }
     if constexpr (MASK & P_MAX) {
       ld_plain<VEC>(t, p + s * BD); ++s;
-      ld_plain<VEC>(u, p + s * BD); ++s;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) u[k] = 0.f;
+      if constexpr (ARG) ld_plain<VEC>(u, p + s * BD);
+      ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) merge_max(k, t[k], __float_as_int(u[k]));
     }
     if constexpr (MASK & P_MIN) {
       ld_plain<VEC>(t, p + s * BD); ++s;
-      ld_plain<VEC>(u, p + s * BD); ++s;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) u[k] = 0.f;
+      if constexpr (ARG) ld_plain<VEC>(u, p + s * BD);
+      ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) merge_min(k, t[k], __float_as_int(u[k]));
     }
@@ -227,47 +268,41 @@ struct Acc {
 
 // ---------------------------------------------------------------------------------------------
 // walk nnz [begin, end) of one row; lanes of group g = lane / G take neighbours g, g + NG, ...
+// `foff` must be a valid feature offset for every lane (inactive lanes are clamped by the caller).
 // ---------------------------------------------------------------------------------------------
-template <int MASK, int VEC, bool LINW>
-__device__ __forceinline__ void accumulate_range(Acc<MASK, VEC, LINW>& acc, const AggParams& p, int begin, int end,
-                                                 int lane, int foff, bool active) {
+template <int MASK, int VEC, bool LINW, bool ARG>
+__device__ __forceinline__ void accumulate_range(Acc<MASK, VEC, LINW, ARG>& acc, const AggParams& p, int begin,
+                                                 int end, int lane, int foff) {
   const int G = p.G, NG = 32 / G, g = lane / G;
   const float* __restrict__ src = p.bases + foff;
-  for (int e0 = begin; e0 < end; e0 += 32) {
-    const int n_here = min(32, end - e0);
-    const bool have = lane < n_here;
-    const int my_col = have ? __ldg(p.col + e0 + lane) : 0;
-    float my_vs = 0.f, my_vl = 0.f;
-    if constexpr (MASK & P_SYM) my_vs = have ? __ldg(p.val_sym + e0 + lane) : 0.f;
-    if constexpr (LINW) my_vl = have ? __ldg(p.val_lin + e0 + lane) : 0.f;
-    const int steps = (n_here + NG - 1) / NG;
-    for (int s = 0; s < steps; s += kGatherUnroll) {
-      float x[kGatherUnroll][VEC];
-      bool ok[kGatherUnroll];
+  const int64_t stride = p.BD;
+  const int last = end - 1;
+  for (int e0 = begin + g; e0 < end + g; e0 += kGatherUnroll * NG) {   // e0 - g is warp-uniform
+    int ec[kGatherUnroll], j[kGatherUnroll];
+    float m[kGatherUnroll], vs[kGatherUnroll], vl[kGatherUnroll];
 #pragma unroll
-      for (int u = 0; u < kGatherUnroll; ++u) {
-        const int idx = (s + u) * NG + g;
-        const int j = __shfl_sync(kFull, my_col, idx & 31);
-        ok[u] = active && (s + u) < steps && idx < n_here;
-        if (ok[u]) ld_row<VEC>(x[u], src + static_cast<int64_t>(j) * p.BD);
-      }
-#pragma unroll
-      for (int u = 0; u < kGatherUnroll; ++u) {
-        const int idx = (s + u) * NG + g;
-        float vs = 0.f, vl = 0.f;
-        if constexpr (MASK & P_SYM) vs = __shfl_sync(kFull, my_vs, idx & 31);
-        if constexpr (LINW) vl = __shfl_sync(kFull, my_vl, idx & 31);
-        if (ok[u]) acc.add(x[u], vs, vl, e0 + idx);
-      }
+    for (int u = 0; u < kGatherUnroll; ++u) {
+      const int e = e0 + u * NG;
+      ec[u] = min(e, last);
+      m[u] = e <= last ? 1.f : 0.f;
+      j[u] = __ldg(p.col + ec[u]);
+      vs[u] = 0.f; vl[u] = 1.f;
+      if constexpr (MASK & P_SYM) vs[u] = e <= last ? __ldg(p.val_sym + ec[u]) : 0.f;
+      if constexpr (LINW) vl[u] = __ldg(p.val_lin + ec[u]);
     }
+    float x[kGatherUnroll][VEC];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) ld_row<VEC>(x[u], src + j[u] * stride);
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u) acc.add(x[u], m[u], vs[u], vl[u], ec[u]);
   }
   for (int off = G; off < 32; off <<= 1) acc.merge_xor(off);
 }
 
 // value of aggregator `code` for feature k of this lane, from the primitives
-template <int MASK, int VEC, bool LINW>
-__device__ __forceinline__ float finalize_one(const Acc<MASK, VEC, LINW>& acc, int code, int k, float cntf,
-                                              float& mean_out, float& var_out) {
+template <int MASK, int VEC, bool LINW, bool ARG>
+__device__ __forceinline__ float finalize_one(const Acc<MASK, VEC, LINW, ARG>& acc, int code, int k, float cntf,
+                                              bool nonempty, float& mean_out, float& var_out) {
   switch (code) {
     case EGC_AGGR_SUM:
       if constexpr (MASK & P_SUM) return acc.sum[k];
@@ -279,10 +314,10 @@ __device__ __forceinline__ float finalize_one(const Acc<MASK, VEC, LINW>& acc, i
       if constexpr (MASK & P_SYM) return acc.sym[k];
       break;
     case EGC_AGGR_MAX:
-      if constexpr (MASK & P_MAX) return acc.amx[k] >= 0 ? acc.mx[k] : 0.f;
+      if constexpr (MASK & P_MAX) return nonempty ? acc.mx[k] : 0.f;     // empty row -> 0
       break;
     case EGC_AGGR_MIN:
-      if constexpr (MASK & P_MIN) return acc.amn[k] >= 0 ? acc.mn[k] : 0.f;
+      if constexpr (MASK & P_MIN) return nonempty ? acc.mn[k] : 0.f;
       break;
     case EGC_AGGR_VAR:
     case EGC_AGGR_STD:
@@ -320,13 +355,23 @@ inline int n_slots_of_mask(int m) {
          ((m & P_MIN) ? 2 : 0);
 }
 
-// host: fill shape / geometry / smem layout fields; returns dynamic smem bytes per CTA
-int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4, bool bwd);
+inline bool has_var_like(const egc_layer_desc& d) {
+  for (int a = 0; a < d.n_aggr; ++a)
+    if (d.aggr[a] == EGC_AGGR_VAR || d.aggr[a] == EGC_AGGR_STD) return true;
+  return false;
+}
+inline int n_arg_slots(const egc_layer_desc& d) {
+  int n = 0;
+  for (int a = 0; a < d.n_aggr; ++a) n += (d.aggr[a] == EGC_AGGR_MAX || d.aggr[a] == EGC_AGGR_MIN) ? 1 : 0;
+  return n;
+}
+inline int n_saved_slots(const egc_layer_desc& d) { return d.n_aggr + (has_var_like(d) ? 1 : 0); }
 
-// launchers (one translation unit per VEC/BWD combination to keep compile times parallel)
-int launch_aggregate_fwd_v4(const AggParams& p, int mask, bool linw, int smem_bytes, cudaStream_t st);
-int launch_aggregate_fwd_v1(const AggParams& p, int mask, bool linw, int smem_bytes, cudaStream_t st);
-int launch_aggregate_bwd_v4(const AggParams& p, int mask, bool linw, int smem_bytes, cudaStream_t st);
-int launch_aggregate_bwd_v1(const AggParams& p, int mask, bool linw, int smem_bytes, cudaStream_t st);
+// host: fill shape / geometry / smem layout fields; returns dynamic smem bytes per CTA
+int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4);
+
+// launchers (one translation unit per VEC/ARG combination to keep compile times parallel)
+int launch_aggregate_v4(const AggParams& p, int mask, bool linw, bool arg, int smem_bytes, cudaStream_t st);
+int launch_aggregate_v1(const AggParams& p, int mask, bool linw, bool arg, int smem_bytes, cudaStream_t st);
 
 }  // namespace egc

@@ -1,5 +1,6 @@
-// extern "C" entry points of the fused aggregation forward / backward, the source-side (CSC)
-// backward pass and the column-sum helper.
+// extern "C" entry points of the fused aggregation forward / backward, plus the two backward
+// kernels: the per-target streaming pass (gradient of the combination, target-side streams,
+// min/max routing) and the per-source CSC gather pass (atomic-free d_bases).
 #include <algorithm>
 
 #include "aggregate.cuh"
@@ -7,10 +8,16 @@
 
 namespace egc {
 
-int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4, bool bwd) {
+int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4) {
   p.H = d.heads; p.B = d.bases; p.D = d.dim; p.A = d.n_aggr;
   p.BD = d.bases * d.dim; p.HD = d.heads * d.dim; p.AB = d.n_aggr * d.bases; p.HAB = d.heads * p.AB;
-  for (int a = 0; a < EGC_MAX_AGGR; ++a) p.aggr[a] = a < d.n_aggr ? d.aggr[a] : -1;
+  int n_arg = 0;
+  for (int a = 0; a < EGC_MAX_AGGR; ++a) {
+    p.aggr[a] = a < d.n_aggr ? d.aggr[a] : -1;
+    p.arg_slot[a] = (a < d.n_aggr && (d.aggr[a] == EGC_AGGR_MAX || d.aggr[a] == EGC_AGGR_MIN)) ? n_arg++ : -1;
+  }
+  p.n_arg = n_arg;
+  p.n_saved = n_saved_slots(d);
   p.sigmoid = d.sigmoid;
   const int vec = vec4 ? 4 : 1;
   p.nvec = (p.BD + vec - 1) / vec;
@@ -22,14 +29,6 @@ int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4, bool bwd) 
   int off = 0;
   p.sm_agg = off; off = a4(off + p.A * p.BD);
   p.sm_w = off; off = a4(off + p.HAB);
-  p.sm_g = p.sm_mean = p.sm_var = p.sm_amx = p.sm_amn = 0;
-  if (bwd) {
-    p.sm_g = off; off = a4(off + p.HD);
-    p.sm_mean = off; off = a4(off + p.BD);
-    p.sm_var = off; off = a4(off + p.BD);
-    p.sm_amx = off; off = a4(off + p.BD);
-    p.sm_amn = off; off = a4(off + p.BD);
-  }
   p.sm_per_warp = off;
   return off * kAggWarps * static_cast<int>(sizeof(float));
 }
@@ -62,9 +61,160 @@ static int validate_plan(const egc_row_plan* plan, const char* who) {
   return EGC_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// source-side (CSC) backward pass: d_bases[j] = sum over column j of the target-side streams
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
+// backward pass 1: per target node, streaming (no graph traversal)
+//   d_w[h,ab]   = sum_d g[h*D+d] * agg[ab*D+d]                       (x sigmoid' when requested)
+//   d_agg[a][p] = sum_h w[h*AB + a*B + b(p)] * g[h*D + d(p)]
+//   -> target-side streams t_sym / t_lin / t_sq (read by pass 2) + single-winner routing of min/max
+// `saved` comes from the forward: per aggregator slot its value (std slots carry the closed relu gate
+// in the sign bit), plus one extra slot with the mean when var/std is present; `saved_arg` holds the
+// winning nnz position of every min/max slot.
+// =============================================================================================
+struct CombineBwdParams {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val_lin;
+  int n_rows;
+  const float* weightings;
+  const float* grad_out;
+  const float* saved;
+  const int32_t* saved_arg;
+  float* d_weightings;
+  float* tstreams;
+  float* d_bases;
+  int n_saved, n_arg, n_ts, ts_sym, ts_lin, ts_sq;
+  int H, B, D, A, BD, HD, AB, HAB;
+  int aggr[EGC_MAX_AGGR];
+  int arg_slot[EGC_MAX_AGGR];
+  int sigmoid;
+  int sm_w, sm_g, sm_saved, sm_arg, sm_per_warp;
+  int vec16;
+};
+
+__device__ __forceinline__ void stage_row(float* dst, const float* src, int n, int lane, bool vec16) {
+  if (vec16) {
+    for (int t = lane * 4; t < n; t += 128) cp_async_16(dst + t, src + t);
+  } else {
+    for (int t = lane; t < n; t += 32) cp_async_4(dst + t, src + t);
+  }
+}
+
+template <int EV, bool LINW>
+__global__ void __launch_bounds__(kAggThreads) k_combine_bwd(const __grid_constant__ CombineBwdParams p) {
+  extern __shared__ __align__(16) float smem_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kAggWarps + warp;
+  if (row >= p.n_rows) return;
+  float* sm = smem_all + warp * p.sm_per_warp;
+  const int D = p.D;
+  const bool v16 = p.vec16 != 0;
+  stage_row(sm + p.sm_w, p.weightings + static_cast<int64_t>(row) * p.HAB, p.HAB, lane, v16);
+  stage_row(sm + p.sm_g, p.grad_out + static_cast<int64_t>(row) * p.HD, p.HD, lane, v16);
+  stage_row(sm + p.sm_saved, p.saved + static_cast<int64_t>(row) * p.n_saved * p.BD, p.n_saved * p.BD, lane, v16);
+  if (p.n_arg > 0)
+    stage_row(sm + p.sm_arg, reinterpret_cast<const float*>(p.saved_arg) + static_cast<int64_t>(row) * p.n_arg * p.BD,
+              p.n_arg * p.BD, lane, v16);
+  const float cntf = static_cast<float>(max(p.rowptr[row + 1] - p.rowptr[row], 1));
+  cp_async_wait_all();
+  __syncwarp();
+
+  const float* w = sm + p.sm_w;
+  const float* g = sm + p.sm_g;
+  const float* sv = sm + p.sm_saved;
+  const int* sarg = reinterpret_cast<const int*>(sm + p.sm_arg);
+
+  // (1) gradient of the combination weights: HAB dot products of length D, skewed start per lane
+  for (int t = lane; t < p.HAB; t += 32) {
+    const int h = t / p.AB, ab = t - h * p.AB;
+    const bool is_std = p.aggr[ab / p.B] == EGC_AGGR_STD;
+    const float* gh = g + h * D;
+    const float* aa = sv + ab * D;
+    float dot = 0.f;
+    if constexpr (EV == 4) {
+      const int nq = D >> 2;
+      int q = lane % nq;
+      for (int i = 0; i < nq; ++i) {
+        const float4 gv = *reinterpret_cast<const float4*>(gh + 4 * q);
+        float4 av = *reinterpret_cast<const float4*>(aa + 4 * q);
+        if (is_std) { av.x = fabsf(av.x); av.y = fabsf(av.y); av.z = fabsf(av.z); av.w = fabsf(av.w); }
+        dot = fmaf(gv.x, av.x, dot); dot = fmaf(gv.y, av.y, dot); dot = fmaf(gv.z, av.z, dot); dot = fmaf(gv.w, av.w, dot);
+        q = (q + 1 == nq) ? 0 : q + 1;
+      }
+    } else {
+      int dd = lane % D;
+      for (int i = 0; i < D; ++i) {
+        const float av = is_std ? fabsf(aa[dd]) : aa[dd];
+        dot = fmaf(gh[dd], av, dot);
+        dd = (dd + 1 == D) ? 0 : dd + 1;
+      }
+    }
+    if (p.sigmoid) { const float s = w[t]; dot *= s * (1.f - s); }
+    p.d_weightings[static_cast<int64_t>(row) * p.HAB + t] = dot;
+  }
+
+  // (2) gradient w.r.t. the aggregates -> target-side streams and min/max routing
+  float* ts = p.tstreams + static_cast<int64_t>(row) * p.n_ts * p.BD;
+  for (int p0 = lane * EV; p0 < p.BD; p0 += 32 * EV) {
+    const int b = p0 / D, d = p0 - b * D;
+    float t_sym[EV], t_lin[EV], t_sq[EV];
+#pragma unroll
+    for (int k = 0; k < EV; ++k) { t_sym[k] = 0.f; t_lin[k] = 0.f; t_sq[k] = 0.f; }
+    for (int a = 0; a < p.A; ++a) {
+      float da[EV];
+#pragma unroll
+      for (int k = 0; k < EV; ++k) da[k] = 0.f;
+      const float* wa = w + a * p.B + b;
+      for (int h = 0; h < p.H; ++h) {
+        const float wv = wa[h * p.AB];
+        float gv[EV];
+        ld_plain<EV>(gv, g + h * D + d);
+#pragma unroll
+        for (int k = 0; k < EV; ++k) da[k] = fmaf(wv, gv[k], da[k]);
+      }
+      const int code = p.aggr[a];
+      if (code == EGC_AGGR_SUM) {
+#pragma unroll
+        for (int k = 0; k < EV; ++k) t_lin[k] += da[k];
+      } else if (code == EGC_AGGR_MEAN) {
+#pragma unroll
+        for (int k = 0; k < EV; ++k) t_lin[k] += __fdiv_rn(da[k], cntf);
+      } else if (code == EGC_AGGR_SYMNORM) {
+#pragma unroll
+        for (int k = 0; k < EV; ++k) t_sym[k] += da[k];
+      } else if (code == EGC_AGGR_MAX || code == EGC_AGGR_MIN) {
+        const int* args = sarg + p.arg_slot[a] * p.BD + p0;
+#pragma unroll
+        for (int k = 0; k < EV; ++k) {
+          const int arg = args[k];
+          if (arg >= 0) {
+            float v = da[k];
+            if (LINW) v *= __ldg(p.val_lin + arg);
+            atomicAdd(p.d_bases + static_cast<int64_t>(__ldg(p.col + arg)) * p.BD + p0 + k, v);
+          }
+        }
+      } else {   // VAR / STD
+        float sa[EV], mean[EV];
+        ld_plain<EV>(sa, sv + a * p.BD + p0);
+        ld_plain<EV>(mean, sv + p.A * p.BD + p0);
+#pragma unroll
+        for (int k = 0; k < EV; ++k) {
+          float dv = da[k];
+          if (code == EGC_AGGR_STD) dv = sa[k] > 0.f ? dv / (2.f * sa[k]) : 0.f;    // relu gate (sign bit), d sqrt
+          const float q = __fdiv_rn(dv, cntf);
+          t_sq[k] += q;
+          t_lin[k] -= 2.f * mean[k] * q;
+        }
+      }
+    }
+    if (p.ts_sym >= 0) st_row<EV>(ts + p.ts_sym * p.BD + p0, t_sym);
+    if (p.ts_lin >= 0) st_row<EV>(ts + p.ts_lin * p.BD + p0, t_lin);
+    if (p.ts_sq >= 0) st_row<EV>(ts + p.ts_sq * p.BD + p0, t_sq);
+  }
+}
+
+// =============================================================================================
+// backward pass 2: per source column (CSC), gather of the target-side streams, atomic-free
+// =============================================================================================
 struct ScatterParams {
   const int32_t* colptr;
   const int32_t* rowidx;
@@ -89,7 +239,7 @@ struct ScatterParams {
 constexpr int kScatterUnroll = 4;
 
 template <int TSMASK, int VEC, bool LINW>
-__global__ void __launch_bounds__(kAggThreads) k_scatter_bwd(const __grid_constant__ ScatterParams p) {
+__global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_constant__ ScatterParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kAggWarps + warp;
   int colj, begin, end, chunk_id = -1, long_idx = -1;
@@ -119,75 +269,72 @@ __global__ void __launch_bounds__(kAggThreads) k_scatter_bwd(const __grid_consta
   for (int pass = 0; pass < p.n_pass; ++pass) {
     const int piece = pass * 32 + (lane & (G - 1));
     const bool active = piece < p.nvec;
-    const int foff = piece * VEC;
+    const int foff = min(piece, p.nvec - 1) * VEC;
     float a_sym[VEC], a_lin[VEC], a_sq[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
 
     if (p.mode == 0) {
       const float* __restrict__ src = p.tstreams + foff;
-      for (int e0 = begin; e0 < end; e0 += 32) {
-        const int n_here = min(32, end - e0);
-        const bool have = lane < n_here;
-        const int my_row = have ? __ldg(p.rowidx + e0 + lane) : 0;
-        float my_vs = 0.f, my_vl = 0.f;
-        if constexpr (TSMASK & 1) my_vs = have ? __ldg(p.val_sym + e0 + lane) : 0.f;
-        if constexpr (LINW) my_vl = have ? __ldg(p.val_lin + e0 + lane) : 0.f;
-        const int steps = (n_here + NG - 1) / NG;
-        for (int s = 0; s < steps; s += kScatterUnroll) {
-          float xs[kScatterUnroll][VEC], xl[kScatterUnroll][VEC], xq[kScatterUnroll][VEC];
-          bool ok[kScatterUnroll];
+      const int last = end - 1;
+      for (int e0 = begin + g; e0 < end + g; e0 += kScatterUnroll * NG) {
+        int i[kScatterUnroll];
+        float m[kScatterUnroll], vs[kScatterUnroll];
 #pragma unroll
-          for (int u = 0; u < kScatterUnroll; ++u) {
-            const int idx = (s + u) * NG + g;
-            const int i = __shfl_sync(kFull, my_row, idx & 31);
-            ok[u] = active && (s + u) < steps && idx < n_here;
-            if (ok[u]) {
-              const float* r = src + static_cast<int64_t>(i) * row_stride;
-              if constexpr (TSMASK & 1) ld_row<VEC>(xs[u], r + p.ts_sym * p.BD);
-              if constexpr (TSMASK & 2) ld_row<VEC>(xl[u], r + p.ts_lin * p.BD);
-              if constexpr (TSMASK & 4) ld_row<VEC>(xq[u], r + p.ts_sq * p.BD);
-            }
-          }
+        for (int u = 0; u < kScatterUnroll; ++u) {
+          const int e = e0 + u * NG, ec = min(e, last);
+          i[u] = __ldg(p.rowidx + ec);
+          m[u] = e <= last ? 1.f : 0.f;
+          if constexpr (LINW) m[u] *= __ldg(p.val_lin + ec);
+          vs[u] = 0.f;
+          if constexpr ((TSMASK & 1) != 0) vs[u] = e <= last ? __ldg(p.val_sym + ec) : 0.f;
+        }
+        float xs[kScatterUnroll][VEC], xl[kScatterUnroll][VEC], xq[kScatterUnroll][VEC];
 #pragma unroll
-          for (int u = 0; u < kScatterUnroll; ++u) {
-            const int idx = (s + u) * NG + g;
-            float vs = 0.f, vl = 1.f;
-            if constexpr (TSMASK & 1) vs = __shfl_sync(kFull, my_vs, idx & 31);
-            if constexpr (LINW) vl = __shfl_sync(kFull, my_vl, idx & 31);
-            if (ok[u]) {
+        for (int u = 0; u < kScatterUnroll; ++u) {
+          const float* r = src + i[u] * row_stride;
+          if constexpr ((TSMASK & 1) != 0) ld_row<VEC>(xs[u], r + p.ts_sym * p.BD);
+          if constexpr ((TSMASK & 2) != 0) ld_row<VEC>(xl[u], r + p.ts_lin * p.BD);
+          if constexpr ((TSMASK & 4) != 0) ld_row<VEC>(xq[u], r + p.ts_sq * p.BD);
+        }
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                if constexpr (TSMASK & 1) a_sym[k] = __fadd_rn(a_sym[k], __fmul_rn(xs[u][k], vs));
-                if constexpr (TSMASK & 2) a_lin[k] = __fadd_rn(a_lin[k], LINW ? __fmul_rn(xl[u][k], vl) : xl[u][k]);
-                if constexpr (TSMASK & 4) a_sq[k] = __fadd_rn(a_sq[k], LINW ? __fmul_rn(xq[u][k], vl) : xq[u][k]);
-              }
-            }
+        for (int u = 0; u < kScatterUnroll; ++u) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            if constexpr ((TSMASK & 1) != 0) a_sym[k] = __fadd_rn(a_sym[k], __fmul_rn(xs[u][k], vs[u]));
+            if constexpr ((TSMASK & 2) != 0) a_lin[k] = fmaf(xl[u][k], m[u], a_lin[k]);
+            if constexpr ((TSMASK & 4) != 0) a_sq[k] = fmaf(xq[u][k], m[u], a_sq[k]);
           }
         }
       }
       for (int off = G; off < 32; off <<= 1) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          if constexpr (TSMASK & 1) a_sym[k] += __shfl_xor_sync(kFull, a_sym[k], off);
-          if constexpr (TSMASK & 2) a_lin[k] += __shfl_xor_sync(kFull, a_lin[k], off);
-          if constexpr (TSMASK & 4) a_sq[k] += __shfl_xor_sync(kFull, a_sq[k], off);
+          if constexpr ((TSMASK & 1) != 0) a_sym[k] += __shfl_xor_sync(kFull, a_sym[k], off);
+          if constexpr ((TSMASK & 2) != 0) a_lin[k] += __shfl_xor_sync(kFull, a_lin[k], off);
+          if constexpr ((TSMASK & 4) != 0) a_sq[k] += __shfl_xor_sync(kFull, a_sq[k], off);
         }
       }
-    } else if (active) {
+    } else {
       const int c0 = p.long_chunk_ptr[long_idx], c1 = p.long_chunk_ptr[long_idx + 1];
       for (int c = c0; c < c1; ++c) {
         const float* q = p.partials + static_cast<int64_t>(c) * row_stride + foff;
         float t[VEC];
-        if constexpr (TSMASK & 1) { ld_plain<VEC>(t, q + p.ts_sym * p.BD);
+        if constexpr ((TSMASK & 1) != 0) {
+          ld_plain<VEC>(t, q + p.ts_sym * p.BD);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) a_sym[k] += t[k]; }
-        if constexpr (TSMASK & 2) { ld_plain<VEC>(t, q + p.ts_lin * p.BD);
+          for (int k = 0; k < VEC; ++k) a_sym[k] += t[k];
+        }
+        if constexpr ((TSMASK & 2) != 0) {
+          ld_plain<VEC>(t, q + p.ts_lin * p.BD);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) a_lin[k] += t[k]; }
-        if constexpr (TSMASK & 4) { ld_plain<VEC>(t, q + p.ts_sq * p.BD);
+          for (int k = 0; k < VEC; ++k) a_lin[k] += t[k];
+        }
+        if constexpr ((TSMASK & 4) != 0) {
+          ld_plain<VEC>(t, q + p.ts_sq * p.BD);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) a_sq[k] += t[k]; }
+          for (int k = 0; k < VEC; ++k) a_sq[k] += t[k];
+        }
       }
     }
 
@@ -195,9 +342,9 @@ __global__ void __launch_bounds__(kAggThreads) k_scatter_bwd(const __grid_consta
     if (!writer) continue;
     if (chunk_id >= 0) {
       float* q = p.partials + static_cast<int64_t>(chunk_id) * row_stride + foff;
-      if constexpr (TSMASK & 1) st_row<VEC>(q + p.ts_sym * p.BD, a_sym);
-      if constexpr (TSMASK & 2) st_row<VEC>(q + p.ts_lin * p.BD, a_lin);
-      if constexpr (TSMASK & 4) st_row<VEC>(q + p.ts_sq * p.BD, a_sq);
+      if constexpr ((TSMASK & 1) != 0) st_row<VEC>(q + p.ts_sym * p.BD, a_sym);
+      if constexpr ((TSMASK & 2) != 0) st_row<VEC>(q + p.ts_lin * p.BD, a_lin);
+      if constexpr ((TSMASK & 4) != 0) st_row<VEC>(q + p.ts_sq * p.BD, a_sq);
       continue;
     }
     float* dst = p.d_bases + static_cast<int64_t>(colj) * p.BD + foff;
@@ -205,7 +352,7 @@ __global__ void __launch_bounds__(kAggThreads) k_scatter_bwd(const __grid_consta
 #pragma unroll
     for (int k = 0; k < VEC; ++k) r[k] = 0.f;
     if (p.routed) ld_plain<VEC>(r, dst);
-    if constexpr (TSMASK & 4) {
+    if constexpr ((TSMASK & 4) != 0) {
       float xj[VEC];
       ld_row<VEC>(xj, p.bases + static_cast<int64_t>(colj) * p.BD + foff);
 #pragma unroll
@@ -213,8 +360,8 @@ __global__ void __launch_bounds__(kAggThreads) k_scatter_bwd(const __grid_consta
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      if constexpr (TSMASK & 1) r[k] += a_sym[k];
-      if constexpr (TSMASK & 2) r[k] += a_lin[k];
+      if constexpr ((TSMASK & 1) != 0) r[k] += a_sym[k];
+      if constexpr ((TSMASK & 2) != 0) r[k] += a_lin[k];
     }
     st_row<VEC>(dst, r);
   }
@@ -268,12 +415,12 @@ static int stream_mask_of(const egc_layer_desc& d, bool& has_route) {
 }
 
 struct BwdLayout {
-  size_t ts_bytes, csr_part_bytes, csc_part_bytes, colsum_bytes, total;
+  size_t ts_bytes, csc_part_bytes, colsum_bytes, total;
   int n_ts, ts_sym, ts_lin, ts_sq, tsmask;
   bool has_route;
 };
 
-static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csr_plan, const egc_row_plan* csc_plan) {
+static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_plan) {
   BwdLayout L{};
   L.tsmask = stream_mask_of(d, L.has_route);
   int s = 0;
@@ -283,11 +430,9 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csr_pla
   L.n_ts = s;
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
-  const int mask = prim_mask_of(d);
-  L.csr_part_bytes = align_up(static_cast<size_t>(csr_plan ? csr_plan->n_chunks : 0) * n_slots_of_mask(mask) * bd * 4, 256);
   L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256);
   L.colsum_bytes = align_up(colsum_workspace_bytes(d.n_dst, d.heads * d.dim), 256);
-  L.total = L.ts_bytes + L.csr_part_bytes + L.csc_part_bytes + L.colsum_bytes + 256;
+  L.total = L.ts_bytes + L.csc_part_bytes + L.colsum_bytes + 256;
   return L;
 }
 
@@ -296,6 +441,9 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csr_pla
 using namespace egc;
 
 extern "C" {
+
+int32_t egc_saved_slots(const egc_layer_desc* desc) { return desc ? n_saved_slots(*desc) : 0; }
+int32_t egc_saved_arg_slots(const egc_layer_desc* desc) { return desc ? n_arg_slots(*desc) : 0; }
 
 size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* plan) {
   if (desc == nullptr) return 0;
@@ -307,107 +455,136 @@ size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
 
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_sym,
                       const float* val_lin, const egc_row_plan* plan, const float* bases, const float* weightings,
-                      const float* bias, float* out, float* agg_out, int32_t* arg_out, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      const float* bias, float* out, float* agg_out, int32_t* arg_out, float* saved,
+                      int32_t* saved_arg, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_fwd")) return rc;
   if (int rc = validate_plan(plan, "egc_aggregate_fwd")) return rc;
   EGC_REQUIRE(rowptr && col && bases, "egc_aggregate_fwd: null graph / bases pointer");
   EGC_REQUIRE(out == nullptr || weightings != nullptr, "egc_aggregate_fwd: weightings required to produce out");
-  EGC_REQUIRE(out || agg_out || arg_out, "egc_aggregate_fwd: no output requested");
+  EGC_REQUIRE(out || agg_out || arg_out || saved, "egc_aggregate_fwd: no output requested");
   const int mask = prim_mask_of(*desc);
   EGC_REQUIRE(!(mask & P_SYM) || val_sym != nullptr, "egc_aggregate_fwd: symnorm requested without val_sym");
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_fwd: val_lin cannot be combined with symnorm (ref :253-254)");
   EGC_REQUIRE(workspace_bytes >= egc_aggregate_fwd_workspace_bytes(desc, plan) && (workspace || !(plan && plan->n_chunks)),
               "egc_aggregate_fwd: workspace too small");
+  const int n_arg = n_arg_slots(*desc);
+  EGC_REQUIRE(saved == nullptr || n_arg == 0 || saved_arg != nullptr, "egc_aggregate_fwd: saved_arg required with saved for min/max");
   AggParams p{};
   const int bd = desc->bases * desc->dim;
-  const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(out) && aligned16(agg_out) && aligned16(workspace);
-  const int smem = fill_agg_params(p, *desc, vec4, false);
+  const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(out) && aligned16(agg_out) && aligned16(workspace) &&
+                    aligned16(arg_out) && aligned16(saved) && aligned16(saved_arg);
+  const int smem = fill_agg_params(p, *desc, vec4);
   EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_fwd: layer too wide for the shared-memory staging (%d bytes)", smem);
   p.rowptr = rowptr; p.col = col; p.val_sym = val_sym; p.val_lin = val_lin; p.n_rows = desc->n_dst;
   set_plan(p, plan);
   p.partials = static_cast<float*>(workspace);
   p.n_slots = n_slots_of_mask(mask);
-  p.bases = bases; p.weightings = weightings ? weightings : bases; p.bias = bias;
-  p.out = out; p.agg_out = agg_out; p.arg_out = arg_out;
+  p.bases = bases; p.weightings = weightings; p.bias = bias;
+  p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
-  auto launch = vec4 ? launch_aggregate_fwd_v4 : launch_aggregate_fwd_v1;
+  const bool want_arg = (arg_out != nullptr || saved_arg != nullptr) && n_arg > 0;
+  if (arg_out != nullptr && !want_arg)   // no min/max slot: every arg is "none"
+    EGC_CUDA(cudaMemsetAsync(arg_out, 0xff, static_cast<size_t>(desc->n_dst) * desc->n_aggr * bd * sizeof(int32_t), st));
+  auto launch = vec4 ? launch_aggregate_v4 : launch_aggregate_v1;
   p.mode = 0;
-  if (int rc = launch(p, mask, val_lin != nullptr, smem, st)) return rc;
+  if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
   if (p.n_long > 0) {
     p.mode = 1;
-    if (int rc = launch(p, mask, val_lin != nullptr, smem, st)) return rc;
+    if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
   }
   return EGC_OK;
 }
 
-size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, int32_t nnz, const egc_row_plan* csr_plan,
-                                         const egc_row_plan* csc_plan, int32_t flags) {
-  (void)nnz; (void)flags;
+size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags) {
+  (void)flags;
   if (desc == nullptr || prim_mask_of(*desc) <= 0) return 0;
-  return bwd_layout(*desc, csr_plan, csc_plan).total;
+  return bwd_layout(*desc, csc_plan).total;
 }
 
-int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_sym,
-                      const float* val_lin, const egc_row_plan* csr_plan, const int32_t* colptr,
-                      const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
+int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
+                      const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
-                      const float* weightings, const float* grad_out, float* d_weightings, float* d_bases,
-                      float* d_bias, int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)csr2csc;
+                      const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
+                      float* d_weightings, float* d_bases, float* d_bias, int32_t flags, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
-  if (int rc = validate_plan(csr_plan, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
-  EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && grad_out && d_weightings && d_bases && workspace,
+  EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
               "egc_aggregate_bwd: null pointer");
-  if (flags & EGC_BWD_DETERMINISTIC) {
-    bool has_route = false;
-    stream_mask_of(*desc, has_route);
-    if (has_route) {
-      set_error("egc_aggregate_bwd: EGC_BWD_DETERMINISTIC routing of min/max gradients is not built yet");
-      return EGC_ERR_UNSUPPORTED;
-    }
+  const BwdLayout L = bwd_layout(*desc, csc_plan);
+  if ((flags & EGC_BWD_DETERMINISTIC) && L.has_route) {
+    set_error("egc_aggregate_bwd: EGC_BWD_DETERMINISTIC routing of min/max gradients is not built yet");
+    return EGC_ERR_UNSUPPORTED;
   }
   const int mask = prim_mask_of(*desc);
-  EGC_REQUIRE(!(mask & P_SYM) || (val_sym && csc_val_sym), "egc_aggregate_bwd: symnorm requested without val_sym / csc_val_sym");
+  const int n_arg = n_arg_slots(*desc);
+  EGC_REQUIRE(n_arg == 0 || saved_arg != nullptr, "egc_aggregate_bwd: saved_arg required for min/max");
+  EGC_REQUIRE(!(mask & P_SYM) || csc_val_sym, "egc_aggregate_bwd: symnorm requested without csc_val_sym");
   EGC_REQUIRE((val_lin == nullptr) == (csc_val_lin == nullptr), "egc_aggregate_bwd: val_lin and csc_val_lin must come together");
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_bwd: val_lin cannot be combined with symnorm");
-  const BwdLayout L = bwd_layout(*desc, csr_plan, csc_plan);
   EGC_REQUIRE(workspace_bytes >= L.total, "egc_aggregate_bwd: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   float* tstreams = reinterpret_cast<float*>(ws);
-  float* csr_part = reinterpret_cast<float*>(ws + L.ts_bytes);
-  float* csc_part = reinterpret_cast<float*>(ws + L.ts_bytes + L.csr_part_bytes);
-  void* colsum_ws = ws + L.ts_bytes + L.csr_part_bytes + L.csc_part_bytes;
+  float* csc_part = reinterpret_cast<float*>(ws + L.ts_bytes);
+  void* colsum_ws = ws + L.ts_bytes + L.csc_part_bytes;
 
-  const int bd = desc->bases * desc->dim;
-  const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(d_bases) && aligned16(workspace) && aligned16(grad_out);
+  const int bd = desc->bases * desc->dim, hd = desc->heads * desc->dim;
+  const int hab = desc->heads * desc->n_aggr * desc->bases;
+  const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(d_bases) && aligned16(workspace);
 
   if (L.has_route || L.tsmask == 0)
     EGC_CUDA(cudaMemsetAsync(d_bases, 0, static_cast<size_t>(desc->n_src) * bd * sizeof(float), st));
 
-  // pass 1: per target row (CSR)
-  AggParams p{};
-  const int smem = fill_agg_params(p, *desc, vec4, true);
-  EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
-  p.rowptr = rowptr; p.col = col; p.val_sym = val_sym; p.val_lin = val_lin; p.n_rows = desc->n_dst;
-  set_plan(p, csr_plan);
-  p.partials = csr_part;
-  p.n_slots = n_slots_of_mask(mask);
-  p.bases = bases; p.weightings = weightings; p.grad_out = grad_out;
-  p.d_weightings = d_weightings; p.tstreams = tstreams; p.d_bases = d_bases;
-  p.n_ts = L.n_ts; p.ts_sym = L.ts_sym; p.ts_lin = L.ts_lin; p.ts_sq = L.ts_sq;
-  auto launch = vec4 ? launch_aggregate_bwd_v4 : launch_aggregate_bwd_v1;
-  p.mode = 0;
-  if (int rc = launch(p, mask, val_lin != nullptr, smem, st)) return rc;
-  if (p.n_long > 0) {
-    p.mode = 1;
-    if (int rc = launch(p, mask, val_lin != nullptr, smem, st)) return rc;
+  // ---- pass 1: streaming over target nodes
+  {
+    CombineBwdParams c{};
+    c.rowptr = rowptr; c.col = col; c.val_lin = val_lin; c.n_rows = desc->n_dst;
+    c.weightings = weightings; c.grad_out = grad_out; c.saved = saved; c.saved_arg = saved_arg;
+    c.d_weightings = d_weightings; c.tstreams = tstreams; c.d_bases = d_bases;
+    c.n_saved = n_saved_slots(*desc); c.n_arg = n_arg;
+    c.n_ts = L.n_ts; c.ts_sym = L.ts_sym; c.ts_lin = L.ts_lin; c.ts_sq = L.ts_sq;
+    c.H = desc->heads; c.B = desc->bases; c.D = desc->dim; c.A = desc->n_aggr;
+    c.BD = bd; c.HD = hd; c.AB = desc->n_aggr * desc->bases; c.HAB = hab;
+    int na = 0;
+    for (int a = 0; a < EGC_MAX_AGGR; ++a) {
+      c.aggr[a] = a < desc->n_aggr ? desc->aggr[a] : -1;
+      c.arg_slot[a] = (a < desc->n_aggr && (desc->aggr[a] == EGC_AGGR_MAX || desc->aggr[a] == EGC_AGGR_MIN)) ? na++ : -1;
+    }
+    c.sigmoid = desc->sigmoid;
+    auto a4 = [](int v) { return (v + 3) & ~3; };
+    int off = 0;
+    c.sm_w = off; off = a4(off + hab);
+    c.sm_g = off; off = a4(off + hd);
+    c.sm_saved = off; off = a4(off + c.n_saved * bd);
+    c.sm_arg = off; off = a4(off + n_arg * bd);
+    c.sm_per_warp = off;
+    const int smem = off * kAggWarps * static_cast<int>(sizeof(float));
+    EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
+    c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
+               aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
+    const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
+    const bool linw = val_lin != nullptr;
+    const int grid = ceil_div(desc->n_dst, kAggWarps);
+#define EGC_LAUNCH_COMBINE(EV, LW)                                                                             \
+    {                                                                                                          \
+      auto kern = k_combine_bwd<EV, LW>;                                                                       \
+      if (smem > 48 * 1024) EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      LaunchScope egc_ls_("k_combine_bwd", st);                                                                \
+      kern<<<grid, kAggThreads, smem, st>>>(c);                                                                \
+    }
+    if (ev4 && !linw) EGC_LAUNCH_COMBINE(4, false)
+    else if (ev4 && linw) EGC_LAUNCH_COMBINE(4, true)
+    else if (!linw) EGC_LAUNCH_COMBINE(1, false)
+    else EGC_LAUNCH_COMBINE(1, true)
+#undef EGC_LAUNCH_COMBINE
+    EGC_LAUNCH_CHECK("k_combine_bwd");
   }
 
-  // pass 2: per source column (CSC), atomic-free
+  // ---- pass 2: per source column (CSC), atomic-free
   if (L.tsmask != 0) {
+    AggParams geo{};
+    fill_agg_params(geo, *desc, vec4);
     ScatterParams s{};
     s.colptr = colptr; s.rowidx = rowidx; s.val_sym = csc_val_sym; s.val_lin = csc_val_lin; s.n_cols = desc->n_src;
     s.n_long = csc_plan ? csc_plan->n_long : 0;
@@ -419,7 +596,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.partials = csc_part;
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
-    s.BD = bd; s.nvec = p.nvec; s.G = p.G; s.n_pass = p.n_pass;
+    s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
     s.routed = L.has_route ? 1 : 0;
     s.mode = 0;
     if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
@@ -430,7 +607,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   }
 
   if (d_bias != nullptr) {
-    if (int rc = colsum_f32(grad_out, desc->n_dst, desc->heads * desc->dim, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
+    if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
   }
   return EGC_OK;
 }

@@ -56,21 +56,28 @@ def project(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Opt
 
 
 def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Optional[Tensor],
-                      bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False):
-    """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg); unrequested ones are None."""
+                      bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False,
+                      want_saved: bool = False):
+    """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg, saved, saved_arg); unrequested ones
+    are None.  `saved` / `saved_arg` are what the backward pass consumes (see include/egc_b200.h)."""
     lib = _lib.load()
     dev = bases.device
     n, bd, hd = desc.n_dst, desc.bases * desc.dim, desc.heads * desc.dim
     out = torch.empty((n, hd), dtype=torch.float32, device=dev) if want_out else None
     agg = torch.empty((n, desc.n_aggr, bd), dtype=torch.float32, device=dev) if want_agg else None
     arg = torch.empty((n, desc.n_aggr, bd), dtype=torch.int32, device=dev) if want_arg else None
+    saved = saved_arg = None
+    if want_saved:
+        saved = torch.empty((n, lib.egc_saved_slots(desc), bd), dtype=torch.float32, device=dev)
+        n_arg = lib.egc_saved_arg_slots(desc)
+        saved_arg = torch.empty((n, n_arg, bd), dtype=torch.int32, device=dev) if n_arg else None
     plan = graph.plan.struct
     nbytes = lib.egc_aggregate_fwd_workspace_bytes(desc, plan)
     ws = _ws(nbytes, dev)
     check(lib.egc_aggregate_fwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin), plan,
-                                ptr(bases), ptr(weightings), ptr(bias), ptr(out), ptr(agg), ptr(arg), ptr(ws), nbytes,
-                                _stream()), "egc_aggregate_fwd")
-    return out, agg, arg
+                                ptr(bases), ptr(weightings), ptr(bias), ptr(out), ptr(agg), ptr(arg), ptr(saved),
+                                ptr(saved_arg), ptr(ws), nbytes, _stream()), "egc_aggregate_fwd")
+    return out, agg, arg, saved, saved_arg
 
 
 class _EGConvFunction(torch.autograd.Function):
@@ -86,17 +93,20 @@ class _EGConvFunction(torch.autograd.Function):
             raise ValueError(f"x must be [num_nodes, in_channels] with num_nodes == {graph.n_src}")
         dim = bases_weight.size(1) // num_bases
         desc = make_desc(graph, heads, num_bases, dim, aggrs, sigmoid)
+        needs_grad = any(ctx.needs_input_grad[:5])
         with torch.cuda.device(x.device):
             bases, weightings = project(x, bases_weight, comb_weight, comb_bias, sigmoid, algo)
-            out, _, _ = aggregate_combine(desc, graph, bases, weightings, bias)
-        ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings)
+            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias,
+                                                            want_saved=needs_grad)
+        if needs_grad:
+            ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings, saved, saved_arg)
         ctx.graph, ctx.desc, ctx.algo, ctx.bwd_flags = graph, desc, algo, bwd_flags
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, bases_weight, comb_weight, bases, weightings = ctx.saved_tensors
+        x, bases_weight, comb_weight, bases, weightings, saved, saved_arg = ctx.saved_tensors
         graph, desc = ctx.graph, ctx.desc
         lib = _lib.load()
         dev = x.device
@@ -109,14 +119,13 @@ class _EGConvFunction(torch.autograd.Function):
             d_w = torch.empty((n, hab), dtype=torch.float32, device=dev)
             d_bases = torch.empty((graph.n_src, bd), dtype=torch.float32, device=dev)
             d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if (need_b and ctx.has_bias) else None
-            nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.nnz, graph.plan.struct, graph.csc_plan.struct,
-                                                           ctx.bwd_flags)
+            nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, ctx.bwd_flags)
             ws = _ws(nbytes, dev)
-            check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin),
-                                        graph.plan.struct, ptr(graph.colptr), ptr(graph.rowidx), ptr(graph.csr2csc),
-                                        ptr(graph.csc_val_sym), ptr(graph.csc_val_lin), graph.csc_plan.struct,
-                                        ptr(bases), ptr(weightings), ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias),
-                                        ctx.bwd_flags, ptr(ws), nbytes, _stream()), "egc_aggregate_bwd")
+            check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
+                                        ptr(graph.rowidx), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
+                                        graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
+                                        ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ctx.bwd_flags, ptr(ws),
+                                        nbytes, _stream()), "egc_aggregate_bwd")
             del ws
             d_x = torch.empty_like(x) if need_x else None
             d_wb = torch.empty_like(bases_weight) if need_wb else None

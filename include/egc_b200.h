@@ -186,33 +186,38 @@ int egc_project_bwd(const float* x, const float* w_bases, const float* w_comb,
  * val_sym: per-nnz weights for symnorm (required iff symnorm is requested).
  * val_lin: per-nnz weights applied by every other aggregator (NULL = unweighted; only a valued
  *          SparseTensor without symnorm produces them, ref :256-258).
- * bias may be NULL.  Optional debug/inspection outputs (NULL to skip):
- *   agg_out[n_dst, A, B*D]  the aggregated bases before combination (ref :249 / :278)
- *   arg_out[n_dst, A, B*D]  int32 nnz position of the winning element for min/max slots (-1: empty row,
- *                           other slots -1); source id = col[arg]. */
+ * bias may be NULL.  Every output is optional (NULL to skip), at least one must be given:
+ *   out[n_dst, H*D]           the layer output (needs weightings)
+ *   agg_out[n_dst, A, B*D]    the aggregated bases before combination (ref :249 / :278)
+ *   arg_out[n_dst, A, B*D]    int32 nnz position of the winning element for min/max slots (-1: empty row,
+ *                             other slots -1); source id = col[arg]
+ *   saved[n_dst, S, B*D]      what egc_aggregate_bwd needs, S = egc_saved_slots(): slot a < A = agg_a (std slots
+ *                             negated when relu(var) gated the gradient off), slot A = mean when var/std is present
+ *   saved_arg[n_dst, R, B*D]  winning nnz positions of the R = egc_saved_arg_slots() min/max aggregators. */
+int32_t egc_saved_slots(const egc_layer_desc* desc);
+int32_t egc_saved_arg_slots(const egc_layer_desc* desc);
 size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* plan);
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
                       const float* val_sym, const float* val_lin, const egc_row_plan* plan,
                       const float* bases, const float* weightings, const float* bias,
-                      float* out, float* agg_out, int32_t* arg_out,
+                      float* out, float* agg_out, int32_t* arg_out, float* saved, int32_t* saved_arg,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above (ref: autograd of :191-208; torch_sparse spmm backward over the cached CSC).
- * Pass 1 (CSR, per target): recomputes the aggregates, writes d_weightings (times sigmoid' when
- * desc->sigmoid; = gradient w.r.t. the Linear output) and the target-side streams; min/max gradients are
- * routed to the single winning source.  Pass 2 (CSC, per source, atomic-free):
+ * Pass 1 (per target, streaming over `saved`): d_weightings (times sigmoid' when desc->sigmoid; = gradient
+ * w.r.t. the Linear output) and the target-side streams t_sym / t_lin / t_sq; min/max gradients are routed
+ * to the single winning source (fp32 atomics into d_bases).  Pass 2 (CSC, per source, atomic-free):
  *   d_bases[j] = sum_e val_sym[e] t_sym[i_e] + val_lin[e] (t_lin[i_e] + 2 bases[j] t_sq[i_e]) + routed.
- * csc_val_sym / csc_val_lin are val_sym / val_lin in CSC order (NULL like their CSR twins).
- * d_bias (may be NULL) = column sums of grad_out.  flags: EGC_BWD_* bits. */
+ * rowptr / col / val_lin are the CSR of the forward (row nnz counts, arg -> source id); colptr / rowidx /
+ * csc_val_sym / csc_val_lin its CSC view from egc_csr_transpose + egc_permute_f32 (values NULL like
+ * their CSR twins).  d_bias (may be NULL) = column sums of grad_out.  flags: EGC_BWD_* bits. */
 #define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients through the CSC pass (no fp32 atomics) */
-size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, int32_t nnz, const egc_row_plan* csr_plan,
-                                         const egc_row_plan* csc_plan, int32_t flags);
-int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
-                      const float* val_sym, const float* val_lin, const egc_row_plan* csr_plan,
-                      const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc,
-                      const float* csc_val_sym, const float* csc_val_lin, const egc_row_plan* csc_plan,
-                      const float* bases, const float* weightings, const float* grad_out,
-                      float* d_weightings, float* d_bases, float* d_bias, int32_t flags,
+size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags);
+int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
+                      const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
+                      const float* csc_val_lin, const egc_row_plan* csc_plan,
+                      const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
+                      const float* grad_out, float* d_weightings, float* d_bases, float* d_bias, int32_t flags,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

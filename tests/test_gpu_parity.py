@@ -164,7 +164,8 @@ def test_aggregate_stage_and_argmax_ids(bd, dim, hub):
     bases = torch.randn(n, bd)
     bases[5] = bases[9]                                            # exact ties between two sources
     desc = make_desc(g, 4, b, dim, aggrs, False)
-    _, agg, arg = aggregate_combine(desc, g, bases.to(DEV), None, None, want_out=False, want_agg=True, want_arg=True)
+    _, agg, arg, _, _ = aggregate_combine(desc, g, bases.to(DEV), None, None, want_out=False, want_agg=True,
+                                            want_arg=True)
     agg_o, arg_o = R.aggregate(o, bases.double(), aggrs)
     assert rel_err(agg, agg_o) < TOL
     for name in ("min", "max"):
@@ -189,7 +190,7 @@ def test_degree_properties_full_arxiv_size():
     aggrs = ["sum", "mean", "symnorm", "min", "max", "var", "std"]
     desc = make_desc(g, 4, 4, 32, aggrs, False)
     ones = torch.ones(n, 128, device=DEV)
-    _, agg, _ = aggregate_combine(desc, g, ones, None, None, want_out=False, want_agg=True)
+    agg = aggregate_combine(desc, g, ones, None, None, want_out=False, want_agg=True)[1]
     deg = (g.rowptr[1:] - g.rowptr[:-1]).float()
     assert torch.equal(agg[:, 0], deg.view(-1, 1).expand(-1, 128))
     for k in (1, 3, 4):
