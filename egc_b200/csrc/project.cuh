@@ -6,6 +6,14 @@
 
 namespace egc {
 
+// exact-fp32 FFMA tiles (project.cu)
+int project_fwd_simt(const float* x, const float* w_bases, const float* w_comb, const float* b_comb, int n, int f_in,
+                     int bd, int hab, int sigmoid, float* bases, float* weightings, cudaStream_t st);
+size_t project_bwd_simt_workspace(int n, int f_in, int bd, int hab);
+int project_bwd_simt(const float* x, const float* w_bases, const float* w_comb, const float* d_bases,
+                     const float* d_lin, int n, int f_in, int bd, int hab, float* d_x, float* d_w_bases,
+                     float* d_w_comb, float* d_b_comb, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 // tensor-core (tcgen05, kind::tf32) path; n_terms = 3 -> 3xTF32 split (fp32-level accuracy), 1 -> plain TF32
 bool project_tc_supported(int n, int f_in, int bd, int hab);
 int project_fwd_tc(const float* x, const float* w_bases, const float* w_comb, const float* b_comb, int n, int f_in,

@@ -1,23 +1,376 @@
-// tcgen05 (kind::tf32) projections - placeholder until the tensor-core kernels land:
-// reports "unsupported" so EGC_GEMM_AUTO resolves to the exact-fp32 FFMA tiles.
+// tcgen05 (5th-gen tensor core) projections for sm_100a:  C[M, N] = [A1 | A2][M, K] . B[K, N]
+//
+//   forward : [bases | weightings] = x . [W_b | W_c^T]   (+ bias, sigmoid on the weightings columns)
+//   backward: d_x = [d_bases | d_lin] . [W_b | W_c^T]^T
+//
+// fp32 parity through kind::tf32 MMAs comes from the 3-term split  a.b ~= ah.bh + ah.bl + al.bh  with
+// ah = a & 0xffffe000 (exact TF32), al = a - ah, accumulated in fp32 in TMEM (n_terms = 1 gives plain TF32).
+//
+// One persistent CTA per SM, 9 warps:
+//   warps 0-3  epilogue   tcgen05.ld of the 128 x N accumulator (TMEM lanes 32w..32w+31) -> global
+//   warp  4    MMA        one elected lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation
+//   warps 5-8  producers  one A row per thread: LDG.128 -> hi/lo split -> st.shared in the canonical
+//                         K-major no-swizzle UMMA layout (8-row x 16-byte core matrices)
+// The weights (B, hi and lo) are staged once per CTA and stay resident in shared memory; A streams
+// through a 3-stage ring of 128 x 16 chunks; the accumulator is double-buffered in TMEM (2 x 256 cols)
+// so the epilogue of tile t overlaps the main loop of tile t+1.
+#include <algorithm>
+
 #include "project.cuh"
 
 namespace egc {
 
-bool project_tc_supported(int, int, int, int) { return false; }
+constexpr int kTcThreads = 288;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 16;                                   // floats of K per A chunk (2 UMMA k-steps of 8)
+constexpr int kStages = 3;
+constexpr int kHalfStageBytes = kTileM * kChunkK * 4;         // 8 KB (hi or lo)
+constexpr int kStageBytes = 2 * kHalfStageBytes;              // hi + lo
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kTmemCols = 512;
 
-int project_fwd_tc(const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
-                   int, cudaStream_t) {
-  set_error("tensor-core projection not built");
-  return EGC_ERR_UNSUPPORTED;
+struct TcParams {
+  const float* a1; int lda1; int k1;      // A = [a1 | a2], row-major
+  const float* a2; int lda2; int k2;
+  int M;
+  // B(n, k) = b[nb][kb][ (n - n_off) * sn + (k - k_off) * sk ],  nb = n >= n1, kb = k >= k1
+  const float* b[2][2];
+  int b_sn[2][2], b_sk[2][2];
+  int n1, n2;                              // N = n1 + n2; columns >= n1 go to c2
+  float* c1; int ldc1;
+  float* c2; int ldc2;
+  const float* bias2;
+  int sigmoid2;
+  int n_pad, k_pad;                        // multiples of 16
+  int n_terms;                             // 3: 3xTF32, 1: TF32
+  int num_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-size_t project_bwd_tc_workspace(int, int, int, int) { return 0; }
+// D[tmem] (+)= A[smem desc] . B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 
-int project_bwd_tc(const float*, const float*, const float*, const float*, const float*, int, int, int, int, float*,
-                   float*, float*, float*, int, void*, size_t, cudaStream_t) {
-  set_error("tensor-core projection not built");
-  return EGC_ERR_UNSUPPORTED;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous);
+// LBO = byte distance between the two 16-byte K pieces of one MMA, SBO = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;       // descriptor version (Blackwell)
+  return d;                                   // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.k1 + p.k2, N = p.n1 + p.n2;
+  const uint32_t b_half_bytes = static_cast<uint32_t>(p.n_pad) * p.k_pad * 4;
+  const uint32_t lbo_b = static_cast<uint32_t>(p.n_pad) * 16;            // bytes between 16-byte K pieces of B
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + b_half_bytes;
+  uint8_t* a_ring = smem + 2 * b_half_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + kStages * kStageBytes);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+
+  // ---- stage the weights once: hi / lo split, canonical K-major layout (zero padded)
+  for (int idx = tid; idx < p.n_pad * p.k_pad; idx += kTcThreads) {
+    const int k = idx / p.n_pad, n = idx - k * p.n_pad;
+    float v = 0.f;
+    if (n < N && k < K) {
+      const int nb = n >= p.n1 ? 1 : 0, kb = k >= p.k1 ? 1 : 0;
+      const float* src = p.b[nb][kb];
+      if (src != nullptr)
+        v = __ldg(src + static_cast<int64_t>(n - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
+                  static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+    }
+    const float hi = tf32_hi(v), lo = v - hi;
+    const uint32_t off = static_cast<uint32_t>(k >> 2) * lbo_b + static_cast<uint32_t>(n) * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(b_hi + off) = hi;
+    *reinterpret_cast<float*>(b_lo + off) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_chunks = p.k_pad / kChunkK;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp >= 5) {
+    // ================= producers: one A row per thread =================
+    const int pt = tid - 5 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+      const int64_t row = static_cast<int64_t>(tile) * kTileM + pt;
+      const bool valid = row < p.M;
+      const float* r1 = p.a1 + row * p.lda1;
+      const float* r2 = p.a2 != nullptr ? p.a2 + row * p.lda2 : nullptr;
+      for (int j = 0; j < n_chunks; ++j) {
+        float4 v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = j * kChunkK + 4 * c;
+          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && k < K) {
+            const float* src = k < p.k1 ? r1 + k : r2 + (k - p.k1);
+            v[c] = __ldcs(reinterpret_cast<const float4*>(src));
+          }
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        uint8_t* hi_base = a_ring + stage * kStageBytes + pt * 16;
+        uint8_t* lo_base = hi_base + kHalfStageBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
+          float4 l = make_float4(v[c].x - h.x, v[c].y - h.y, v[c].z - h.z, v[c].w - h.w);
+          *reinterpret_cast<float4*>(hi_base + c * (kTileM * 16)) = h;
+          *reinterpret_cast<float4*>(lo_base + c * (kTileM * 16)) = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(full_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
+                             (static_cast<uint32_t>(kTileM >> 4) << 24);
+      const uint32_t a_lbo = kTileM * 16, sbo = 128;
+      const uint32_t b_hi_addr = smem_u32(b_hi), b_lo_addr = smem_u32(b_lo), ring_addr = smem_u32(a_ring);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
+        const int acc = t & 1;
+        mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+        for (int j = 0; j < n_chunks; ++j) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_hi_addr = ring_addr + stage * kStageBytes, a_lo_addr = a_hi_addr + kHalfStageBytes;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t ks = static_cast<uint32_t>(2 * j + s);
+            const uint64_t da_hi = make_desc(a_hi_addr + s * 2 * a_lbo, a_lbo, sbo);
+            const uint64_t db_hi = make_desc(b_hi_addr + ks * 2 * lbo_b, lbo_b, sbo);
+            umma_tf32(d_tmem, da_hi, db_hi, idesc, (j | s) != 0 ? 1u : 0u);
+            if (p.n_terms == 3) {
+              const uint64_t da_lo = make_desc(a_lo_addr + s * 2 * a_lbo, a_lbo, sbo);
+              const uint64_t db_lo = make_desc(b_lo_addr + ks * 2 * lbo_b, lbo_b, sbo);
+              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(stage));          // frees the A slot once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue: TMEM -> registers -> global =================
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int t = 0;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
+      const int acc = t & 1;
+      mbar_wait(tfull_bar(acc), (static_cast<uint32_t>(t) >> 1) & 1u);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(tile) * kTileM + tid;
+      const bool valid = row < p.M;
+      float* o1 = p.c1 + row * p.ldc1;
+      float* o2 = p.c2 != nullptr ? p.c2 + row * p.ldc2 : nullptr;
+      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(acc) * 256u + static_cast<uint32_t>(col0), r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = col0 + 4 * q;
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (col < p.n1) {
+              *reinterpret_cast<float4*>(o1 + col) = v;
+            } else if (col < N) {
+              const int c2 = col - p.n1;
+              if (p.bias2 != nullptr) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + c2));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              if (p.sigmoid2) {
+                v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
+                v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
+              }
+              *reinterpret_cast<float4*>(o2 + c2) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int round16(int v) { return (v + 15) / 16 * 16; }
+
+static size_t tc_smem_bytes(int n_pad, int k_pad) {
+  return static_cast<size_t>(2) * n_pad * k_pad * 4 + kStages * kStageBytes + 256;
+}
+
+static bool tc_shape_ok(int k, int n) {
+  const int k_pad = round16(k), n_pad = round16(n);
+  return n_pad >= 16 && n_pad <= 256 && tc_smem_bytes(n_pad, k_pad) <= kMaxSmem;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool project_tc_supported(int n, int f_in, int bd, int hab) {
+  if (n < 1 || f_in % 4 || bd % 4 || hab % 4) return false;
+  return tc_shape_ok(f_in, bd + hab) && tc_shape_ok(bd + hab, f_in);
+}
+
+static int launch_tc(TcParams& p, cudaStream_t st) {
+  const int K = p.k1 + p.k2, N = p.n1 + p.n2;
+  p.k_pad = round16(K);
+  p.n_pad = round16(N);
+  p.num_tiles = ceil_div(p.M, kTileM);
+  const size_t smem = tc_smem_bytes(p.n_pad, p.k_pad);
+  EGC_REQUIRE(smem <= kMaxSmem, "tensor-core projection: shape does not fit shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGC_CUDA(cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.num_tiles, sm_count());
+  {
+    LaunchScope ls("k_project_tc", st);
+    k_project_tc<<<grid, kTcThreads, smem, st>>>(p);
+  }
+  EGC_LAUNCH_CHECK("k_project_tc");
+  return EGC_OK;
+}
+
+int project_fwd_tc(const float* x, const float* w_bases, const float* w_comb, const float* b_comb, int n, int f_in,
+                   int bd, int hab, int sigmoid, float* bases, float* weightings, int n_terms, cudaStream_t st) {
+  EGC_REQUIRE(aligned16(x) && aligned16(bases) && aligned16(weightings) && (b_comb == nullptr || aligned16(b_comb)),
+              "tensor-core projection needs 16-byte aligned tensors");
+  TcParams p{};
+  p.a1 = x; p.lda1 = f_in; p.k1 = f_in; p.a2 = nullptr; p.lda2 = 0; p.k2 = 0; p.M = n;
+  p.b[0][0] = w_bases; p.b_sn[0][0] = 1; p.b_sk[0][0] = bd;          // B(n,k) = W_b[k][n]
+  p.b[1][0] = w_comb; p.b_sn[1][0] = f_in; p.b_sk[1][0] = 1;         // B(n,k) = W_c[n][k]
+  p.n1 = bd; p.n2 = hab;
+  p.c1 = bases; p.ldc1 = bd; p.c2 = weightings; p.ldc2 = hab; p.bias2 = b_comb; p.sigmoid2 = sigmoid;
+  p.n_terms = n_terms;
+  return launch_tc(p, st);
+}
+
+size_t project_bwd_tc_workspace(int n, int f_in, int bd, int hab) {
+  return project_bwd_simt_workspace(n, f_in, bd, hab);
+}
+
+int project_bwd_tc(const float* x, const float* w_bases, const float* w_comb, const float* d_bases, const float* d_lin,
+                   int n, int f_in, int bd, int hab, float* d_x, float* d_w_bases, float* d_w_comb, float* d_b_comb,
+                   int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (d_x != nullptr) {
+    EGC_REQUIRE(aligned16(d_bases) && aligned16(d_lin) && aligned16(d_x), "tensor-core projection needs 16-byte aligned tensors");
+    TcParams p{};
+    p.a1 = d_bases; p.lda1 = bd; p.k1 = bd; p.a2 = d_lin; p.lda2 = hab; p.k2 = hab; p.M = n;
+    p.b[0][0] = w_bases; p.b_sn[0][0] = bd; p.b_sk[0][0] = 1;         // k < bd : B(n,k) = W_b[n][k]
+    p.b[0][1] = w_comb; p.b_sn[0][1] = 1; p.b_sk[0][1] = f_in;        // k >= bd: B(n,k) = W_c[k-bd][n]
+    p.n1 = f_in; p.n2 = 0;
+    p.c1 = d_x; p.ldc1 = f_in; p.c2 = nullptr; p.ldc2 = 0; p.bias2 = nullptr; p.sigmoid2 = 0;
+    p.n_terms = n_terms;
+    if (int rc = launch_tc(p, st)) return rc;
+  }
+  // parameter gradients: reductions over the node dimension (fp32 FFMA split-K tiles)
+  return project_bwd_simt(x, w_bases, w_comb, d_bases, d_lin, n, f_in, bd, hab, nullptr, d_w_bases, d_w_comb, d_b_comb,
+                          workspace, workspace_bytes, st);
 }
 
 }  // namespace egc
