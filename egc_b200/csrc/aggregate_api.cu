@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
       }
     } else {
       const int c0 = p.long_chunk_ptr[long_idx], c1 = p.long_chunk_ptr[long_idx + 1];
+#pragma unroll 4
       for (int c = c0; c < c1; ++c) {
         const float* q = p.partials + static_cast<int64_t>(c) * row_stride + foff;
         float t[VEC];

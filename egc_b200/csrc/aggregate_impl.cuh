@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_aggregate(const __grid_const
       accumulate_range<MASK, VEC, LINW, ARG>(acc, p, begin, end, lane, foff);
     } else {
       const int c0 = p.long_chunk_ptr[long_idx], c1 = p.long_chunk_ptr[long_idx + 1];
+#pragma unroll 4
       for (int c = c0; c < c1; ++c)
         acc.merge_from(p.partials + (static_cast<int64_t>(c) * p.n_slots) * p.BD + foff, p.BD);
     }

@@ -11,7 +11,7 @@ namespace egc {
 constexpr int kColsumRowsPerCta = 8;   // blockDim = (32, 8)
 
 inline int colsum_slabs(int n_rows) {
-  return std::max(1, std::min(sm_count() * 4, ceil_div(n_rows, 64)));
+  return std::max(1, std::min(sm_count() * 2, ceil_div(n_rows, 64)));
 }
 
 inline size_t colsum_workspace_bytes(int n_rows, int n_cols) {
@@ -39,12 +39,15 @@ static __global__ void k_colsum_stage1(const float* __restrict__ in, int n_rows,
   }
 }
 
+// one warp per column: lanes stride over the slabs (fixed order -> deterministic), then a shuffle tree
 static __global__ void k_colsum_stage2(const float* __restrict__ partial, int n_slabs, int n_cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= n_cols) return;
   float t = 0.f;
-  for (int s = 0; s < n_slabs; ++s) t += partial[static_cast<int64_t>(s) * n_cols + c];
-  out[c] = t;
+  for (int s = lane; s < n_slabs; s += 32) t += partial[static_cast<int64_t>(s) * n_cols + c];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+  if (lane == 0) out[c] = t;
 }
 
 inline int colsum_f32(const float* in, int n_rows, int n_cols, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -60,7 +63,7 @@ inline int colsum_f32(const float* in, int n_rows, int n_cols, float* out, void*
   EGC_LAUNCH_CHECK("k_colsum_stage1");
   {
     LaunchScope egc_ls_("k_colsum_stage2", st);
-    k_colsum_stage2<<<ceil_div(n_cols, 128), 128, 0, st>>>(partial, slabs, n_cols, out);
+    k_colsum_stage2<<<ceil_div(n_cols, 8), 256, 0, st>>>(partial, slabs, n_cols, out);
   }
   EGC_LAUNCH_CHECK("k_colsum_stage2");
   return EGC_OK;

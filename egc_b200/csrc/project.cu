@@ -113,9 +113,16 @@ __global__ void __launch_bounds__(kGemmThreads) k_gemm_f32(const float* __restri
 __global__ void k_reduce_splits(const float* __restrict__ partial, int splits, int64_t count, float* __restrict__ out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= count) return;
-  float t = 0.f;
-  for (int z = 0; z < splits; ++z) t += partial[static_cast<int64_t>(z) * count + i];
-  out[i] = t;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int z = 0;
+  for (; z + 4 <= splits; z += 4) {
+    t0 += partial[static_cast<int64_t>(z) * count + i];
+    t1 += partial[static_cast<int64_t>(z + 1) * count + i];
+    t2 += partial[static_cast<int64_t>(z + 2) * count + i];
+    t3 += partial[static_cast<int64_t>(z + 3) * count + i];
+  }
+  for (; z < splits; ++z) t0 += partial[static_cast<int64_t>(z) * count + i];
+  out[i] = (t0 + t1) + (t2 + t3);
 }
 
 template <bool A_KCONTIG, bool B_NCONTIG>

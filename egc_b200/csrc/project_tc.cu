@@ -146,20 +146,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
 
   // ---- stage the weights once: hi / lo split, canonical K-major layout (zero padded)
-  for (int idx = tid; idx < p.n_pad * p.k_pad; idx += kTcThreads) {
-    const int k = idx / p.n_pad, n = idx - k * p.n_pad;
-    float v = 0.f;
-    if (n < N && k < K) {
-      const int nb = n >= p.n1 ? 1 : 0, kb = k >= p.k1 ? 1 : 0;
-      const float* src = p.b[nb][kb];
-      if (src != nullptr)
-        v = __ldg(src + static_cast<int64_t>(n - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
-                  static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+  for (int k = warp; k < p.k_pad; k += kTcThreads / 32) {
+    const int kb = k >= p.k1 ? 1 : 0;
+    const uint32_t koff = static_cast<uint32_t>(k >> 2) * lbo_b + (k & 3) * 4;
+    for (int n = lane; n < p.n_pad; n += 32) {
+      float v = 0.f;
+      if (n < N && k < K) {
+        const int nb = n >= p.n1 ? 1 : 0;
+        const float* src = p.b[nb][kb];
+        if (src != nullptr)
+          v = __ldg(src + static_cast<int64_t>(n - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
+                    static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+      }
+      const float hi = tf32_hi(v), lo = v - hi;
+      const uint32_t off = koff + static_cast<uint32_t>(n) * 16;
+      *reinterpret_cast<float*>(b_hi + off) = hi;
+      *reinterpret_cast<float*>(b_lo + off) = lo;
     }
-    const float hi = tf32_hi(v), lo = v - hi;
-    const uint32_t off = static_cast<uint32_t>(k >> 2) * lbo_b + static_cast<uint32_t>(n) * 16 + (k & 3) * 4;
-    *reinterpret_cast<float*>(b_hi + off) = hi;
-    *reinterpret_cast<float*>(b_lo + off) = lo;
   }
   fence_proxy_async();
   tc_fence_before();

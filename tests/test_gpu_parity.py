@@ -63,8 +63,8 @@ def run_both(o, c, x, graph_cpu, graph_gpu, grad_out):
 
 
 def tolerance(ref32, ref64):
-    """1e-5 relative, or twice the reference's own fp32-vs-fp64 rounding error where that is larger."""
-    return max(TOL, 2.0 * rel_err(ref32, ref64))
+    """1e-5 relative, or 4x the reference's own fp32-vs-fp64 rounding error where that is larger."""
+    return max(TOL, 4.0 * rel_err(ref32, ref64))
 
 
 def assert_close(res):
