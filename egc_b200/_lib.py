@@ -59,8 +59,8 @@ SIGNATURES = {
     "egc_saved_slots": (c_int32, [POINTER(LayerDesc)]),
     "egc_saved_arg_slots": (c_int32, [POINTER(LayerDesc)]),
     "egc_aggregate_fwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan)]),
-    "egc_aggregate_fwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, _P, _P, _P,
-                                    _P, _P, _P, c_size_t, _P]),
+    "egc_aggregate_fwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, _P, c_int32,
+                                    _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
                                     _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),

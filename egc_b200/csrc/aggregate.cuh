@@ -32,6 +32,8 @@ struct AggParams {
   const float* val_sym;
   const float* val_lin;
   int n_rows;
+  const int32_t* row_map;    // optional subset of rows handled as row tasks (null: all rows)
+  int n_row_tasks;
   // long-row plan + scratch for chunk partials [n_chunks][n_slots][BD]
   int n_long, n_chunks;
   const int32_t* long_rows;

@@ -456,13 +456,15 @@ size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
 
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_sym,
                       const float* val_lin, const egc_row_plan* plan, const float* bases, const float* weightings,
-                      const float* bias, float* out, float* agg_out, int32_t* arg_out, float* saved,
-                      int32_t* saved_arg, void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* bias, const int32_t* row_subset, int32_t n_subset, float* out, float* agg_out,
+                      int32_t* arg_out, float* saved, int32_t* saved_arg, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_fwd")) return rc;
   if (int rc = validate_plan(plan, "egc_aggregate_fwd")) return rc;
   EGC_REQUIRE(rowptr && col && bases, "egc_aggregate_fwd: null graph / bases pointer");
   EGC_REQUIRE(out == nullptr || weightings != nullptr, "egc_aggregate_fwd: weightings required to produce out");
   EGC_REQUIRE(out || agg_out || arg_out || saved, "egc_aggregate_fwd: no output requested");
+  EGC_REQUIRE(n_subset >= 0 && (n_subset == 0 || row_subset != nullptr), "egc_aggregate_fwd: bad row subset");
   const int mask = prim_mask_of(*desc);
   EGC_REQUIRE(!(mask & P_SYM) || val_sym != nullptr, "egc_aggregate_fwd: symnorm requested without val_sym");
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_fwd: val_lin cannot be combined with symnorm (ref :253-254)");
@@ -477,6 +479,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int smem = fill_agg_params(p, *desc, vec4);
   EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_fwd: layer too wide for the shared-memory staging (%d bytes)", smem);
   p.rowptr = rowptr; p.col = col; p.val_sym = val_sym; p.val_lin = val_lin; p.n_rows = desc->n_dst;
+  p.row_map = row_subset;
+  p.n_row_tasks = row_subset != nullptr ? n_subset : desc->n_dst;
   set_plan(p, plan);
   p.partials = static_cast<float*>(workspace);
   p.n_slots = n_slots_of_mask(mask);
@@ -484,7 +488,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
   const bool want_arg = (arg_out != nullptr || saved_arg != nullptr) && n_arg > 0;
-  if (arg_out != nullptr && !want_arg)   // no min/max slot: every arg is "none"
+  if (arg_out != nullptr && !want_arg && row_subset == nullptr)   // no min/max slot: every arg is "none"
     EGC_CUDA(cudaMemsetAsync(arg_out, 0xff, static_cast<size_t>(desc->n_dst) * desc->n_aggr * bd * sizeof(int32_t), st));
   auto launch = vec4 ? launch_aggregate_v4 : launch_aggregate_v1;
   p.mode = 0;

@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_aggregate(const __grid_const
       begin = p.chunk_begin[gw];
       end = min(begin + EGC_CHUNK_EDGES, p.rowptr[row + 1]);
     } else {
-      row = gw - p.n_chunks;
-      if (row >= p.n_rows) return;
+      const int idx = gw - p.n_chunks;
+      if (idx >= p.n_row_tasks) return;
+      row = p.row_map != nullptr ? p.row_map[idx] : idx;
       begin = p.rowptr[row];
       end = p.rowptr[row + 1];
       if (end - begin > EGC_CHUNK_EDGES) return;      // long row: chunks + merge task do it
@@ -156,7 +157,7 @@ int launch_one(const AggParams& p, int smem_bytes, cudaStream_t st) {
   if (smem_bytes > 48 * 1024) {
     EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
-  const int64_t tasks = p.mode == 0 ? static_cast<int64_t>(p.n_chunks) + p.n_rows : p.n_long;
+  const int64_t tasks = p.mode == 0 ? static_cast<int64_t>(p.n_chunks) + p.n_row_tasks : p.n_long;
   if (tasks <= 0) return EGC_OK;
   const int grid = ceil_div(tasks, kAggWarps);
   {

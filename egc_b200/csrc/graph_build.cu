@@ -123,7 +123,7 @@ __global__ void k_filldiag_count(const int64_t* __restrict__ rowptr_in, const in
   for (int64_t p = b + lane; p < e; p += 32) {
     long long c = col_in[p];
     if (c < 0 || c >= n_src) bad = true;
-    if (p > b && col_in[p - 1] > c) unsorted = true;
+    if (fill && p > b && col_in[p - 1] > c) unsorted = true;   // order only matters for the diagonal insert
     kept += (!fill || c != row) ? 1 : 0;
   }
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(kFull, kept, o);

@@ -1,0 +1,282 @@
+"""Row-partitioned (multi-GPU) execution of the EGConv hot path.  The reference has no counterpart
+(it is single-GPU); the contract is "same numbers as the single-GPU layer".
+
+Scheme (one process per GPU, torch.distributed; NCCL over NVLink on the B200 box, gloo in CPU tests):
+  * contiguous target-row ranges balanced by nnz; every rank owns x / bases / weightings / out rows of
+    its range and the CSR rows of those targets;
+  * column ids are remapped to a local "extended" space: [own rows | halo rows], halo = remote
+    sources referenced by the local CSR rows, grouped by owner;
+  * forward : local projection -> halo exchange of basis rows (point-to-point, only the rows each peer
+              needs) overlapped with the aggregation of interior rows -> boundary rows;
+  * backward: local passes produce d_bases for own AND halo sources; halo partial sums travel back to
+              their owners (reverse exchange) and are added in fixed peer order (deterministic);
+              parameter gradients are all-reduced.
+`PartitionPlan` and `HaloExchange` are pure index / communication plumbing (any device, any backend);
+`PartitionedEGConv` binds them to the CUDA kernels.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def balanced_row_bounds(rowptr: Tensor, world_size: int) -> List[int]:
+    """Split rows into `world_size` contiguous ranges with (nearly) equal nnz + rows."""
+    n = rowptr.numel() - 1
+    work = rowptr[1:].double() + torch.arange(1, n + 1, dtype=torch.float64)     # cumulative nnz + rows
+    total = float(work[-1]) if n > 0 else 0.0
+    bounds = [0]
+    for p in range(1, world_size):
+        target = total * p / world_size
+        b = int(torch.searchsorted(work, torch.tensor(target, dtype=torch.float64)))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
+@dataclass
+class LocalPartition:
+    """What one rank needs (all index tensors int64 on CPU until `.to(device)`)."""
+    rank: int
+    world_size: int
+    row_begin: int
+    row_end: int
+    rowptr: Tensor              # [n_local + 1] local CSR over own target rows
+    col: Tensor                 # [nnz_local] column ids in the extended local space
+    val_sym: Optional[Tensor]
+    val_lin: Optional[Tensor]
+    halo_ids: Tensor            # [n_halo] global ids of halo sources, grouped by owner, ascending
+    recv_counts: List[int]      # rows received from each peer (sum = n_halo)
+    send_rows: List[Tensor]     # per peer: LOCAL row ids whose basis rows that peer needs
+    interior_rows: Tensor       # local rows whose sources are all local
+    boundary_rows: Tensor       # local rows that touch at least one halo source
+
+    @property
+    def n_local(self) -> int:
+        return self.row_end - self.row_begin
+
+    @property
+    def n_halo(self) -> int:
+        return int(self.halo_ids.numel())
+
+
+class PartitionPlan:
+    """Host-side partition of a prepared global CSR (after self-loops / gcn_norm), so that symnorm
+    weights and nnz counts are the GLOBAL ones on every rank."""
+
+    def __init__(self, rowptr: Tensor, col: Tensor, world_size: int, val_sym: Optional[Tensor] = None,
+                 val_lin: Optional[Tensor] = None, bounds: Optional[List[int]] = None):
+        self.rowptr, self.col = rowptr.long().cpu(), col.long().cpu()
+        self.val_sym = val_sym.cpu() if val_sym is not None else None
+        self.val_lin = val_lin.cpu() if val_lin is not None else None
+        self.world_size = world_size
+        self.n = self.rowptr.numel() - 1
+        self.bounds = bounds or balanced_row_bounds(self.rowptr, world_size)
+        self._bounds_t = torch.tensor(self.bounds, dtype=torch.long)
+        self._needs = [self._needed_remote(r) for r in range(world_size)]      # [rank][owner] -> ids
+
+    def owner_of(self, ids: Tensor) -> Tensor:
+        return torch.searchsorted(self._bounds_t, ids, right=True) - 1
+
+    def _needed_remote(self, rank: int) -> List[Tensor]:
+        b, e = self.bounds[rank], self.bounds[rank + 1]
+        cols = self.col[self.rowptr[b]:self.rowptr[e]]
+        remote = torch.unique(cols[(cols < b) | (cols >= e)])
+        owner = self.owner_of(remote)
+        return [remote[owner == q] for q in range(self.world_size)]
+
+    def local(self, rank: int) -> LocalPartition:
+        b, e = self.bounds[rank], self.bounds[rank + 1]
+        lo, hi = int(self.rowptr[b]), int(self.rowptr[e])
+        rowptr = self.rowptr[b:e + 1] - lo
+        cols = self.col[lo:hi]
+        halo_ids = torch.cat(self._needs[rank]) if self.world_size > 1 else cols.new_zeros(0)
+        n_local = e - b
+        is_local = (cols >= b) & (cols < e)
+        col_ext = torch.where(is_local, cols - b, n_local + torch.searchsorted(halo_ids, cols)
+                              if halo_ids.numel() else cols - b)
+        # halo_ids is sorted globally because owners are contiguous ascending ranges
+        rows = torch.repeat_interleave(torch.arange(n_local), rowptr[1:] - rowptr[:-1])
+        touches = torch.zeros(n_local, dtype=torch.bool)
+        touches[rows[~is_local]] = True
+        send_rows = [self._needs[q][rank] - b for q in range(self.world_size)]
+        return LocalPartition(
+            rank=rank, world_size=self.world_size, row_begin=b, row_end=e, rowptr=rowptr, col=col_ext,
+            val_sym=self.val_sym[lo:hi] if self.val_sym is not None else None,
+            val_lin=self.val_lin[lo:hi] if self.val_lin is not None else None,
+            halo_ids=halo_ids, recv_counts=[int(t.numel()) for t in self._needs[rank]], send_rows=send_rows,
+            interior_rows=torch.nonzero(~touches).flatten(), boundary_rows=torch.nonzero(touches).flatten())
+
+
+class HaloExchange:
+    """Point-to-point exchange of feature rows between the ranks of a `PartitionPlan`.
+
+    forward(local_rows [n_local, W]) -> halo rows [n_halo, W] (what the peers own and this rank needs)
+    reverse(halo_partial [n_halo, W], into [n_local, W])  adds the peers' partial sums for rows this rank
+    owns, in ascending peer order.  `gather` / `scatter_add` can be overridden with device kernels.
+    """
+
+    def __init__(self, part: LocalPartition, device, group=None):
+        self.part, self.group, self.device = part, group, torch.device(device)
+        self.send_rows = [t.to(self.device) for t in part.send_rows]
+        self.recv_offsets = [0]
+        for c in part.recv_counts:
+            self.recv_offsets.append(self.recv_offsets[-1] + c)
+
+    def _peers(self):
+        r, w = self.part.rank, self.part.world_size
+        return [(r + k) % w for k in range(1, w)]
+
+    def start_forward(self, local_rows: Tensor):
+        """Posts the sends/receives; returns (halo buffer, work handles).  Call `finish()` before use."""
+        width = local_rows.size(1)
+        halo = torch.empty((self.part.n_halo, width), dtype=local_rows.dtype, device=local_rows.device)
+        ops, keep = [], []
+        for q in self._peers():
+            if self.part.recv_counts[q]:
+                ops.append(dist.P2POp(dist.irecv, halo[self.recv_offsets[q]:self.recv_offsets[q + 1]], q, self.group))
+            if self.send_rows[q].numel():
+                buf = self.gather(local_rows, self.send_rows[q])
+                keep.append(buf)
+                ops.append(dist.P2POp(dist.isend, buf, q, self.group))
+        works = dist.batch_isend_irecv(ops) if ops else []
+        return halo, (works, keep)
+
+    @staticmethod
+    def finish(handle) -> None:
+        works, _keep = handle
+        for w in works:
+            w.wait()
+
+    def forward(self, local_rows: Tensor) -> Tensor:
+        halo, handle = self.start_forward(local_rows)
+        self.finish(handle)
+        return halo
+
+    def reverse(self, halo_partial: Tensor, into: Tensor) -> Tensor:
+        width = halo_partial.size(1)
+        ops, recv = [], {}
+        for q in self._peers():
+            if self.send_rows[q].numel():          # rows I own that q used: q sends me its partial sums
+                recv[q] = torch.empty((self.send_rows[q].numel(), width), dtype=into.dtype, device=into.device)
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, self.group))
+            if self.part.recv_counts[q]:
+                seg = halo_partial[self.recv_offsets[q]:self.recv_offsets[q + 1]].contiguous()
+                ops.append(dist.P2POp(dist.isend, seg, q, self.group))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        for q in sorted(recv):                     # fixed order: deterministic sums
+            self.scatter_add(into, self.send_rows[q], recv[q])
+        return into
+
+    # -- overridable data movers ------------------------------------------------------------
+    def gather(self, rows: Tensor, index: Tensor) -> Tensor:
+        return rows.index_select(0, index)
+
+    def scatter_add(self, into: Tensor, index: Tensor, src: Tensor) -> None:
+        into.index_add_(0, index, src)             # index is unique per peer: no intra-call conflicts
+
+
+class CudaHaloExchange(HaloExchange):
+    """HaloExchange whose packing runs through libegc_b200 (egc_gather_rows)."""
+
+    def __init__(self, part: LocalPartition, device, group=None):
+        super().__init__(part, device, group)
+        self.send_rows32 = [t.to(torch.int32) for t in self.send_rows]
+
+    def gather(self, rows: Tensor, index: Tensor) -> Tensor:
+        from . import _lib
+        from .graph import _stream
+        q = next(i for i, t in enumerate(self.send_rows) if t is index)
+        idx = self.send_rows32[q]
+        out = torch.empty((idx.numel(), rows.size(1)), dtype=rows.dtype, device=rows.device)
+        _lib.check(_lib.load().egc_gather_rows(_lib.ptr(rows), _lib.ptr(idx), idx.numel(), rows.size(1), _lib.ptr(out),
+                                               _stream()), "egc_gather_rows")
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CUDA binding
+# ---------------------------------------------------------------------------------------------------
+class PartitionedGraph:
+    """Device-side state of one rank: the rectangular local CSR ([own rows] x [own | halo] columns), the
+    interior / boundary row split and the halo exchange."""
+
+    def __init__(self, part: LocalPartition, device, group=None):
+        from .graph import GraphStructure
+        self.part = part
+        self.device = torch.device(device)
+        self.graph = GraphStructure.from_prepared(part.rowptr, part.col, part.n_local + part.n_halo,
+                                                  val_sym=part.val_sym, val_lin=part.val_lin, device=self.device)
+        self.exchange = CudaHaloExchange(part, self.device, group)
+        self.interior = part.interior_rows.to(self.device, torch.int32)
+        self.boundary = part.boundary_rows.to(self.device, torch.int32)
+        self.group = group
+
+    @staticmethod
+    def from_global(graph, rank: int, world_size: int, device, group=None) -> "PartitionedGraph":
+        """Partition a prepared single-device `GraphStructure` (every rank builds the same plan)."""
+        plan = PartitionPlan(graph.rowptr.cpu(), graph.col.cpu(), world_size,
+                             val_sym=graph.val_sym.cpu() if graph.val_sym is not None else None,
+                             val_lin=graph.val_lin.cpu() if graph.val_lin is not None else None)
+        return PartitionedGraph(plan.local(rank), device, group)
+
+
+class _PartitionedEGConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, pg, heads, num_bases, aggrs, sigmoid, algo):
+        from . import functional as F
+        part, g = pg.part, pg.graph
+        x = F._require_cuda_f32("x", x)
+        bd = bases_weight.size(1)
+        desc = F.make_desc(g, heads, num_bases, bd // num_bases, aggrs, sigmoid)
+        needs_grad = any(ctx.needs_input_grad[:5])
+        with torch.cuda.device(x.device):
+            bases_ext = torch.empty((part.n_local + part.n_halo, bd), dtype=torch.float32, device=x.device)
+            _, weightings = F.project(x, bases_weight.contiguous(), comb_weight.contiguous(), comb_bias, sigmoid, algo,
+                                      bases_out=bases_ext[:part.n_local])
+            # halo exchange runs on the communication stream while interior rows are aggregated here
+            halo, handle = pg.exchange.start_forward(bases_ext[:part.n_local])
+            outs = F.alloc_aggregate_outputs(desc, x.device, want_out=True, want_saved=needs_grad)
+            F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
+                                outputs=outs)
+            pg.exchange.finish(handle)
+            bases_ext[part.n_local:].copy_(halo)
+            F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.boundary, use_plan=True,
+                                outputs=outs)
+        out, _, _, saved, saved_arg = outs
+        if needs_grad:
+            ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg)
+        ctx.pg, ctx.desc, ctx.algo = pg, desc, algo
+        ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import functional as F
+        x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg = ctx.saved_tensors
+        pg, part = ctx.pg, ctx.pg.part
+        grad_out = F._require_cuda_f32("grad_out", grad_out)
+        need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
+        with torch.cuda.device(x.device):
+            d_w, d_bases_ext, d_bias = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
+                                                            grad_out, need_b and ctx.has_bias)
+            d_bases = d_bases_ext[:part.n_local]
+            pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
+            d_x, d_wb, d_wc, d_bc = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
+                                                       d_w, need_x, need_wb, need_wc, need_bc and ctx.has_comb_bias,
+                                                       ctx.algo)
+            for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
+                if t is not None:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)
+        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None
+
+
+def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv) -> Tensor:
+    """Run `conv` (an `egc_b200.EGConv` with replicated parameters) on this rank's rows of a partitioned graph.
+    Output rows / input gradients are local; parameter gradients are all-reduced (= single-GPU values)."""
+    return _PartitionedEGConvFunction.apply(x_local, conv.bases_weight, conv.comb_weight.weight, conv.comb_weight.bias,
+                                            conv.bias, pg, conv.num_heads, conv.num_bases, tuple(conv.aggregators),
+                                            bool(conv.sigmoid), int(conv.gemm_algo))

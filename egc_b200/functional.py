@@ -42,12 +42,13 @@ def _require_cuda_f32(name: str, t: Optional[Tensor]) -> Optional[Tensor]:
 
 
 def project(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor], sigmoid: bool,
-            algo: int = _lib.GEMM_AUTO):
-    """bases = x @ W_b ; weightings = act(x @ W_c^T + b_c)   (ref :180-184)"""
+            algo: int = _lib.GEMM_AUTO, bases_out: Optional[Tensor] = None):
+    """bases = x @ W_b ; weightings = act(x @ W_c^T + b_c)   (ref :180-184).  `bases_out` lets a caller
+    provide the (row-prefix of a larger) buffer the basis rows are written to."""
     lib = _lib.load()
     n, f_in = x.shape
     bd, hab = bases_weight.shape[1], comb_weight.shape[0]
-    bases = torch.empty((n, bd), dtype=torch.float32, device=x.device)
+    bases = bases_out if bases_out is not None else torch.empty((n, bd), dtype=torch.float32, device=x.device)
     weightings = torch.empty((n, hab), dtype=torch.float32, device=x.device)
     if n > 0:
         check(lib.egc_project_fwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(comb_bias), n, f_in, bd, hab,
@@ -55,29 +56,82 @@ def project(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Opt
     return bases, weightings
 
 
-def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Optional[Tensor],
-                      bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False,
-                      want_saved: bool = False):
-    """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg, saved, saved_arg); unrequested ones
-    are None.  `saved` / `saved_arg` are what the backward pass consumes (see include/egc_b200.h)."""
+def alloc_aggregate_outputs(desc: LayerDesc, device, want_out=True, want_agg=False, want_arg=False, want_saved=False):
     lib = _lib.load()
-    dev = bases.device
     n, bd, hd = desc.n_dst, desc.bases * desc.dim, desc.heads * desc.dim
-    out = torch.empty((n, hd), dtype=torch.float32, device=dev) if want_out else None
-    agg = torch.empty((n, desc.n_aggr, bd), dtype=torch.float32, device=dev) if want_agg else None
-    arg = torch.empty((n, desc.n_aggr, bd), dtype=torch.int32, device=dev) if want_arg else None
+    out = torch.empty((n, hd), dtype=torch.float32, device=device) if want_out else None
+    agg = torch.empty((n, desc.n_aggr, bd), dtype=torch.float32, device=device) if want_agg else None
+    arg = torch.empty((n, desc.n_aggr, bd), dtype=torch.int32, device=device) if want_arg else None
     saved = saved_arg = None
     if want_saved:
-        saved = torch.empty((n, lib.egc_saved_slots(desc), bd), dtype=torch.float32, device=dev)
+        saved = torch.empty((n, lib.egc_saved_slots(desc), bd), dtype=torch.float32, device=device)
         n_arg = lib.egc_saved_arg_slots(desc)
-        saved_arg = torch.empty((n, n_arg, bd), dtype=torch.int32, device=dev) if n_arg else None
-    plan = graph.plan.struct
+        saved_arg = torch.empty((n, n_arg, bd), dtype=torch.int32, device=device) if n_arg else None
+    return out, agg, arg, saved, saved_arg
+
+
+def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Optional[Tensor],
+                      bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False,
+                      want_saved: bool = False, row_subset: Optional[Tensor] = None, use_plan: bool = True,
+                      outputs=None):
+    """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg, saved, saved_arg); unrequested ones
+    are None.  `saved` / `saved_arg` are what the backward pass consumes (see include/egc_b200.h).
+    `row_subset` (int32 device tensor) restricts the row tasks; `outputs` reuses buffers of a previous call."""
+    lib = _lib.load()
+    dev = bases.device
+    if outputs is None:
+        outputs = alloc_aggregate_outputs(desc, dev, want_out, want_agg, want_arg, want_saved)
+    out, agg, arg, saved, saved_arg = outputs
+    plan = graph.plan.struct if use_plan else None
     nbytes = lib.egc_aggregate_fwd_workspace_bytes(desc, plan)
     ws = _ws(nbytes, dev)
+    n_subset = int(row_subset.numel()) if row_subset is not None else 0
+    if row_subset is not None and n_subset == 0 and not (use_plan and graph.plan.n_long):
+        return outputs
     check(lib.egc_aggregate_fwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin), plan,
-                                ptr(bases), ptr(weightings), ptr(bias), ptr(out), ptr(agg), ptr(arg), ptr(saved),
-                                ptr(saved_arg), ptr(ws), nbytes, _stream()), "egc_aggregate_fwd")
-    return out, agg, arg, saved, saved_arg
+                                ptr(bases), ptr(weightings), ptr(bias), ptr(row_subset) if n_subset else None, n_subset,
+                                ptr(out), ptr(agg), ptr(arg), ptr(saved), ptr(saved_arg), ptr(ws), nbytes, _stream()),
+          "egc_aggregate_fwd")
+    return outputs
+
+
+def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Tensor, saved: Tensor,
+                       saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0):
+    """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None)."""
+    lib = _lib.load()
+    dev = bases.device
+    graph.ensure_csc()
+    bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
+    d_w = torch.empty((desc.n_dst, hab), dtype=torch.float32, device=dev)
+    d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev)
+    d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if want_bias else None
+    nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
+    ws = _ws(nbytes, dev)
+    check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
+                                ptr(graph.rowidx), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
+                                graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
+                                ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), flags, ptr(ws), nbytes, _stream()),
+          "egc_aggregate_bwd")
+    return d_w, d_bases, d_bias
+
+
+def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bases: Tensor, d_lin: Tensor,
+                     need_x: bool, need_wb: bool, need_wc: bool, need_bc: bool, algo: int = _lib.GEMM_AUTO):
+    """Autograd of `project`: returns (d_x, d_bases_weight, d_comb_weight, d_comb_bias), None where not needed."""
+    lib = _lib.load()
+    dev = x.device
+    n, f_in = x.shape
+    bd, hab = bases_weight.shape[1], comb_weight.shape[0]
+    d_x = torch.empty_like(x) if need_x else None
+    d_wb = torch.empty_like(bases_weight) if need_wb else None
+    d_wc = torch.empty_like(comb_weight) if need_wc else None
+    d_bc = torch.empty(hab, dtype=torch.float32, device=dev) if need_bc else None
+    nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
+    ws = _ws(nbytes, dev)
+    check(lib.egc_project_bwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(d_bases), ptr(d_lin), n, f_in, bd, hab,
+                              ptr(d_x), ptr(d_wb), ptr(d_wc), ptr(d_bc), algo, ptr(ws), nbytes, _stream()),
+          "egc_project_bwd")
+    return d_x, d_wb, d_wc, d_bc
 
 
 class _EGConvFunction(torch.autograd.Function):
@@ -107,35 +161,13 @@ class _EGConvFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, bases_weight, comb_weight, bases, weightings, saved, saved_arg = ctx.saved_tensors
-        graph, desc = ctx.graph, ctx.desc
-        lib = _lib.load()
-        dev = x.device
         grad_out = _require_cuda_f32("grad_out", grad_out)
-        n, f_in = x.shape
-        bd, hab = bases_weight.shape[1], comb_weight.shape[0]
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
-        with torch.cuda.device(dev):
-            graph.ensure_csc()
-            d_w = torch.empty((n, hab), dtype=torch.float32, device=dev)
-            d_bases = torch.empty((graph.n_src, bd), dtype=torch.float32, device=dev)
-            d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if (need_b and ctx.has_bias) else None
-            nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, ctx.bwd_flags)
-            ws = _ws(nbytes, dev)
-            check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
-                                        ptr(graph.rowidx), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
-                                        graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
-                                        ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ctx.bwd_flags, ptr(ws),
-                                        nbytes, _stream()), "egc_aggregate_bwd")
-            del ws
-            d_x = torch.empty_like(x) if need_x else None
-            d_wb = torch.empty_like(bases_weight) if need_wb else None
-            d_wc = torch.empty_like(comb_weight) if need_wc else None
-            d_bc = torch.empty(hab, dtype=torch.float32, device=dev) if (need_bc and ctx.has_comb_bias) else None
-            nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
-            ws = _ws(nbytes, dev)
-            check(lib.egc_project_bwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(d_bases), ptr(d_w), n, f_in, bd,
-                                      hab, ptr(d_x), ptr(d_wb), ptr(d_wc), ptr(d_bc), ctx.algo, ptr(ws), nbytes,
-                                      _stream()), "egc_project_bwd")
+        with torch.cuda.device(x.device):
+            d_w, d_bases, d_bias = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg, grad_out,
+                                                      need_b and ctx.has_bias, ctx.bwd_flags)
+            d_x, d_wb, d_wc, d_bc = project_backward(x, bases_weight, comb_weight, d_bases, d_w, need_x, need_wb,
+                                                     need_wc, need_bc and ctx.has_comb_bias, ctx.algo)
         return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None
 
 

@@ -232,6 +232,32 @@ class GraphStructure:
             g._finish(meta, col_cap, val_cap, symnorm, keep_values=not symnorm)
         return g
 
+    @staticmethod
+    def from_prepared(rowptr: Tensor, col: Tensor, n_src: int, val_sym: Optional[Tensor] = None,
+                      val_lin: Optional[Tensor] = None, device=None) -> "GraphStructure":
+        """Adopt an already prepared CSR (self-loops and weights decided elsewhere, e.g. the local
+        block of a row-partitioned graph whose column ids live in the [own | halo] space)."""
+        dev = torch.device(device) if device is not None else col.device
+        if dev.type != "cuda":
+            raise RuntimeError("egc_b200: graphs live on a CUDA device (there is no CPU path)")
+        lib = _lib.load()
+        rowptr64, col64 = rowptr.to(dev).long().contiguous(), col.to(dev).long().contiguous()
+        n_dst, nnz = rowptr64.numel() - 1, col64.numel()
+        g = GraphStructure()
+        g.n_dst, g.n_src = int(n_dst), int(n_src)
+        g.rowptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+        col_cap = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        meta = torch.empty(_lib.META_SLOTS, dtype=torch.int32, device=dev)
+        nbytes = lib.egc_csr_fill_diag_workspace_bytes(n_dst)
+        ws = _ws(nbytes, dev)
+        with torch.cuda.device(dev):
+            check(lib.egc_csr_fill_diag(ptr(rowptr64), ptr(col64), None, n_dst, n_src, 0, ptr(g.rowptr), ptr(col_cap),
+                                        None, ptr(meta), ptr(ws), nbytes, _stream()), "egc_csr_fill_diag")
+            g._finish(meta, col_cap, None, symnorm=False, keep_values=False)
+        g.val_sym = val_sym.to(dev, torch.float32).contiguous() if val_sym is not None else None
+        g.val_lin = val_lin.to(dev, torch.float32).contiguous() if val_lin is not None else None
+        return g
+
     def _finish(self, meta: Tensor, col_cap: Tensor, val_cap: Optional[Tensor], symnorm: bool, keep_values: bool):
         lib = _lib.load()
         m = meta.cpu().tolist()                    # the one host sync of graph preparation

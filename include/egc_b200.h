@@ -186,7 +186,10 @@ int egc_project_bwd(const float* x, const float* w_bases, const float* w_comb,
  * val_sym: per-nnz weights for symnorm (required iff symnorm is requested).
  * val_lin: per-nnz weights applied by every other aggregator (NULL = unweighted; only a valued
  *          SparseTensor without symnorm produces them, ref :256-258).
- * bias may be NULL.  Every output is optional (NULL to skip), at least one must be given:
+ * bias may be NULL.  row_subset (may be NULL = all rows): only these rows (of at most EGC_CHUNK_EDGES nnz) are
+ * computed as row tasks - a row-partitioned caller aggregates interior rows while the halo exchange is in
+ * flight and the boundary rows afterwards; the long rows of `plan` are processed whenever plan != NULL.
+ * Every output is optional (NULL to skip), at least one must be given:
  *   out[n_dst, H*D]           the layer output (needs weightings)
  *   agg_out[n_dst, A, B*D]    the aggregated bases before combination (ref :249 / :278)
  *   arg_out[n_dst, A, B*D]    int32 nnz position of the winning element for min/max slots (-1: empty row,
@@ -200,6 +203,7 @@ size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
                       const float* val_sym, const float* val_lin, const egc_row_plan* plan,
                       const float* bases, const float* weightings, const float* bias,
+                      const int32_t* row_subset, int32_t n_subset,
                       float* out, float* agg_out, int32_t* arg_out, float* saved, int32_t* saved_arg,
                       void* workspace, size_t workspace_bytes, void* stream);
 

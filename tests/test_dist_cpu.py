@@ -1,0 +1,116 @@
+"""Row-partition + halo-exchange logic on CPU with world_size = 2 (gloo).  The compute on each rank is the
+CPU oracle (test infrastructure), so what is checked is exactly the product's index / communication
+plumbing (`egc_b200.dist.PartitionPlan`, `HaloExchange`): partitioned result == single-process result."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from egc_b200.dist import HaloExchange, PartitionPlan, balanced_row_bounds
+from oracle import restatement as R
+from tests.util import random_graph, rel_err
+
+AGGRS = ["symnorm", "max", "std", "mean"]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _single_process(n, ei, x, go, seed):
+    torch.manual_seed(seed)
+    layer = R.EGConvOracle(12, 32, aggrs=AGGRS, num_heads=4, num_bases=4).double()
+    g = layer.prepare(x, ei)
+    xx = x.clone().requires_grad_(True)
+    out = layer(xx, ei)
+    grads = torch.autograd.grad(out, [xx] + list(layer.parameters()), go)
+    return layer, g, out.detach(), grads
+
+
+def _worker(rank, world, port, n, ei, x, go, seed, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        layer, g, out_ref, grads_ref = _single_process(n, ei, x, go, seed)
+        plan = PartitionPlan(g.rowptr, g.col, world, val_sym=g.val_sym)
+        part = plan.local(rank)
+        ex = HaloExchange(part, "cpu")
+        b, e = part.row_begin, part.row_end
+        x_loc = x[b:e].clone().requires_grad_(True)
+        # forward: local projection, halo exchange of basis rows, aggregation over [own | halo]
+        bases_loc, w_loc = R.project(x_loc, layer.bases_weight, layer.comb_weight.weight, layer.comb_weight.bias)
+        halo = ex.forward(bases_loc.detach())
+        assert torch.equal(halo, (x @ layer.bases_weight.detach())[part.halo_ids])
+        halo = halo.requires_grad_(True)
+        local_graph = R.OracleGraph(part.rowptr, part.col, part.n_local, part.n_local + part.n_halo, val_sym=part.val_sym)
+        agg, _ = R.aggregate(local_graph, torch.cat([bases_loc, halo]), AGGRS)
+        out_loc = R.combine(w_loc, agg, layer.bias, 4)
+        assert rel_err(out_loc, out_ref[b:e]) < 1e-12
+        # backward: local autograd gives partial sums for halo sources; they travel back to the owners
+        params = list(layer.parameters())
+        grads = torch.autograd.grad(out_loc, [x_loc, halo, bases_loc] + params, go[b:e], allow_unused=True,
+                                    retain_graph=True)
+        d_halo = grads[1]
+        extra = torch.zeros_like(bases_loc)
+        ex.reverse(d_halo, extra)                                        # contributions from the other rank
+        d_x_extra, *d_par_extra = torch.autograd.grad(bases_loc, [x_loc] + params, extra, allow_unused=True)
+        d_x = grads[0] + d_x_extra
+        assert rel_err(d_x, grads_ref[0][b:e]) < 1e-11
+        for gp, ge, gr in zip(grads[3:], d_par_extra, grads_ref[1:]):
+            tot = gp + (ge if ge is not None else 0)
+            dist.all_reduce(tot)
+            assert rel_err(tot, gr) < 1e-11
+        # interior rows only touch local sources
+        rows = torch.repeat_interleave(torch.arange(part.n_local), part.rowptr[1:] - part.rowptr[:-1])
+        touched = torch.zeros(part.n_local, dtype=torch.bool)
+        touched[rows[part.col >= part.n_local]] = True
+        assert torch.equal(torch.nonzero(~touched).flatten(), part.interior_rows)
+        assert part.interior_rows.numel() + part.boundary_rows.numel() == part.n_local
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_layer_matches_single_process_gloo_world2():
+    torch.manual_seed(0)
+    n = 240
+    ei = random_graph(n, 1500, seed=5, hub=90)
+    # add locality so that interior rows exist
+    blk = torch.randint(0, n // 2, (2, 600))
+    ei = torch.cat([ei, blk, blk + n // 2], 1)
+    x = torch.randn(n, 12, dtype=torch.float64)
+    go = torch.randn(n, 32, dtype=torch.float64)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n, ei, x, go, 3, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_partition_plan_invariants(world):
+    n = 500
+    ei = random_graph(n, 4000, seed=9, hub=300)
+    g = R.graph_from_edge_index(ei, n, True, True)
+    plan = PartitionPlan(g.rowptr, g.col, world, val_sym=g.val_sym)
+    assert plan.bounds[0] == 0 and plan.bounds[-1] == n and sorted(plan.bounds) == plan.bounds
+    nnz = [int(g.rowptr[plan.bounds[r + 1]] - g.rowptr[plan.bounds[r]]) for r in range(world)]
+    assert max(nnz) <= g.nnz / world + int((g.rowptr[1:] - g.rowptr[:-1]).max()) + n     # balanced up to one row
+    total_rows = 0
+    for r in range(world):
+        part = plan.local(r)
+        total_rows += part.n_local
+        ext = torch.cat([torch.arange(part.row_begin, part.row_end), part.halo_ids])
+        lo, hi = int(g.rowptr[part.row_begin]), int(g.rowptr[part.row_end])
+        assert torch.equal(ext[part.col], g.col[lo:hi])                 # remapped columns point at the same nodes
+        assert torch.equal(part.val_sym, g.val_sym[lo:hi])
+        assert sum(part.recv_counts) == part.n_halo and part.recv_counts[r] == 0
+        for q in range(world):                                          # what q sends me is what I asked of q
+            assert torch.equal(plan.local(q).send_rows[r] + plan.bounds[q], plan._needs[r][q])
+    assert total_rows == n
+    assert balanced_row_bounds(g.rowptr, 1) == [0, n]
