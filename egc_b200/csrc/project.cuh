@@ -23,4 +23,10 @@ int project_bwd_tc(const float* x, const float* w_bases, const float* w_comb, co
                    int n, int f_in, int bd, int hab, float* d_x, float* d_w_bases, float* d_w_comb, float* d_b_comb,
                    int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+// tensor-core parameter gradients (wgrad_tc.cu): dW_b = x^T d_bases, dW_c = d_lin^T x
+bool wgrad_tc_supported(int n, int f_in, int bd, int hab);
+size_t wgrad_tc_workspace(int n, int f_in, int bd, int hab);
+int wgrad_tc(const float* x, const float* d_bases, const float* d_lin, int n, int f_in, int bd, int hab,
+             float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace egc

@@ -38,4 +38,12 @@ for (n, f_in, bd, hab) in [(128, 128, 128, 48), (1000, 128, 128, 48), (169343, 1
         torch.cuda.synchronize()
         e3 = rel(outs[0], d_bases.double() @ wb.double().t() + d_lin.double() @ wc.double())
         e4 = rel(outs[1], x.double().t() @ d_bases.double())
-        print(f"n={n:7d} f_in={f_in} bd={bd} hab={hab} {name:7s} bases {e1:.2e} w {e2:.2e} d_x {e3:.2e} dWb {e4:.2e}  fwd {t0.elapsed_time(t1)/10*1e3:8.1f} us", flush=True)
+        e5 = rel(outs[2], d_lin.double().t() @ x.double())
+        e6 = rel(outs[3], d_lin.double().sum(0))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            _lib.check(lib.egc_project_bwd(*[P(t) for t in ins], n, f_in, bd, hab, *[P(t) for t in outs], algo, P(ws), nbytes,
+                                           torch.cuda.current_stream().cuda_stream))
+        b1.record(); torch.cuda.synchronize()
+        print(f"n={n:7d} f_in={f_in} bd={bd} hab={hab} {name:7s} bases {e1:.1e} w {e2:.1e} d_x {e3:.1e} dWb {e4:.1e} dWc {e5:.1e} dbc {e6:.1e} fwd {t0.elapsed_time(t1)/10*1e3:7.1f} us bwd {b0.elapsed_time(b1)/10*1e3:7.1f} us", flush=True)
