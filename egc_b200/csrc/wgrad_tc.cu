@@ -1,16 +1,14 @@
 // tcgen05 parameter-gradient GEMM for sm_100a:  C[F_in, BD + HAB] = x^T . [d_bases | d_lin]
 // (dW_b = x^T d_bases, dW_c^T = x^T d_lin; ref: autograd of optimized_layers.py:180-182).
 //
-// The contraction runs over the NODE dimension, so both operands stream and both are MN-major
-// (features contiguous in memory).  Each persistent CTA owns a contiguous range of 16-node chunks,
-// accumulates one 128 x N_pad fp32 tile in TMEM with kind::tf32 MMAs (3-term hi/lo split), and
-// writes its partial tile to the workspace; a small deterministic kernel reduces the partials and
-// scatters them into dW_b / dW_c (transposing the latter).
-//
-// Shared-memory layout = canonical no-swizzle MN-major UMMA layout: core matrix = 8 K-rows (nodes)
-// x 16 bytes (4 consecutive features), 128 B contiguous; SBO = 128 B between feature quads,
-// LBO = bytes between 8-node groups.  Producers map lane -> (node%8, quad%4) so that one warp
-// instruction reads 8 x 64 B contiguous global segments and writes 512 contiguous shared bytes.
+// The contraction runs over the NODE dimension, so both operands stream and both are feature-contiguous
+// in memory (MN-major).  kind::tf32 MMAs with no-swizzle descriptors only accept K-major operands on
+// this part (tools/umma_probe.cu: the MN-major bits yield zeros), so the producers transpose on the
+// fly: lane -> (node%4, feature%8) reads 4 x 32 B global sectors per warp instruction and writes 128
+// contiguous shared bytes (conflict-free) of the canonical K-major layout (8 rows x 16 B core matrices).
+// Each persistent CTA owns a contiguous range of 16-node chunks, accumulates one 128 x N_pad fp32
+// tile in TMEM (3-term hi/lo split) and writes its partial tile to the workspace; a small
+// deterministic kernel reduces the partials into dW_b / dW_c (transposing the latter).
 #include <algorithm>
 
 #include "project.cuh"
@@ -22,6 +20,7 @@ constexpr int kWgThreads = 288;          // warps 0-3 epilogue, 4 MMA, 5-8 produ
 constexpr int kWgChunk = 16;             // nodes per chunk (2 UMMA k-steps)
 constexpr int kWgM = 128;                // feature rows of the accumulator tile (F_in padded)
 constexpr int kWgMaxSmem = 227 * 1024;
+constexpr int kMaxSlots = 40;            // register-prefetched scalars per producer thread and chunk
 
 struct WgParams {
   const float* x; int f_in;              // A^T source: x[n, f_in]
@@ -41,7 +40,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   const uint32_t a_half = kWgM * kWgChunk * 4;                       // 8 KB: hi (or lo) of an A chunk
   const uint32_t b_half = static_cast<uint32_t>(p.n_pad) * kWgChunk * 4;
   const uint32_t stage_bytes = 2 * (a_half + b_half);
-  const uint32_t a_lbo = (kWgM / 4) * 128, b_lbo = static_cast<uint32_t>(p.n_pad / 4) * 128;   // per 8-node group
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
   // bars: [0,S) full, [S,2S) empty, [2S] accumulator done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
@@ -64,35 +62,35 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   const int c_begin = blockIdx.x * p.chunks_per_cta;
   const int c_end = min(c_begin + p.chunks_per_cta, p.chunks_total);
   const int n_chunks = max(c_end - c_begin, 0);
-  const int a_units = kWgM / 4, b_units = p.n_pad / 4;
-  const int a_slots = 2 * (a_units / 4), b_slots = 2 * ((b_units + 3) / 4);    // warp-instruction slots per chunk
+  const uint32_t a_lbo = kWgM * 16, b_lbo = static_cast<uint32_t>(p.n_pad) * 16;   // bytes between 4-node K pieces
+  constexpr int kASlots = 4 * (kWgM / 8);                   // (K piece, 8-feature group) pairs of A per chunk
+  const int b_groups = p.n_pad / 8;
+  const int n_slots = kASlots + 4 * b_groups;               // <= kMaxSlots * 4
 
   if (warp >= 5) {
-    // ================= producers =================
+    // ================= producers: transposing stage-in =================
     const int pw = warp - 5;
-    const int kk = lane & 7, uq = lane >> 3;           // node within the 8-group, quad within the 4-quad block
+    const int kk = lane & 3, mm = lane >> 2;                // node within the 4-piece, feature within the 8-group
     int stage = 0;
     uint32_t phase = 0;
     for (int c = c_begin; c < c_end; ++c) {
       const int node0 = c * kWgChunk;
-      // issue this chunk's loads before waiting for the slot (register prefetch)
-      float4 v[10];
-      const int n_slots = a_slots + b_slots;
+      float v[kMaxSlots];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
+      for (int i = 0; i < kMaxSlots; ++i) {
         const int slot = pw + 4 * i;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (slot < a_slots) {
-          const int kg = slot / (a_units / 4), ub = slot - kg * (a_units / 4);
-          const int node = node0 + kg * 8 + kk, f = (ub * 4 + uq) * 4;
-          if (node < p.n_nodes && f < p.f_in) t = __ldcs(reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(node) * p.f_in + f));
+        float t = 0.f;
+        if (slot < kASlots) {
+          const int piece = slot / (kWgM / 8), grp = slot - piece * (kWgM / 8);
+          const int node = node0 + piece * 4 + kk, f = grp * 8 + mm;
+          if (node < p.n_nodes && f < p.f_in) t = __ldcs(p.x + static_cast<int64_t>(node) * p.f_in + f);
         } else if (slot < n_slots) {
-          const int s2 = slot - a_slots, per = (b_units + 3) / 4;
-          const int kg = s2 / per, ub = s2 - kg * per;
-          const int node = node0 + kg * 8 + kk, u = ub * 4 + uq, col = u * 4;
-          if (node < p.n_nodes && u < b_units) {
-            if (col < p.n1) t = __ldcs(reinterpret_cast<const float4*>(p.d1 + static_cast<int64_t>(node) * p.n1 + col));
-            else if (col < p.n1 + p.n2) t = __ldcs(reinterpret_cast<const float4*>(p.d2 + static_cast<int64_t>(node) * p.n2 + (col - p.n1)));
+          const int s2 = slot - kASlots;
+          const int piece = s2 / b_groups, grp = s2 - piece * b_groups;
+          const int node = node0 + piece * 4 + kk, col = grp * 8 + mm;
+          if (node < p.n_nodes) {
+            if (col < p.n1) t = __ldcs(p.d1 + static_cast<int64_t>(node) * p.n1 + col);
+            else if (col < p.n1 + p.n2) t = __ldcs(p.d2 + static_cast<int64_t>(node) * p.n2 + (col - p.n1));
           }
         }
         v[i] = t;
@@ -100,24 +98,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
       mbar_wait(empty_bar(stage), phase ^ 1u);
       uint8_t* st_base = smem + static_cast<size_t>(stage) * stage_bytes;
 #pragma unroll
-      for (int i = 0; i < 10; ++i) {
+      for (int i = 0; i < kMaxSlots; ++i) {
         const int slot = pw + 4 * i;
-        const float4 t = v[i];
-        const float4 h = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
-        const float4 l = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
-        if (slot < a_slots) {
-          const int kg = slot / (a_units / 4), ub = slot - kg * (a_units / 4);
-          const uint32_t off = kg * a_lbo + (ub * 4 + uq) * 128 + kk * 16;
-          *reinterpret_cast<float4*>(st_base + off) = h;
-          *reinterpret_cast<float4*>(st_base + a_half + off) = l;
+        const float h = tf32_hi(v[i]), l = v[i] - h;
+        if (slot < kASlots) {
+          const int piece = slot / (kWgM / 8), grp = slot - piece * (kWgM / 8);
+          const uint32_t off = piece * a_lbo + (grp * 8 + mm) * 16 + kk * 4;
+          *reinterpret_cast<float*>(st_base + off) = h;
+          *reinterpret_cast<float*>(st_base + a_half + off) = l;
         } else if (slot < n_slots) {
-          const int s2 = slot - a_slots, per = (b_units + 3) / 4;
-          const int kg = s2 / per, ub = s2 - kg * per, u = ub * 4 + uq;
-          if (u < b_units) {
-            const uint32_t off = 2 * a_half + kg * b_lbo + u * 128 + kk * 16;
-            *reinterpret_cast<float4*>(st_base + off) = h;
-            *reinterpret_cast<float4*>(st_base + b_half + off) = l;
-          }
+          const int s2 = slot - kASlots;
+          const int piece = s2 / b_groups, grp = s2 - piece * b_groups;
+          const uint32_t off = 2 * a_half + piece * b_lbo + (grp * 8 + mm) * 16 + kk * 4;
+          *reinterpret_cast<float*>(st_base + off) = h;
+          *reinterpret_cast<float*>(st_base + b_half + off) = l;
         }
       }
       fence_proxy_async();
@@ -127,8 +121,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             (static_cast<uint32_t>(p.n_pad >> 3) << 17) | (static_cast<uint32_t>(kWgM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
+                             (static_cast<uint32_t>(kWgM >> 4) << 24);
       const uint32_t base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
@@ -139,12 +133,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
         const uint32_t b_hi = a_hi + 2 * a_half, b_lo = b_hi + b_half;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          const uint64_t da_hi = make_desc(a_hi + s * a_lbo, a_lbo, 128);
-          const uint64_t db_hi = make_desc(b_hi + s * b_lbo, b_lbo, 128);
+          const uint64_t da_hi = make_desc(a_hi + s * 2 * a_lbo, a_lbo, 128);
+          const uint64_t db_hi = make_desc(b_hi + s * 2 * b_lbo, b_lbo, 128);
           umma_tf32(tmem_base, da_hi, db_hi, idesc, (c | s) != 0 ? 1u : 0u);
           if (p.n_terms == 3) {
-            const uint64_t da_lo = make_desc(a_lo + s * a_lbo, a_lbo, 128);
-            const uint64_t db_lo = make_desc(b_lo + s * b_lbo, b_lbo, 128);
+            const uint64_t da_lo = make_desc(a_lo + s * 2 * a_lbo, a_lbo, 128);
+            const uint64_t db_lo = make_desc(b_lo + s * 2 * b_lbo, b_lbo, 128);
             umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
             umma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
           }
@@ -213,9 +207,8 @@ static int wgrad_stages(int n_pad) {
 bool wgrad_tc_supported(int n, int f_in, int bd, int hab) {
   if (n < 1 || f_in % 4 || bd % 4 || hab % 4 || f_in > kWgM) return false;
   const int n_pad = round16w(bd + hab);
-  // producer register prefetch holds at most 10 pieces per thread
-  const int slots = 2 * (kWgM / 16) + 2 * ((n_pad / 4 + 3) / 4);
-  return n_pad <= 256 && wgrad_stages(n_pad) >= 2 && (slots + 3) / 4 <= 10;
+  const int slots = 4 * (kWgM / 8) + 4 * (n_pad / 8);      // producer register prefetch: kMaxSlots scalars per thread
+  return n_pad <= 256 && wgrad_stages(n_pad) >= 2 && (slots + 3) / 4 <= kMaxSlots;
 }
 
 size_t wgrad_tc_workspace(int n, int f_in, int bd, int hab) {
