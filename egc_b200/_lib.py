@@ -10,6 +10,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libegc_b200.so")
 
+ABI_VERSION = 2
 EGC_MAX_AGGR = 8
 EGC_CHUNK_EDGES = 256
 META_SLOTS = 8
@@ -63,7 +64,7 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
-                                    _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
+                                    _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
 }
 
@@ -101,8 +102,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)     # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.egc_abi_version() != 1:
-        raise ImportError(f"libegc_b200 ABI {lib.egc_abi_version()} != 1 expected by the Python host code")
+    if lib.egc_abi_version() != ABI_VERSION:
+        raise ImportError(f"libegc_b200 ABI {lib.egc_abi_version()} != {ABI_VERSION} expected by the Python host code")
     _lib = lib
     return lib
 

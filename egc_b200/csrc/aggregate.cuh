@@ -375,5 +375,8 @@ int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4);
 // launchers (one translation unit per VEC/ARG combination to keep compile times parallel)
 int launch_aggregate_v4(const AggParams& p, int mask, bool linw, bool arg, int smem_bytes, cudaStream_t st);
 int launch_aggregate_v1(const AggParams& p, int mask, bool linw, bool arg, int smem_bytes, cudaStream_t st);
+// fast path (aggregate_fast.cuh): vec4 rows of <= 128 floats, no per-nnz linear weights, mode 0 only
+int launch_aggregate_fast_g32(const AggParams& p, int mask, bool arg, int smem_bytes, cudaStream_t st);
+int launch_aggregate_fast_g16(const AggParams& p, int mask, bool arg, int smem_bytes, cudaStream_t st);
 
 }  // namespace egc

@@ -89,6 +89,8 @@ struct CombineBwdParams {
   int sigmoid;
   int sm_w, sm_g, sm_saved, sm_arg, sm_per_warp;
   int vec16;
+  int64_t ts_row_stride, ts_stream_stride;   // floats between the streams of consecutive rows / between streams of a row
+  float* colsum_part;                        // [grid][HD + HAB] or null
 };
 
 __device__ __forceinline__ void stage_row(float* dst, const float* src, int n, int lane, bool vec16) {
@@ -99,116 +101,214 @@ __device__ __forceinline__ void stage_row(float* dst, const float* src, int n, i
   }
 }
 
+constexpr int kCbColIt = 4;     // per-lane column-sum accumulators: HD <= 32 * EV * kCbColIt, HAB <= 32 * kCbColIt
+
+__device__ __forceinline__ void stg_stream_f4(float* p, const float (&v)[4]) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// Persistent warps (one target row per task).  Everything that does not depend on the row - the (head, slot)
+// decomposition of a weight index, the (basis, offset) of a feature, the aggregator of a slot - is computed
+// once per CTA into shared-memory tables.  The column sums of grad_out (d_bias) and of d_weightings (the
+// gradient of the comb-weight bias) ride along in registers and leave as one partial row per CTA
+// (deterministic: reduced in CTA order by k_colsum_partials).
 template <int EV, bool LINW>
-__global__ void __launch_bounds__(kAggThreads) k_combine_bwd(const __grid_constant__ CombineBwdParams p) {
+__global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_constant__ CombineBwdParams p) {
   extern __shared__ __align__(16) float smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kAggWarps + warp;
-  if (row >= p.n_rows) return;
-  float* sm = smem_all + warp * p.sm_per_warp;
-  const int D = p.D;
-  const bool v16 = p.vec16 != 0;
-  stage_row(sm + p.sm_w, p.weightings + static_cast<int64_t>(row) * p.HAB, p.HAB, lane, v16);
-  stage_row(sm + p.sm_g, p.grad_out + static_cast<int64_t>(row) * p.HD, p.HD, lane, v16);
-  stage_row(sm + p.sm_saved, p.saved + static_cast<int64_t>(row) * p.n_saved * p.BD, p.n_saved * p.BD, lane, v16);
-  if (p.n_arg > 0)
-    stage_row(sm + p.sm_arg, reinterpret_cast<const float*>(p.saved_arg) + static_cast<int64_t>(row) * p.n_arg * p.BD,
-              p.n_arg * p.BD, lane, v16);
-  const float cntf = static_cast<float>(max(p.rowptr[row + 1] - p.rowptr[row], 1));
-  cp_async_wait_all();
-  __syncwarp();
+  const int D = p.D, BD = p.BD, HD = p.HD, AB = p.AB, HAB = p.HAB;
+  // CTA-wide tables (ints) live behind the per-warp staging areas
+  int* tab_goff = reinterpret_cast<int*>(smem_all + kAggWarps * p.sm_per_warp);   // [HAB] h * D
+  int* tab_aoff = tab_goff + HAB;                                                  // [HAB] ab * D
+  int* tab_std = tab_aoff + HAB;                                                   // [HAB] slot belongs to a std aggregator
+  for (int t = threadIdx.x; t < HAB; t += kAggThreads) {
+    const int h = t / AB, ab = t - h * AB;
+    tab_goff[t] = h * D;
+    tab_aoff[t] = ab * D;
+    tab_std[t] = p.aggr[ab / p.B] == EGC_AGGR_STD ? 1 : 0;
+  }
+  __syncthreads();
 
+  float* sm = smem_all + warp * p.sm_per_warp;
+  const bool v16 = p.vec16 != 0;
   const float* w = sm + p.sm_w;
   const float* g = sm + p.sm_g;
   const float* sv = sm + p.sm_saved;
   const int* sarg = reinterpret_cast<const int*>(sm + p.sm_arg);
+  const int nq = D >> 2;
+  const int q0 = nq > 0 ? lane % nq : 0, dd0 = lane % D;
+  const int warps_total = gridDim.x * kAggWarps;
 
-  // (1) gradient of the combination weights: HAB dot products of length D, skewed start per lane
-  for (int t = lane; t < p.HAB; t += 32) {
-    const int h = t / p.AB, ab = t - h * p.AB;
-    const bool is_std = p.aggr[ab / p.B] == EGC_AGGR_STD;
-    const float* gh = g + h * D;
-    const float* aa = sv + ab * D;
-    float dot = 0.f;
-    if constexpr (EV == 4) {
-      const int nq = D >> 2;
-      int q = lane % nq;
-      for (int i = 0; i < nq; ++i) {
-        const float4 gv = *reinterpret_cast<const float4*>(gh + 4 * q);
-        float4 av = *reinterpret_cast<const float4*>(aa + 4 * q);
-        if (is_std) { av.x = fabsf(av.x); av.y = fabsf(av.y); av.z = fabsf(av.z); av.w = fabsf(av.w); }
-        dot = fmaf(gv.x, av.x, dot); dot = fmaf(gv.y, av.y, dot); dot = fmaf(gv.z, av.z, dot); dot = fmaf(gv.w, av.w, dot);
-        q = (q + 1 == nq) ? 0 : q + 1;
-      }
-    } else {
-      int dd = lane % D;
-      for (int i = 0; i < D; ++i) {
-        const float av = is_std ? fabsf(aa[dd]) : aa[dd];
-        dot = fmaf(gh[dd], av, dot);
-        dd = (dd + 1 == D) ? 0 : dd + 1;
-      }
-    }
-    if (p.sigmoid) { const float s = w[t]; dot *= s * (1.f - s); }
-    p.d_weightings[static_cast<int64_t>(row) * p.HAB + t] = dot;
+  float gsum[kCbColIt][EV], wsum[kCbColIt];
+#pragma unroll
+  for (int it = 0; it < kCbColIt; ++it) {
+    wsum[it] = 0.f;
+#pragma unroll
+    for (int k = 0; k < EV; ++k) gsum[it][k] = 0.f;
   }
 
-  // (2) gradient w.r.t. the aggregates -> target-side streams and min/max routing
-  float* ts = p.tstreams + static_cast<int64_t>(row) * p.n_ts * p.BD;
-  for (int p0 = lane * EV; p0 < p.BD; p0 += 32 * EV) {
-    const int b = p0 / D, d = p0 - b * D;
-    float t_sym[EV], t_lin[EV], t_sq[EV];
+  for (int row = blockIdx.x * kAggWarps + warp; row < p.n_rows; row += warps_total) {
+    stage_row(sm + p.sm_w, p.weightings + static_cast<int64_t>(row) * HAB, HAB, lane, v16);
+    stage_row(sm + p.sm_g, p.grad_out + static_cast<int64_t>(row) * HD, HD, lane, v16);
+    stage_row(sm + p.sm_saved, p.saved + static_cast<int64_t>(row) * p.n_saved * BD, p.n_saved * BD, lane, v16);
+    if (p.n_arg > 0)
+      stage_row(sm + p.sm_arg, reinterpret_cast<const float*>(p.saved_arg) + static_cast<int64_t>(row) * p.n_arg * BD,
+                p.n_arg * BD, lane, v16);
+    const float cntf = static_cast<float>(max(__ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row), 1));
+    const float inv_cnt = __frcp_rn(cntf);
+    cp_async_wait_all();
+    __syncwarp();
+
+    // (0) column sums of grad_out
+    if (p.colsum_part != nullptr) {
 #pragma unroll
-    for (int k = 0; k < EV; ++k) { t_sym[k] = 0.f; t_lin[k] = 0.f; t_sq[k] = 0.f; }
-    for (int a = 0; a < p.A; ++a) {
-      float da[EV];
+      for (int it = 0; it < kCbColIt; ++it) {
+        const int c = lane * EV + 32 * EV * it;
+        if (c < HD) {
+          float t[EV];
+          ld_plain<EV>(t, g + c);
 #pragma unroll
-      for (int k = 0; k < EV; ++k) da[k] = 0.f;
-      const float* wa = w + a * p.B + b;
-      for (int h = 0; h < p.H; ++h) {
-        const float wv = wa[h * p.AB];
-        float gv[EV];
-        ld_plain<EV>(gv, g + h * D + d);
-#pragma unroll
-        for (int k = 0; k < EV; ++k) da[k] = fmaf(wv, gv[k], da[k]);
-      }
-      const int code = p.aggr[a];
-      if (code == EGC_AGGR_SUM) {
-#pragma unroll
-        for (int k = 0; k < EV; ++k) t_lin[k] += da[k];
-      } else if (code == EGC_AGGR_MEAN) {
-#pragma unroll
-        for (int k = 0; k < EV; ++k) t_lin[k] += __fdiv_rn(da[k], cntf);
-      } else if (code == EGC_AGGR_SYMNORM) {
-#pragma unroll
-        for (int k = 0; k < EV; ++k) t_sym[k] += da[k];
-      } else if (code == EGC_AGGR_MAX || code == EGC_AGGR_MIN) {
-        const int* args = sarg + p.arg_slot[a] * p.BD + p0;
-#pragma unroll
-        for (int k = 0; k < EV; ++k) {
-          const int arg = args[k];
-          if (arg >= 0) {
-            float v = da[k];
-            if (LINW) v *= __ldg(p.val_lin + arg);
-            atomicAdd(p.d_bases + static_cast<int64_t>(__ldg(p.col + arg)) * p.BD + p0 + k, v);
-          }
-        }
-      } else {   // VAR / STD
-        float sa[EV], mean[EV];
-        ld_plain<EV>(sa, sv + a * p.BD + p0);
-        ld_plain<EV>(mean, sv + p.A * p.BD + p0);
-#pragma unroll
-        for (int k = 0; k < EV; ++k) {
-          float dv = da[k];
-          if (code == EGC_AGGR_STD) dv = sa[k] > 0.f ? dv / (2.f * sa[k]) : 0.f;    // relu gate (sign bit), d sqrt
-          const float q = __fdiv_rn(dv, cntf);
-          t_sq[k] += q;
-          t_lin[k] -= 2.f * mean[k] * q;
+          for (int k = 0; k < EV; ++k) gsum[it][k] += t[k];
         }
       }
     }
-    if (p.ts_sym >= 0) st_row<EV>(ts + p.ts_sym * p.BD + p0, t_sym);
-    if (p.ts_lin >= 0) st_row<EV>(ts + p.ts_lin * p.BD + p0, t_lin);
-    if (p.ts_sq >= 0) st_row<EV>(ts + p.ts_sq * p.BD + p0, t_sq);
+
+    // (1) gradient of the combination weights: HAB dot products of length D, skewed start per lane
+#pragma unroll
+    for (int it = 0; it < kCbColIt; ++it) {
+      for (int t = lane + 32 * it; t < HAB; t += 32 * kCbColIt) {
+        const bool is_std = tab_std[t] != 0;
+        const float* gh = g + tab_goff[t];
+        const float* aa = sv + tab_aoff[t];
+        float dot = 0.f;
+        if constexpr (EV == 4) {
+          int q = q0;
+          for (int i = 0; i < nq; ++i) {
+            const float4 gv = *reinterpret_cast<const float4*>(gh + 4 * q);
+            float4 av = *reinterpret_cast<const float4*>(aa + 4 * q);
+            if (is_std) { av.x = fabsf(av.x); av.y = fabsf(av.y); av.z = fabsf(av.z); av.w = fabsf(av.w); }
+            dot = fmaf(gv.x, av.x, dot); dot = fmaf(gv.y, av.y, dot); dot = fmaf(gv.z, av.z, dot); dot = fmaf(gv.w, av.w, dot);
+            q = (q + 1 == nq) ? 0 : q + 1;
+          }
+        } else {
+          int dd = dd0;
+          for (int i = 0; i < D; ++i) {
+            const float av = is_std ? fabsf(aa[dd]) : aa[dd];
+            dot = fmaf(gh[dd], av, dot);
+            dd = (dd + 1 == D) ? 0 : dd + 1;
+          }
+        }
+        if (p.sigmoid) { const float s = w[t]; dot *= s * (1.f - s); }
+        __stcs(p.d_weightings + static_cast<int64_t>(row) * HAB + t, dot);
+        if (t < 32 * kCbColIt) wsum[it] += dot;
+      }
+    }
+
+    // (2) gradient w.r.t. the aggregates -> target-side streams and min/max routing
+    float* ts = p.tstreams + static_cast<int64_t>(row) * p.ts_row_stride;
+    for (int p0 = lane * EV; p0 < BD; p0 += 32 * EV) {
+      const int b = p0 / D, d = p0 - b * D;
+      float t_sym[EV], t_lin[EV], t_sq[EV];
+#pragma unroll
+      for (int k = 0; k < EV; ++k) { t_sym[k] = 0.f; t_lin[k] = 0.f; t_sq[k] = 0.f; }
+      for (int a = 0; a < p.A; ++a) {
+        float da[EV];
+#pragma unroll
+        for (int k = 0; k < EV; ++k) da[k] = 0.f;
+        const float* wa = w + a * p.B + b;
+        for (int h = 0; h < p.H; ++h) {
+          const float wv = wa[h * AB];
+          float gv[EV];
+          ld_plain<EV>(gv, g + h * D + d);
+#pragma unroll
+          for (int k = 0; k < EV; ++k) da[k] = fmaf(wv, gv[k], da[k]);
+        }
+        const int code = p.aggr[a];
+        if (code == EGC_AGGR_SUM) {
+#pragma unroll
+          for (int k = 0; k < EV; ++k) t_lin[k] += da[k];
+        } else if (code == EGC_AGGR_MEAN) {
+#pragma unroll
+          for (int k = 0; k < EV; ++k) t_lin[k] = fmaf(da[k], inv_cnt, t_lin[k]);
+        } else if (code == EGC_AGGR_SYMNORM) {
+#pragma unroll
+          for (int k = 0; k < EV; ++k) t_sym[k] += da[k];
+        } else if (code == EGC_AGGR_MAX || code == EGC_AGGR_MIN) {
+          const int* args = sarg + p.arg_slot[a] * BD + p0;
+#pragma unroll
+          for (int k = 0; k < EV; ++k) {
+            const int arg = args[k];
+            if (arg >= 0) {
+              float v = da[k];
+              if (LINW) v *= __ldg(p.val_lin + arg);
+              atomicAdd(p.d_bases + static_cast<int64_t>(__ldg(p.col + arg)) * BD + p0 + k, v);
+            }
+          }
+        } else {   // VAR / STD
+          float sa[EV], mean[EV];
+          ld_plain<EV>(sa, sv + a * BD + p0);
+          ld_plain<EV>(mean, sv + p.A * BD + p0);
+#pragma unroll
+          for (int k = 0; k < EV; ++k) {
+            float dv = da[k];
+            if (code == EGC_AGGR_STD) dv = sa[k] > 0.f ? __fdividef(dv, 2.f * sa[k]) : 0.f;    // relu gate (sign bit), d sqrt
+            const float q = dv * inv_cnt;
+            t_sq[k] += q;
+            t_lin[k] = fmaf(-2.f * mean[k], q, t_lin[k]);
+          }
+        }
+      }
+      if constexpr (EV == 4) {
+        if (p.ts_sym >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_sym) * p.ts_stream_stride + p0, t_sym);
+        if (p.ts_lin >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_lin) * p.ts_stream_stride + p0, t_lin);
+        if (p.ts_sq >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_sq) * p.ts_stream_stride + p0, t_sq);
+      } else {
+        if (p.ts_sym >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_sym) * p.ts_stream_stride + p0, t_sym);
+        if (p.ts_lin >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_lin) * p.ts_stream_stride + p0, t_lin);
+        if (p.ts_sq >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_sq) * p.ts_stream_stride + p0, t_sq);
+      }
+    }
+    __syncwarp();     // the next row overwrites this warp's staging area
+  }
+
+  // ---- column-sum partials of this CTA: [HD] grad_out sums | [HAB] d_weightings sums
+  if (p.colsum_part != nullptr) {
+    __syncthreads();
+    float* red = smem_all;                                   // reuse the staging areas: [kAggWarps][HD + HAB]
+    const int width = HD + HAB;
+#pragma unroll
+    for (int it = 0; it < kCbColIt; ++it) {
+      const int c = lane * EV + 32 * EV * it;
+      if (c < HD) {
+#pragma unroll
+        for (int k = 0; k < EV; ++k) red[warp * width + c + k] = gsum[it][k];
+      }
+      const int t = lane + 32 * it;
+      if (t < HAB) red[warp * width + HD + t] = wsum[it];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < width; c += kAggThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kAggWarps; ++wv) t += red[wv * width + c];
+      p.colsum_part[static_cast<int64_t>(blockIdx.x) * width + c] = t;
+    }
+  }
+}
+
+// out[c] = sum over CTAs of part[cta][c] in CTA order; columns [0, n1) -> out1, [n1, n1 + n2) -> out2
+__global__ void k_colsum_partials(const float* __restrict__ part, int n_cta, int n1, int n2, float* __restrict__ out1,
+                                  float* __restrict__ out2) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int width = n1 + n2;
+  if (c >= width) return;
+  float t = 0.f;
+  for (int s = lane; s < n_cta; s += 32) t += part[static_cast<int64_t>(s) * width + c];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+  if (lane == 0) {
+    if (c < n1) { if (out1 != nullptr) out1[c] = t; }
+    else if (out2 != nullptr) out2[c - n1] = t;
   }
 }
 
@@ -415,6 +515,8 @@ static int stream_mask_of(const egc_layer_desc& d, bool& has_route) {
   return m;
 }
 
+static int combine_bwd_grid(int n_rows) { return std::max(1, std::min(ceil_div(n_rows, kAggWarps), sm_count() * 4)); }
+
 struct BwdLayout {
   size_t ts_bytes, csc_part_bytes, colsum_bytes, total;
   int n_ts, ts_sym, ts_lin, ts_sq, tsmask;
@@ -432,7 +534,11 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
   L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256);
-  L.colsum_bytes = align_up(colsum_workspace_bytes(d.n_dst, d.heads * d.dim), 256);
+  // per-CTA column-sum partials of the fused pass-1 kernel, or the two-stage colsum scratch when it cannot fuse
+  const size_t hd = static_cast<size_t>(d.heads) * d.dim, hab = static_cast<size_t>(d.heads) * d.n_aggr * d.bases;
+  const size_t fused = static_cast<size_t>(combine_bwd_grid(d.n_dst)) * (hd + hab) * sizeof(float) + 256;
+  L.colsum_bytes = align_up(std::max(fused, std::max(colsum_workspace_bytes(d.n_dst, static_cast<int>(hd)),
+                                                     colsum_workspace_bytes(d.n_dst, static_cast<int>(hab)))), 256);
   L.total = L.ts_bytes + L.csc_part_bytes + L.colsum_bytes + 256;
   return L;
 }
@@ -492,7 +598,14 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     EGC_CUDA(cudaMemsetAsync(arg_out, 0xff, static_cast<size_t>(desc->n_dst) * desc->n_aggr * bd * sizeof(int32_t), st));
   auto launch = vec4 ? launch_aggregate_v4 : launch_aggregate_v1;
   p.mode = 0;
-  if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
+  const int hd = desc->heads * desc->dim;
+  const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
+                    hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) && (desc->dim % 4 != 0 || aligned16(bias));
+  if (fast) {
+    if (int rc = (p.G == 32 ? launch_aggregate_fast_g32 : launch_aggregate_fast_g16)(p, mask, want_arg, smem, st)) return rc;
+  } else {
+    if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
+  }
   if (p.n_long > 0) {
     p.mode = 1;
     if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
@@ -510,8 +623,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
-                      float* d_weightings, float* d_bases, float* d_bias, int32_t flags, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum, int32_t flags,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
   EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
@@ -542,6 +655,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     EGC_CUDA(cudaMemsetAsync(d_bases, 0, static_cast<size_t>(desc->n_src) * bd * sizeof(float), st));
 
   // ---- pass 1: streaming over target nodes
+  bool fuse_colsum = false;
   {
     CombineBwdParams c{};
     c.rowptr = rowptr; c.col = col; c.val_lin = val_lin; c.n_rows = desc->n_dst;
@@ -564,13 +678,19 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     c.sm_saved = off; off = a4(off + c.n_saved * bd);
     c.sm_arg = off; off = a4(off + n_arg * bd);
     c.sm_per_warp = off;
-    const int smem = off * kAggWarps * static_cast<int>(sizeof(float));
+    const int smem = (off * kAggWarps + 3 * hab) * static_cast<int>(sizeof(float));    // staging areas + index tables
     EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
+    c.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;
+    c.ts_stream_stride = bd;
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
                aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
     const bool linw = val_lin != nullptr;
-    const int grid = ceil_div(desc->n_dst, kAggWarps);
+    const int grid = combine_bwd_grid(desc->n_dst);
+    // column sums fused into pass 1 when the per-lane accumulators cover the row widths
+    fuse_colsum = (d_bias != nullptr || d_lin_colsum != nullptr) && hab <= 32 * kCbColIt &&
+                  hd <= 32 * kCbColIt * (ev4 ? 4 : 1);
+    c.colsum_part = fuse_colsum ? static_cast<float*>(colsum_ws) : nullptr;
 #define EGC_LAUNCH_COMBINE(EV, LW)                                                                             \
     {                                                                                                          \
       auto kern = k_combine_bwd<EV, LW>;                                                                       \
@@ -584,6 +704,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     else EGC_LAUNCH_COMBINE(1, true)
 #undef EGC_LAUNCH_COMBINE
     EGC_LAUNCH_CHECK("k_combine_bwd");
+    if (fuse_colsum) {
+      {
+        LaunchScope egc_ls_("k_colsum_partials", st);
+        k_colsum_partials<<<ceil_div(hd + hab, 8), 256, 0, st>>>(c.colsum_part, grid, hd, hab, d_bias, d_lin_colsum);
+      }
+      EGC_LAUNCH_CHECK("k_colsum_partials");
+    }
   }
 
   // ---- pass 2: per source column (CSC), atomic-free
@@ -611,8 +738,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     }
   }
 
-  if (d_bias != nullptr) {
-    if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
+  if (!fuse_colsum) {
+    if (d_bias != nullptr) {
+      if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
+    }
+    if (d_lin_colsum != nullptr) {
+      if (int rc = colsum_f32(d_weightings, desc->n_dst, hab, d_lin_colsum, colsum_ws, L.colsum_bytes, st)) return rc;
+    }
   }
   return EGC_OK;
 }

@@ -93,7 +93,7 @@ int egc_abi_version(void) { return EGC_ABI_VERSION; }
 const char* egc_last_error_string(void) { return egc::g_err; }
 
 const char* egc_build_info(void) {
-  return "libegc_b200 abi=1 arch=sm_100a cuda=" EGC_STR(__CUDACC_VER_MAJOR__) "." EGC_STR(__CUDACC_VER_MINOR__)
+  return "libegc_b200 abi=" EGC_STR(EGC_ABI_VERSION) " arch=sm_100a cuda=" EGC_STR(__CUDACC_VER_MAJOR__) "." EGC_STR(__CUDACC_VER_MINOR__)
          " chunk_edges=" EGC_STR(EGC_CHUNK_EDGES);
 }
 

@@ -6,14 +6,20 @@
 // fp32 parity through kind::tf32 MMAs comes from the 3-term split  a.b ~= ah.bh + ah.bl + al.bh  with
 // ah = a & 0xffffe000 (exact TF32), al = a - ah, accumulated in fp32 in TMEM (n_terms = 1 gives plain TF32).
 //
-// One persistent CTA per SM, 9 warps:
-//   warps 0-3  epilogue   tcgen05.ld of the 128 x N accumulator (TMEM lanes 32w..32w+31) -> global
-//   warp  4    MMA        one elected lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation
-//   warps 5-8  producers  one A row per thread: LDG.128 -> hi/lo split -> st.shared in the canonical
-//                         K-major no-swizzle UMMA layout (8-row x 16-byte core matrices)
-// The weights (B, hi and lo) are staged once per CTA and stay resident in shared memory; A streams
-// through a 3-stage ring of 128 x 16 chunks; the accumulator is double-buffered in TMEM (2 x 256 cols)
-// so the epilogue of tile t overlaps the main loop of tile t+1.
+// The op is an HBM stream (AI ~ 37 flop/B), so the kernel is organised around bytes in flight:
+// one persistent CTA per SM, 11 warps:
+//   warps 9-10  copy      cp.async (16 B, L2-only) of raw A chunks into a deep shared-memory ring, already in
+//                         the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices);
+//                         completion is signalled on an mbarrier (cp.async.mbarrier.arrive.noinc), so up to
+//                         `raw_stages` x 8 KB per SM are in flight without holding registers
+//   warps 5-8   convert   raw chunk -> hi (in place) and lo (2-deep side ring), fence.proxy.async
+//   warp  4     MMA       one elected lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation
+//   warps 0-3   epilogue  tcgen05.ld of the 128 x N accumulator (TMEM lanes 32w..32w+31) -> global
+// The weights (B, hi and lo) are staged once per CTA and stay resident in shared memory.  When B (hi + lo)
+// would leave too little room for the A ring, the output columns are split over `n_split` groups of CTAs
+// (CTA c serves group c % n_split); the groups walk the row tiles in lockstep, so the second read of an A
+// tile is an L2 hit.  The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile t
+// overlaps the main loop of tile t+1.
 #include <algorithm>
 
 #include "project.cuh"
@@ -21,12 +27,14 @@
 
 namespace egc {
 
-constexpr int kTcThreads = 288;
+constexpr int kTcThreads = 352;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 16;                                   // floats of K per A chunk (2 UMMA k-steps of 8)
-constexpr int kStages = 3;
-constexpr int kHalfStageBytes = kTileM * kChunkK * 4;         // 8 KB (hi or lo)
-constexpr int kStageBytes = 2 * kHalfStageBytes;              // hi + lo
+constexpr int kChunkBytes = kTileM * kChunkK * 4;             // 8 KB (raw / hi, or lo)
+constexpr int kLoStages = 4;
+constexpr int kMaxRawStages = 16;
+constexpr int kCopyThreads = 64;
+constexpr int kConvThreads = 128;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kTmemCols = 512;
 
@@ -42,7 +50,9 @@ struct TcParams {
   float* c2; int ldc2;
   const float* bias2;
   int sigmoid2;
-  int n_pad, k_pad;                        // multiples of 16
+  int k_pad;                               // multiple of 16
+  int n_split, cols_per_group;             // output columns [g * cols_per_group, ...) belong to CTA group g
+  int raw_stages;
   int n_terms;                             // 3: 3xTF32, 1: TF32
   int num_tiles;
 };
@@ -54,44 +64,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
-  const uint32_t b_half_bytes = static_cast<uint32_t>(p.n_pad) * p.k_pad * 4;
-  const uint32_t lbo_b = static_cast<uint32_t>(p.n_pad) * 16;            // bytes between 16-byte K pieces of B
+  const int R = p.raw_stages;
+  const int group = blockIdx.x % p.n_split;
+  const int n_begin = group * p.cols_per_group;
+  const int n_count = min(p.cols_per_group, N - n_begin);
+  const int n_pad = (n_count + 15) & ~15;
+  const uint32_t b_half_bytes = static_cast<uint32_t>(p.cols_per_group) * p.k_pad * 4;
+  const uint32_t lbo_b = static_cast<uint32_t>(n_pad) * 16;              // bytes between 16-byte K pieces of B
   uint8_t* b_hi = smem;
   uint8_t* b_lo = smem + b_half_bytes;
-  uint8_t* a_ring = smem + 2 * b_half_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + kStages * kStageBytes);
-  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* lo_ring = smem + 2 * b_half_bytes;
+  uint8_t* raw_ring = lo_ring + kLoStages * kChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + static_cast<size_t>(R) * kChunkBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxRawStages + kLoStages + 4);
   const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 + s); };
+  auto raw_full = [&](int s) { return bar0 + 8u * s; };
+  auto raw_empty = [&](int s) { return bar0 + 8u * (R + s); };
+  auto conv_full = [&](int s) { return bar0 + 8u * (2 * R + s); };
+  auto lo_empty = [&](int s) { return bar0 + 8u * (3 * R + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * R + kLoStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * R + kLoStages + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), kCopyThreads); mbar_init(raw_empty(s), 1); mbar_init(conv_full(s), kConvThreads); }
+    for (int s = 0; s < kLoStages; ++s) mbar_init(lo_empty(s), 1);
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
 
-  // ---- stage the weights once: hi / lo split, canonical K-major layout (zero padded)
-  for (int k = warp; k < p.k_pad; k += kTcThreads / 32) {
-    const int kb = k >= p.k1 ? 1 : 0;
-    const uint32_t koff = static_cast<uint32_t>(k >> 2) * lbo_b + (k & 3) * 4;
-    for (int n = lane; n < p.n_pad; n += 32) {
-      float v = 0.f;
-      if (n < N && k < K) {
-        const int nb = n >= p.n1 ? 1 : 0;
-        const float* src = p.b[nb][kb];
-        if (src != nullptr)
-          v = __ldg(src + static_cast<int64_t>(n - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
-                    static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+  // ---- stage this group's weights once: hi / lo split, canonical K-major layout (zero padded).
+  // Batches of 8 independent loads per thread keep the (L2-resident) weight fetch off the critical path.
+  {
+    const int total = p.k_pad * n_pad;
+    constexpr int kBatch = 8;
+    for (int e0 = tid; e0 < total; e0 += kTcThreads * kBatch) {
+      float v[kBatch];
+      uint32_t off[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int e = e0 + u * kTcThreads;
+        v[u] = 0.f;
+        off[u] = 0xffffffffu;
+        if (e < total) {
+          const int k = e / n_pad, n = e - k * n_pad;
+          off[u] = static_cast<uint32_t>(k >> 2) * lbo_b + (k & 3) * 4 + static_cast<uint32_t>(n) * 16;
+          const int ng = n_begin + n;
+          if (n < n_count && k < K) {
+            const int kb = k >= p.k1 ? 1 : 0, nb = ng >= p.n1 ? 1 : 0;
+            const float* src = p.b[nb][kb];
+            if (src != nullptr)
+              v[u] = __ldg(src + static_cast<int64_t>(ng - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
+                           static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+          }
+        }
       }
-      const float hi = tf32_hi(v), lo = v - hi;
-      const uint32_t off = koff + static_cast<uint32_t>(n) * 16;
-      *reinterpret_cast<float*>(b_hi + off) = hi;
-      *reinterpret_cast<float*>(b_lo + off) = lo;
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (off[u] != 0xffffffffu) {
+          const float hi = tf32_hi(v[u]);
+          *reinterpret_cast<float*>(b_hi + off[u]) = hi;
+          *reinterpret_cast<float*>(b_lo + off[u]) = v[u] - hi;
+        }
+      }
     }
   }
   fence_proxy_async();
@@ -101,52 +136,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_chunks = p.k_pad / kChunkK;
-  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  const int first_tile = blockIdx.x / p.n_split, tile_step = gridDim.x / p.n_split;
+  const uint32_t raw_addr = smem_u32(raw_ring), lo_addr = smem_u32(lo_ring);
 
-  if (warp >= 5) {
-    // ================= producers: one A row per thread =================
-    const int pt = tid - 5 * 32;
+  if (warp >= 9) {
+    // ================= copy producers: raw A chunks, global -> shared ring =================
+    const int pt = tid - 9 * 32;
+    const int c = pt & 3, r0 = pt >> 2;                       // 16-byte K piece, first row (rows r0 + 16 i)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-      const int64_t row = static_cast<int64_t>(tile) * kTileM + pt;
-      const bool valid = row < p.M;
-      const float* r1 = p.a1 + row * p.lda1;
-      const float* r2 = p.a2 != nullptr ? p.a2 + row * p.lda2 : nullptr;
+      const int64_t row_base = static_cast<int64_t>(tile) * kTileM;
       for (int j = 0; j < n_chunks; ++j) {
+        const int k = j * kChunkK + 4 * c;
+        const float* base;
+        int64_t ld;
+        if (k < p.k1) { base = p.a1 + k; ld = p.lda1; } else { base = p.a2 + (k - p.k1); ld = p.lda2; }
+        const bool k_ok = k < K;
+        mbar_wait(raw_empty(stage), phase ^ 1u);
+        const uint32_t dst = raw_addr + stage * kChunkBytes + c * (kTileM * 16) + r0 * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row_base + r0 + 16 * i;
+          const bool ok = k_ok && row < p.M;
+          cp_async_16_zfill(dst + i * 256, ok ? base + row * ld : p.a1, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(raw_full(stage));
+        if (++stage == R) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 5) {
+    // ================= converters: raw -> hi (in place) + lo =================
+    const int ct = tid - 5 * 32;
+    int stage = 0, lo = 0;
+    uint32_t phase = 0, lo_phase = 0;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+      for (int j = 0; j < n_chunks; ++j) {
+        mbar_wait(raw_full(stage), phase);
+        const uint32_t src = raw_addr + stage * kChunkBytes + ct * 16;
         float4 v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k = j * kChunkK + 4 * c;
-          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && k < K) {
-            const float* src = k < p.k1 ? r1 + k : r2 + (k - p.k1);
-            v[c] = __ldcs(reinterpret_cast<const float4*>(src));
-          }
-        }
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        uint8_t* hi_base = a_ring + stage * kStageBytes + pt * 16;
-        uint8_t* lo_base = hi_base + kHalfStageBytes;
+        for (int i = 0; i < 4; ++i) v[i] = lds128(src + i * 2048);
+        mbar_wait(lo_empty(lo), lo_phase ^ 1u);
+        const uint32_t dlo = lo_addr + lo * kChunkBytes + ct * 16;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
-          float4 l = make_float4(v[c].x - h.x, v[c].y - h.y, v[c].z - h.z, v[c].w - h.w);
-          *reinterpret_cast<float4*>(hi_base + c * (kTileM * 16)) = h;
-          *reinterpret_cast<float4*>(lo_base + c * (kTileM * 16)) = l;
+        for (int i = 0; i < 4; ++i) {
+          const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+          const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+          sts128(src + i * 2048, h);
+          sts128(dlo + i * 2048, l);
         }
         fence_proxy_async();
-        mbar_arrive(full_bar(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        mbar_arrive(conv_full(stage));
+        if (++stage == R) { stage = 0; phase ^= 1u; }
+        if (++lo == kLoStages) { lo = 0; lo_phase ^= 1u; }
       }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n_pad >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
       const uint32_t a_lbo = kTileM * 16, sbo = 128;
-      const uint32_t b_hi_addr = smem_u32(b_hi), b_lo_addr = smem_u32(b_lo), ring_addr = smem_u32(a_ring);
-      int stage = 0;
+      const uint32_t b_hi_addr = smem_u32(b_hi), b_lo_addr = smem_u32(b_lo);
+      int stage = 0, lo = 0;
       uint32_t phase = 0;
       int t = 0;
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
@@ -155,9 +208,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
         for (int j = 0; j < n_chunks; ++j) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(conv_full(stage), phase);
           tc_fence_after();
-          const uint32_t a_hi_addr = ring_addr + stage * kStageBytes, a_lo_addr = a_hi_addr + kHalfStageBytes;
+          const uint32_t a_hi_addr = raw_addr + stage * kChunkBytes, a_lo_addr = lo_addr + lo * kChunkBytes;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const uint32_t ks = static_cast<uint32_t>(2 * j + s);
@@ -171,8 +224,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
               umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
             }
           }
-          umma_commit(empty_bar(stage));          // frees the A slot once these MMAs have read it
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          umma_commit(raw_empty(stage));          // frees the raw / hi slot once these MMAs have read it
+          umma_commit(lo_empty(lo));
+          if (++stage == R) { stage = 0; phase ^= 1u; }
+          if (++lo == kLoStages) lo = 0;
         }
         umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
       }
@@ -181,6 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   } else {
     // ================= epilogue: TMEM -> registers -> global =================
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int n_end = n_begin + n_count;
     int t = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
       const int acc = t & 1;
@@ -190,19 +246,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       const bool valid = row < p.M;
       float* o1 = p.c1 + row * p.ldc1;
       float* o2 = p.c2 != nullptr ? p.c2 + row * p.ldc2 : nullptr;
-      for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
+      for (int col0 = 0; col0 < n_pad; col0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(acc) * 256u + static_cast<uint32_t>(col0), r);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int col = col0 + 4 * q;
+            const int col = n_begin + col0 + 4 * q;
             float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (col < p.n1) {
-              *reinterpret_cast<float4*>(o1 + col) = v;
-            } else if (col < N) {
+            if (col >= n_end) {
+            } else if (col < p.n1) {
+              __stcs(reinterpret_cast<float4*>(o1 + col), v);
+            } else {
               const int c2 = col - p.n1;
               if (p.bias2 != nullptr) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + c2));
@@ -212,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
                 v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
                 v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
               }
-              *reinterpret_cast<float4*>(o2 + c2) = v;
+              __stcs(reinterpret_cast<float4*>(o2 + c2), v);
             }
           }
         }
@@ -232,38 +289,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
 // ---------------------------------------------------------------------------------------------
 static int round16(int v) { return (v + 15) / 16 * 16; }
 
-static size_t tc_smem_bytes(int n_pad, int k_pad) {
-  return static_cast<size_t>(2) * n_pad * k_pad * 4 + kStages * kStageBytes + 256;
-}
+struct TcPlan { int n_split, cols_per_group, raw_stages; size_t smem; };
 
-static bool tc_shape_ok(int k, int n) {
-  const int k_pad = round16(k), n_pad = round16(n);
-  return n_pad >= 16 && n_pad <= 256 && tc_smem_bytes(n_pad, k_pad) <= kMaxSmem;
+// smallest column split that leaves a deep A ring next to the resident weights
+static bool tc_plan(int k, int n, TcPlan& out) {
+  const int k_pad = round16(k);
+  const size_t fixed = static_cast<size_t>(kLoStages) * kChunkBytes + (3 * kMaxRawStages + kLoStages + 4) * 8 + 64;
+  TcPlan best{0, 0, 0, 0};
+  for (int s = 1; s <= 4; ++s) {
+    const int cpg = round16(ceil_div(n, s));
+    if (cpg < 16 || cpg > 256) continue;
+    const size_t b_bytes = static_cast<size_t>(2) * cpg * k_pad * 4;
+    if (b_bytes + fixed + 2 * kChunkBytes > static_cast<size_t>(kMaxSmem)) continue;
+    const int r = static_cast<int>(std::min<size_t>(kMaxRawStages, (kMaxSmem - b_bytes - fixed) / kChunkBytes));
+    if (r > best.raw_stages) best = TcPlan{s, cpg, r, b_bytes + fixed + static_cast<size_t>(r) * kChunkBytes};
+    if (r >= 8) break;
+  }
+  out = best;
+  return best.raw_stages >= 2;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 bool project_tc_supported(int n, int f_in, int bd, int hab) {
   if (n < 1 || f_in % 4 || bd % 4 || hab % 4) return false;
-  return tc_shape_ok(f_in, bd + hab) && tc_shape_ok(bd + hab, f_in);
+  TcPlan a, b;
+  return tc_plan(f_in, bd + hab, a) && tc_plan(bd + hab, f_in, b);
 }
 
 static int launch_tc(TcParams& p, cudaStream_t st) {
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
+  TcPlan plan;
+  EGC_REQUIRE(tc_plan(K, N, plan), "tensor-core projection: shape does not fit shared memory");
   p.k_pad = round16(K);
-  p.n_pad = round16(N);
+  p.n_split = plan.n_split;
+  p.cols_per_group = plan.cols_per_group;
+  p.raw_stages = plan.raw_stages;
   p.num_tiles = ceil_div(p.M, kTileM);
-  const size_t smem = tc_smem_bytes(p.n_pad, p.k_pad);
-  EGC_REQUIRE(smem <= kMaxSmem, "tensor-core projection: shape does not fit shared memory");
   static bool attr_set = false;
   if (!attr_set) {
     EGC_CUDA(cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
-  const int grid = std::min(p.num_tiles, sm_count());
+  const int per_group = std::max(1, std::min(p.num_tiles, sm_count() / p.n_split));
+  const int grid = per_group * p.n_split;
   {
     LaunchScope ls("k_project_tc", st);
-    k_project_tc<<<grid, kTcThreads, smem, st>>>(p);
+    k_project_tc<<<grid, kTcThreads, plan.smem, st>>>(p);
   }
   EGC_LAUNCH_CHECK("k_project_tc");
   return EGC_OK;

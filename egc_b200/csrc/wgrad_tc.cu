@@ -2,13 +2,19 @@
 // (dW_b = x^T d_bases, dW_c^T = x^T d_lin; ref: autograd of optimized_layers.py:180-182).
 //
 // The contraction runs over the NODE dimension, so both operands stream and both are feature-contiguous
-// in memory (MN-major).  kind::tf32 MMAs with no-swizzle descriptors only accept K-major operands on
-// this part (tools/umma_probe.cu: the MN-major bits yield zeros), so the producers transpose on the
-// fly: lane -> (node%4, feature%8) reads 4 x 32 B global sectors per warp instruction and writes 128
-// contiguous shared bytes (conflict-free) of the canonical K-major layout (8 rows x 16 B core matrices).
-// Each persistent CTA owns a contiguous range of 16-node chunks, accumulates one 128 x N_pad fp32
-// tile in TMEM (3-term hi/lo split) and writes its partial tile to the workspace; a small
-// deterministic kernel reduces the partials into dW_b / dW_c (transposing the latter).
+// in memory (MN-major).  kind::tf32 MMAs only accept MN-major operands in the 128B/32B-atom swizzle
+// (tools/umma_probe.cu: the no-swizzle MN-major bits yield zeros), so the operands are transposed on the
+// way through shared memory instead, and the MMA sees the plain K-major no-swizzle layout:
+//   warps 9-10  copy      cp.async (16 B) of raw node rows [x | d_bases | d_lin] into a deep row-major ring
+//                         (mbarrier-tracked, ~130 KB in flight per SM)
+//   warps 5-8   convert   4 nodes x 4 features register transposes -> hi / lo split -> the canonical K-major
+//                         layout (8 rows x 16 B core matrices, K = node), conflict-free rotated stores
+//   warp  4     MMA       one elected lane, 3-term split into a 128 x N_pad fp32 accumulator in TMEM
+//   warps 0-3   epilogue  every kSegChunks chunks the accumulator is flushed into this CTA's partial tile
+//                         in global memory (fp32 RN adds; bounds the length of the in-TMEM accumulation);
+//                         two accumulators alternate so the flush overlaps the next segment's MMAs
+// Each persistent CTA owns a contiguous range of 16-node chunks; a small deterministic kernel reduces the
+// per-CTA partial tiles into dW_b / dW_c (transposing the latter).
 #include <algorithm>
 
 #include "project.cuh"
@@ -16,11 +22,15 @@
 
 namespace egc {
 
-constexpr int kWgThreads = 288;          // warps 0-3 epilogue, 4 MMA, 5-8 producers
+constexpr int kWgThreads = 352;          // warps 0-3 epilogue, 4 MMA, 5-8 converters, 9-10 copy producers
 constexpr int kWgChunk = 16;             // nodes per chunk (2 UMMA k-steps)
 constexpr int kWgM = 128;                // feature rows of the accumulator tile (F_in padded)
 constexpr int kWgMaxSmem = 227 * 1024;
-constexpr int kMaxSlots = 40;            // register-prefetched scalars per producer thread and chunk
+constexpr int kWgOpStages = 2;
+constexpr int kWgMaxRaw = 12;
+constexpr int kSegChunks = 24;           // chunks accumulated in TMEM between two flushes (384 nodes)
+constexpr int kWgCopyThreads = 64;
+constexpr int kWgConvThreads = 128;
 
 struct WgParams {
   const float* x; int f_in;              // A^T source: x[n, f_in]
@@ -29,31 +39,47 @@ struct WgParams {
   int n_nodes;
   int n_pad;                             // multiple of 16
   int n_terms;
-  int stages;
+  int raw_stages;
   int chunks_total, chunks_per_cta;
+  uint32_t ppn_magic;                    // ceil(2^32 / pieces_per_node)
   float* partial;                        // [grid][kWgM][n_pad]
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = p.f_in + p.n1 + p.n2;                                // floats per raw node row
+  const int ppn = W >> 2;                                            // 16-byte pieces per node
   const uint32_t a_half = kWgM * kWgChunk * 4;                       // 8 KB: hi (or lo) of an A chunk
   const uint32_t b_half = static_cast<uint32_t>(p.n_pad) * kWgChunk * 4;
-  const uint32_t stage_bytes = 2 * (a_half + b_half);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
-  // bars: [0,S) full, [S,2S) empty, [2S] accumulator done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  const uint32_t op_bytes = 2 * (a_half + b_half);                   // [A_hi | A_lo | B_hi | B_lo]
+  const uint32_t raw_bytes = static_cast<uint32_t>(kWgChunk) * W * 4;
+  const int R = p.raw_stages;
+  uint8_t* op_ring = smem;
+  uint8_t* raw_ring = smem + kWgOpStages * op_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + static_cast<size_t>(R) * raw_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxRaw + 8);
   const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  const uint32_t done_bar = bar0 + 8u * (2 * p.stages);
+  auto raw_full = [&](int s) { return bar0 + 8u * s; };
+  auto raw_empty = [&](int s) { return bar0 + 8u * (R + s); };
+  auto op_full = [&](int s) { return bar0 + 8u * (2 * R + s); };
+  auto op_empty = [&](int s) { return bar0 + 8u * (2 * R + 2 + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * R + 4 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * R + 6 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
-    mbar_init(done_bar, 1);
+    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), kWgCopyThreads); mbar_init(raw_empty(s), kWgConvThreads); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(op_full(s), kWgConvThreads); mbar_init(op_empty(s), 1);
+      mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 512);
+  // operand rows beyond f_in / n1 + n2 are never written by the converters: zero them once
+  for (uint32_t off = tid * 16; off < kWgOpStages * op_bytes; off += kWgThreads * 16)
+    *reinterpret_cast<float4*>(op_ring + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -63,117 +89,146 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   const int c_end = min(c_begin + p.chunks_per_cta, p.chunks_total);
   const int n_chunks = max(c_end - c_begin, 0);
   const uint32_t a_lbo = kWgM * 16, b_lbo = static_cast<uint32_t>(p.n_pad) * 16;   // bytes between 4-node K pieces
-  constexpr int kASlots = 4 * (kWgM / 8);                   // (K piece, 8-feature group) pairs of A per chunk
-  const int b_groups = p.n_pad / 8;
-  const int n_slots = kASlots + 4 * b_groups;               // <= kMaxSlots * 4
+  const uint32_t raw_addr = smem_u32(raw_ring), op_addr = smem_u32(op_ring);
 
-  if (warp >= 5) {
-    // ================= producers: transposing stage-in =================
-    const int pw = warp - 5;
-    const int kk = lane & 3, mm = lane >> 2;                // node within the 4-piece, feature within the 8-group
+  if (warp >= 9) {
+    // ================= copy producers: raw node rows, global -> shared ring =================
+    const int pt = tid - 9 * 32;
+    const int n_pieces = kWgChunk * ppn;
     int stage = 0;
     uint32_t phase = 0;
     for (int c = c_begin; c < c_end; ++c) {
       const int node0 = c * kWgChunk;
-      float v[kMaxSlots];
-#pragma unroll
-      for (int i = 0; i < kMaxSlots; ++i) {
-        const int slot = pw + 4 * i;
-        float t = 0.f;
-        if (slot < kASlots) {
-          const int piece = slot / (kWgM / 8), grp = slot - piece * (kWgM / 8);
-          const int node = node0 + piece * 4 + kk, f = grp * 8 + mm;
-          if (node < p.n_nodes && f < p.f_in) t = __ldcs(p.x + static_cast<int64_t>(node) * p.f_in + f);
-        } else if (slot < n_slots) {
-          const int s2 = slot - kASlots;
-          const int piece = s2 / b_groups, grp = s2 - piece * b_groups;
-          const int node = node0 + piece * 4 + kk, col = grp * 8 + mm;
-          if (node < p.n_nodes) {
-            if (col < p.n1) t = __ldcs(p.d1 + static_cast<int64_t>(node) * p.n1 + col);
-            else if (col < p.n1 + p.n2) t = __ldcs(p.d2 + static_cast<int64_t>(node) * p.n2 + (col - p.n1));
-          }
-        }
-        v[i] = t;
+      mbar_wait(raw_empty(stage), phase ^ 1u);
+      const uint32_t dst = raw_addr + stage * raw_bytes;
+      for (int piece = pt; piece < n_pieces; piece += kWgCopyThreads) {
+        const int i = static_cast<int>(__umulhi(static_cast<uint32_t>(piece), p.ppn_magic));   // piece / ppn
+        const int f = (piece - i * ppn) * 4;
+        const int64_t node = node0 + i;
+        const float* src;
+        if (f < p.f_in) src = p.x + node * p.f_in + f;
+        else if (f < p.f_in + p.n1) src = p.d1 + node * p.n1 + (f - p.f_in);
+        else src = p.d2 + node * p.n2 + (f - p.f_in - p.n1);
+        const bool ok = node < p.n_nodes;
+        cp_async_16_zfill(dst + piece * 16, ok ? src : p.x, ok ? 16u : 0u);
       }
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      uint8_t* st_base = smem + static_cast<size_t>(stage) * stage_bytes;
+      cp_async_mbar_arrive_noinc(raw_full(stage));
+      if (++stage == R) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= 5) {
+    // ================= converters: transpose 4 nodes x 4 features, hi / lo split =================
+    const int ct = tid - 5 * 32;
+    const int n_blocks = 4 * ppn;                          // (node quad, feature quad) blocks per chunk
+    const uint32_t row_bytes = static_cast<uint32_t>(W) * 4;
+    int stage = 0, op = 0;
+    uint32_t phase = 0, op_phase = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      mbar_wait(raw_full(stage), phase);
+      mbar_wait(op_empty(op), op_phase ^ 1u);
+      const uint32_t src0 = raw_addr + stage * raw_bytes;
+      const uint32_t dst0 = op_addr + op * op_bytes;
+      for (int b = ct; b < n_blocks; b += kWgConvThreads) {
+        const int quad = static_cast<int>(__umulhi(static_cast<uint32_t>(b), p.ppn_magic));    // b / ppn
+        const int fq = b - quad * ppn;
+        const uint32_t src = src0 + static_cast<uint32_t>(quad) * 4 * row_bytes + fq * 16;
+        const float4 v0 = lds128(src), v1 = lds128(src + row_bytes), v2 = lds128(src + 2 * row_bytes),
+                     v3 = lds128(src + 3 * row_bytes);
+        float4 o[4] = {make_float4(v0.x, v1.x, v2.x, v3.x), make_float4(v0.y, v1.y, v2.y, v3.y),
+                       make_float4(v0.z, v1.z, v2.z, v3.z), make_float4(v0.w, v1.w, v2.w, v3.w)};
+        // rotate the store order by (fq / 2) % 4 so that the 8 lanes of a store phase hit 8 distinct 16-byte bank groups
+        const int rot = (fq >> 1) & 3;
+        if (rot & 1) { const float4 t = o[0]; o[0] = o[1]; o[1] = o[2]; o[2] = o[3]; o[3] = t; }
+        if (rot & 2) { float4 t = o[0]; o[0] = o[2]; o[2] = t; t = o[1]; o[1] = o[3]; o[3] = t; }
+        const int f = fq * 4;
+        uint32_t dst, lo_off;
+        if (f < p.f_in) { dst = dst0 + quad * a_lbo + f * 16; lo_off = a_half; }
+        else { dst = dst0 + 2 * a_half + quad * b_lbo + (f - p.f_in) * 16; lo_off = b_half; }
 #pragma unroll
-      for (int i = 0; i < kMaxSlots; ++i) {
-        const int slot = pw + 4 * i;
-        const float h = tf32_hi(v[i]), l = v[i] - h;
-        if (slot < kASlots) {
-          const int piece = slot / (kWgM / 8), grp = slot - piece * (kWgM / 8);
-          const uint32_t off = piece * a_lbo + (grp * 8 + mm) * 16 + kk * 4;
-          *reinterpret_cast<float*>(st_base + off) = h;
-          *reinterpret_cast<float*>(st_base + a_half + off) = l;
-        } else if (slot < n_slots) {
-          const int s2 = slot - kASlots;
-          const int piece = s2 / b_groups, grp = s2 - piece * b_groups;
-          const uint32_t off = 2 * a_half + piece * b_lbo + (grp * 8 + mm) * 16 + kk * 4;
-          *reinterpret_cast<float*>(st_base + off) = h;
-          *reinterpret_cast<float*>(st_base + b_half + off) = l;
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t d = dst + ((i + rot) & 3) * 16;
+          const float4 h = make_float4(tf32_hi(o[i].x), tf32_hi(o[i].y), tf32_hi(o[i].z), tf32_hi(o[i].w));
+          const float4 l = make_float4(o[i].x - h.x, o[i].y - h.y, o[i].z - h.z, o[i].w - h.w);
+          sts128(d, h);
+          sts128(d + lo_off, l);
         }
       }
+      mbar_arrive(raw_empty(stage));
       fence_proxy_async();
-      mbar_arrive(full_bar(stage));
-      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      mbar_arrive(op_full(op));
+      if (++stage == R) { stage = 0; phase ^= 1u; }
+      if (++op == kWgOpStages) { op = 0; op_phase ^= 1u; }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
                              (static_cast<uint32_t>(kWgM >> 4) << 24);
-      const uint32_t base = smem_u32(smem);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int c = 0; c < n_chunks; ++c) {
-        mbar_wait(full_bar(stage), phase);
+      int op = 0;
+      uint32_t op_phase = 0;
+      int seg = 0;
+      for (int c = 0; c < n_chunks; ++seg) {
+        const int acc = seg & 1;
+        mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(seg) >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t a_hi = base + stage * stage_bytes, a_lo = a_hi + a_half;
-        const uint32_t b_hi = a_hi + 2 * a_half, b_lo = b_hi + b_half;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+        const int seg_end = min(c + kSegChunks, n_chunks);
+        for (int first = 1; c < seg_end; ++c, first = 0) {
+          mbar_wait(op_full(op), op_phase);
+          tc_fence_after();
+          const uint32_t a_hi = op_addr + op * op_bytes, a_lo = a_hi + a_half;
+          const uint32_t b_hi = a_hi + 2 * a_half, b_lo = b_hi + b_half;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const uint64_t da_hi = make_desc(a_hi + s * 2 * a_lbo, a_lbo, 128);
-          const uint64_t db_hi = make_desc(b_hi + s * 2 * b_lbo, b_lbo, 128);
-          umma_tf32(tmem_base, da_hi, db_hi, idesc, (c | s) != 0 ? 1u : 0u);
-          if (p.n_terms == 3) {
-            const uint64_t da_lo = make_desc(a_lo + s * 2 * a_lbo, a_lbo, 128);
-            const uint64_t db_lo = make_desc(b_lo + s * 2 * b_lbo, b_lbo, 128);
-            umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-            umma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+          for (int s = 0; s < 2; ++s) {
+            const uint64_t da_hi = make_desc(a_hi + s * 2 * a_lbo, a_lbo, 128);
+            const uint64_t db_hi = make_desc(b_hi + s * 2 * b_lbo, b_lbo, 128);
+            umma_tf32(d_tmem, da_hi, db_hi, idesc, (first && s == 0) ? 0u : 1u);
+            if (p.n_terms == 3) {
+              const uint64_t da_lo = make_desc(a_lo + s * 2 * a_lbo, a_lbo, 128);
+              const uint64_t db_lo = make_desc(b_lo + s * 2 * b_lbo, b_lbo, 128);
+              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
           }
+          umma_commit(op_empty(op));
+          if (++op == kWgOpStages) { op = 0; op_phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        umma_commit(tfull_bar(acc));
       }
-      umma_commit(done_bar);
     }
     __syncwarp();
   } else {
-    // ================= epilogue: this CTA's partial tile -> workspace =================
+    // ================= epilogue: flush each segment into this CTA's partial tile =================
     float* dst = p.partial + (static_cast<int64_t>(blockIdx.x) * kWgM + tid) * p.n_pad;
-    if (n_chunks > 0) {
-      mbar_wait(done_bar, 0);
+    if (n_chunks == 0) {
+      for (int col = 0; col < p.n_pad; col += 4) *reinterpret_cast<float4*>(dst + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int seg = 0;
+    for (int c = 0; c < n_chunks; c += kSegChunks, ++seg) {
+      const int acc = seg & 1;
+      mbar_wait(tfull_bar(acc), (static_cast<uint32_t>(seg) >> 1) & 1u);
       tc_fence_after();
-      const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
       for (int col0 = 0; col0 < p.n_pad; col0 += 16) {
         uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(col0), r);
+        tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(acc) * 256u + static_cast<uint32_t>(col0), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(dst + col0 + 4 * q) =
-              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                          __uint_as_float(r[4 * q + 3]));
+        for (int q = 0; q < 4; ++q) {
+          float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                 __uint_as_float(r[4 * q + 3]));
+          float4* d4 = reinterpret_cast<float4*>(dst + col0 + 4 * q);
+          if (seg > 0) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *d4 = v;
+        }
       }
-    } else {
-      for (int col = 0; col < p.n_pad; col += 4) *reinterpret_cast<float4*>(dst + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
 // dW_b[m][n] = sum_cta partial[cta][m][n] (n < n1);  dW_c[n - n1][m] = sum_cta partial[cta][m][n] (n >= n1)
@@ -198,17 +253,19 @@ __global__ void k_wgrad_reduce(const float* __restrict__ partial, int n_cta, int
 
 static int round16w(int v) { return (v + 15) / 16 * 16; }
 
-static int wgrad_stages(int n_pad) {
-  const size_t stage = 2 * (static_cast<size_t>(kWgM) * kWgChunk * 4 + static_cast<size_t>(n_pad) * kWgChunk * 4);
-  const int s = static_cast<int>((kWgMaxSmem - 512) / stage);
-  return std::min(s, 6);
+static int wgrad_raw_stages(int f_in, int n_pad, int width) {
+  const size_t op = 2 * (static_cast<size_t>(kWgM) * kWgChunk * 4 + static_cast<size_t>(n_pad) * kWgChunk * 4);
+  const size_t raw = static_cast<size_t>(kWgChunk) * width * 4;
+  const size_t fixed = kWgOpStages * op + (2 * kWgMaxRaw + 8) * 8 + 64;
+  (void)f_in;
+  if (fixed + 2 * raw > static_cast<size_t>(kWgMaxSmem)) return 0;
+  return static_cast<int>(std::min<size_t>(kWgMaxRaw, (kWgMaxSmem - fixed) / raw));
 }
 
 bool wgrad_tc_supported(int n, int f_in, int bd, int hab) {
   if (n < 1 || f_in % 4 || bd % 4 || hab % 4 || f_in > kWgM) return false;
   const int n_pad = round16w(bd + hab);
-  const int slots = 4 * (kWgM / 8) + 4 * (n_pad / 8);      // producer register prefetch: kMaxSlots scalars per thread
-  return n_pad <= 256 && wgrad_stages(n_pad) >= 2 && (slots + 3) / 4 <= kMaxSlots;
+  return n_pad <= 256 && wgrad_raw_stages(f_in, n_pad, f_in + bd + hab) >= 2;
 }
 
 size_t wgrad_tc_workspace(int n, int f_in, int bd, int hab) {
@@ -223,13 +280,17 @@ int wgrad_tc(const float* x, const float* d_bases, const float* d_lin, int n, in
   p.x = x; p.f_in = f_in; p.d1 = d_bases; p.n1 = bd; p.d2 = d_lin; p.n2 = hab; p.n_nodes = n;
   p.n_pad = round16w(bd + hab);
   p.n_terms = n_terms;
-  p.stages = wgrad_stages(p.n_pad);
+  const int width = f_in + bd + hab;
+  p.raw_stages = wgrad_raw_stages(f_in, p.n_pad, width);
+  EGC_REQUIRE(p.raw_stages >= 2, "wgrad_tc: shape does not fit shared memory");
   p.chunks_total = ceil_div(n, kWgChunk);
   const int grid = std::min(sm_count(), p.chunks_total);
   p.chunks_per_cta = ceil_div(p.chunks_total, grid);
+  const uint32_t ppn = static_cast<uint32_t>(width / 4);
+  p.ppn_magic = static_cast<uint32_t>((0x100000000ull + ppn - 1) / ppn);
   p.partial = static_cast<float*>(workspace);
-  const size_t stage = 2 * (static_cast<size_t>(kWgM) * kWgChunk * 4 + static_cast<size_t>(p.n_pad) * kWgChunk * 4);
-  const size_t smem = p.stages * stage + 512;
+  const size_t op = 2 * (static_cast<size_t>(kWgM) * kWgChunk * 4 + static_cast<size_t>(p.n_pad) * kWgChunk * 4);
+  const size_t smem = kWgOpStages * op + static_cast<size_t>(p.raw_stages) * kWgChunk * width * 4 + (2 * kWgMaxRaw + 8) * 8 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     EGC_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgMaxSmem));

@@ -261,13 +261,15 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         grad_out = F._require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
         with torch.cuda.device(x.device):
-            d_w, d_bases_ext, d_bias = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
-                                                            grad_out, need_b and ctx.has_bias)
+            d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
+                                                                  saved_arg, grad_out, need_b and ctx.has_bias,
+                                                                  want_lin_colsum=True)
             d_bases = d_bases_ext[:part.n_local]
             pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
-            d_x, d_wb, d_wc, d_bc = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
-                                                       d_w, need_x, need_wb, need_wc, need_bc and ctx.has_comb_bias,
-                                                       ctx.algo)
+            d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
+                                                    d_w, need_x, need_wb, need_wc, False, ctx.algo)
+            if not (need_bc and ctx.has_comb_bias):
+                d_bc = None
             for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
                 if t is not None:
                     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)

@@ -96,8 +96,10 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
 
 
 def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Tensor, saved: Tensor,
-                       saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0):
-    """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None)."""
+                       saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
+                       want_lin_colsum: bool = False):
+    """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
+    with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias)."""
     lib = _lib.load()
     dev = bases.device
     graph.ensure_csc()
@@ -105,13 +107,17 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
     d_w = torch.empty((desc.n_dst, hab), dtype=torch.float32, device=dev)
     d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev)
     d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if want_bias else None
+    d_lin_sum = torch.empty(hab, dtype=torch.float32, device=dev) if want_lin_colsum else None
     nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
     ws = _ws(nbytes, dev)
     check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
                                 ptr(graph.rowidx), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
                                 graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
-                                ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), flags, ptr(ws), nbytes, _stream()),
+                                ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags, ptr(ws), nbytes,
+                                _stream()),
           "egc_aggregate_bwd")
+    if want_lin_colsum:
+        return d_w, d_bases, d_bias, d_lin_sum
     return d_w, d_bases, d_bias
 
 
@@ -164,10 +170,14 @@ class _EGConvFunction(torch.autograd.Function):
         grad_out = _require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
         with torch.cuda.device(x.device):
-            d_w, d_bases, d_bias = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg, grad_out,
-                                                      need_b and ctx.has_bias, ctx.bwd_flags)
-            d_x, d_wb, d_wc, d_bc = project_backward(x, bases_weight, comb_weight, d_bases, d_w, need_x, need_wb,
-                                                     need_wc, need_bc and ctx.has_comb_bias, ctx.algo)
+            want_bc = bool(need_bc and ctx.has_comb_bias)
+            d_w, d_bases, d_bias, d_bc = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg,
+                                                            grad_out, need_b and ctx.has_bias, ctx.bwd_flags,
+                                                            want_lin_colsum=True)
+            d_x, d_wb, d_wc, _ = project_backward(x, bases_weight, comb_weight, d_bases, d_w, need_x, need_wb,
+                                                  need_wc, False, ctx.algo)
+            if not want_bc:
+                d_bc = None
         return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None
 
 

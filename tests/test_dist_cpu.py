@@ -45,7 +45,8 @@ def _worker(rank, world, port, n, ei, x, go, seed, ret):
         # forward: local projection, halo exchange of basis rows, aggregation over [own | halo]
         bases_loc, w_loc = R.project(x_loc, layer.bases_weight, layer.comb_weight.weight, layer.comb_weight.bias)
         halo = ex.forward(bases_loc.detach())
-        assert torch.equal(halo, (x @ layer.bases_weight.detach())[part.halo_ids])
+        # (a row-sliced matmul may block differently from the full one: equal up to fp64 rounding, not bit-equal)
+        assert rel_err(halo, (x @ layer.bases_weight.detach())[part.halo_ids]) < 1e-13
         halo = halo.requires_grad_(True)
         local_graph = R.OracleGraph(part.rowptr, part.col, part.n_local, part.n_local + part.n_halo, val_sym=part.val_sym)
         agg, _ = R.aggregate(local_graph, torch.cat([bases_loc, halo]), AGGRS)
