@@ -100,7 +100,7 @@ class EGConv(torch.nn.Module):
         if not x.is_cuda:
             raise RuntimeError("egc_b200.EGConv runs on CUDA (sm_100a) only; move the module and inputs to the GPU")
         graph = self._prepare(x, edge_index)
-        flags = _lib.BWD_DETERMINISTIC if self.deterministic else 0
+        flags = (_lib.BWD_DETERMINISTIC if self.deterministic else 0) | int(getattr(self, "bwd_flags", 0))
         return egconv(x, graph, self.bases_weight, self.comb_weight.weight, self.comb_weight.bias, self.bias,
                       self.num_heads, self.num_bases, self.aggregators, self.sigmoid, self.gemm_algo, flags)
 

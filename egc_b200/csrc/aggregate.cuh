@@ -378,5 +378,7 @@ int launch_aggregate_v1(const AggParams& p, int mask, bool linw, bool arg, int s
 // fast path (aggregate_fast.cuh): vec4 rows of <= 128 floats, no per-nnz linear weights, mode 0 only
 int launch_aggregate_fast_g32(const AggParams& p, int mask, bool arg, int smem_bytes, cudaStream_t st);
 int launch_aggregate_fast_g16(const AggParams& p, int mask, bool arg, int smem_bytes, cudaStream_t st);
+// fast path with heads / bases / head dim / aggregator list baked in (aggregate_fast_static.cu); cfg_index from static_cfg_index()
+int launch_aggregate_fast_static(int cfg_index, const AggParams& p, bool arg, int smem_bytes, cudaStream_t st);
 
 }  // namespace egc

@@ -3,7 +3,7 @@
 // min/max routing) and the per-source CSC gather pass (atomic-free d_bases).
 #include <algorithm>
 
-#include "aggregate.cuh"
+#include "aggregate_fast.cuh"
 #include "colsum.cuh"
 
 namespace egc {
@@ -91,6 +91,8 @@ struct CombineBwdParams {
   int vec16;
   int64_t ts_row_stride, ts_stream_stride;   // floats between the streams of consecutive rows / between streams of a row
   float* colsum_part;                        // [grid][HD + HAB] or null
+  int skip_route;                            // diagnostics: drop the min/max routing
+  float* t_route;                            // [n_rows][n_arg][BD] gradients of the min/max slots, routed by k_route_minmax
 };
 
 __device__ __forceinline__ void stage_row(float* dst, const float* src, int n, int lane, bool vec16) {
@@ -112,29 +114,31 @@ __device__ __forceinline__ void stg_stream_f4(float* p, const float (&v)[4]) {
 // once per CTA into shared-memory tables.  The column sums of grad_out (d_bias) and of d_weightings (the
 // gradient of the comb-weight bias) ride along in registers and leave as one partial row per CTA
 // (deterministic: reduced in CTA order by k_colsum_partials).
-template <int EV, bool LINW>
+template <class Cfg, int EV, bool LINW>
 __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_constant__ CombineBwdParams p) {
+  using GB = GetB<Cfg, CombineBwdParams>;
   extern __shared__ __align__(16) float smem_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = p.D, BD = p.BD, HD = p.HD, AB = p.AB, HAB = p.HAB;
+  const int D = GB::D(p), BD = GB::BD(p), HD = GB::HD(p), AB = GB::AB(p), HAB = GB::HAB(p);
   // CTA-wide tables (ints) live behind the per-warp staging areas
-  int* tab_goff = reinterpret_cast<int*>(smem_all + kAggWarps * p.sm_per_warp);   // [HAB] h * D
+  int* tab_goff = reinterpret_cast<int*>(smem_all + kAggWarps * GB::sm_per_warp(p));   // [HAB] h * D
   int* tab_aoff = tab_goff + HAB;                                                  // [HAB] ab * D
   int* tab_std = tab_aoff + HAB;                                                   // [HAB] slot belongs to a std aggregator
-  for (int t = threadIdx.x; t < HAB; t += kAggThreads) {
-    const int h = t / AB, ab = t - h * AB;
-    tab_goff[t] = h * D;
-    tab_aoff[t] = ab * D;
-    tab_std[t] = p.aggr[ab / p.B] == EGC_AGGR_STD ? 1 : 0;
+  if constexpr (!Cfg::kStatic) {
+    for (int t = threadIdx.x; t < HAB; t += kAggThreads) {
+      const int h = t / AB, ab = t - h * AB;
+      tab_goff[t] = h * D;
+      tab_aoff[t] = ab * D;
+      tab_std[t] = p.aggr[ab / GB::B(p)] == EGC_AGGR_STD ? 1 : 0;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
-  float* sm = smem_all + warp * p.sm_per_warp;
+  float* sm = smem_all + warp * GB::sm_per_warp(p);
   const bool v16 = p.vec16 != 0;
-  const float* w = sm + p.sm_w;
-  const float* g = sm + p.sm_g;
-  const float* sv = sm + p.sm_saved;
-  const int* sarg = reinterpret_cast<const int*>(sm + p.sm_arg);
+  const float* w = sm + GB::sm_w(p);
+  const float* g = sm + GB::sm_g(p);
+  const float* sv = sm + GB::sm_saved(p);
   const int nq = D >> 2;
   const int q0 = nq > 0 ? lane % nq : 0, dd0 = lane % D;
   const int warps_total = gridDim.x * kAggWarps;
@@ -148,12 +152,9 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
   }
 
   for (int row = blockIdx.x * kAggWarps + warp; row < p.n_rows; row += warps_total) {
-    stage_row(sm + p.sm_w, p.weightings + static_cast<int64_t>(row) * HAB, HAB, lane, v16);
-    stage_row(sm + p.sm_g, p.grad_out + static_cast<int64_t>(row) * HD, HD, lane, v16);
-    stage_row(sm + p.sm_saved, p.saved + static_cast<int64_t>(row) * p.n_saved * BD, p.n_saved * BD, lane, v16);
-    if (p.n_arg > 0)
-      stage_row(sm + p.sm_arg, reinterpret_cast<const float*>(p.saved_arg) + static_cast<int64_t>(row) * p.n_arg * BD,
-                p.n_arg * BD, lane, v16);
+    stage_row(sm + GB::sm_w(p), p.weightings + static_cast<int64_t>(row) * HAB, HAB, lane, v16);
+    stage_row(sm + GB::sm_g(p), p.grad_out + static_cast<int64_t>(row) * HD, HD, lane, v16);
+    stage_row(sm + GB::sm_saved(p), p.saved + static_cast<int64_t>(row) * GB::n_saved(p) * BD, GB::n_saved(p) * BD, lane, v16);
     const float cntf = static_cast<float>(max(__ldg(p.rowptr + row + 1) - __ldg(p.rowptr + row), 1));
     const float inv_cnt = __frcp_rn(cntf);
     cp_async_wait_all();
@@ -177,9 +178,19 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
 #pragma unroll
     for (int it = 0; it < kCbColIt; ++it) {
       for (int t = lane + 32 * it; t < HAB; t += 32 * kCbColIt) {
-        const bool is_std = tab_std[t] != 0;
-        const float* gh = g + tab_goff[t];
-        const float* aa = sv + tab_aoff[t];
+        bool is_std;
+        const float* gh;
+        const float* aa;
+        if constexpr (Cfg::kStatic) {
+          const int h = t / AB, ab = t - h * AB;
+          is_std = GB::aggr(p, ab / GB::B(p)) == EGC_AGGR_STD;
+          gh = g + h * D;
+          aa = sv + ab * D;
+        } else {
+          is_std = tab_std[t] != 0;
+          gh = g + tab_goff[t];
+          aa = sv + tab_aoff[t];
+        }
         float dot = 0.f;
         if constexpr (EV == 4) {
           int q = q0;
@@ -211,19 +222,21 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
       float t_sym[EV], t_lin[EV], t_sq[EV];
 #pragma unroll
       for (int k = 0; k < EV; ++k) { t_sym[k] = 0.f; t_lin[k] = 0.f; t_sq[k] = 0.f; }
-      for (int a = 0; a < p.A; ++a) {
+#pragma unroll
+      for (int a = 0; a < GB::A(p); ++a) {
         float da[EV];
 #pragma unroll
         for (int k = 0; k < EV; ++k) da[k] = 0.f;
-        const float* wa = w + a * p.B + b;
-        for (int h = 0; h < p.H; ++h) {
+        const float* wa = w + a * GB::B(p) + b;
+#pragma unroll
+        for (int h = 0; h < GB::H(p); ++h) {
           const float wv = wa[h * AB];
           float gv[EV];
           ld_plain<EV>(gv, g + h * D + d);
 #pragma unroll
           for (int k = 0; k < EV; ++k) da[k] = fmaf(wv, gv[k], da[k]);
         }
-        const int code = p.aggr[a];
+        const int code = GB::aggr(p, a);
         if (code == EGC_AGGR_SUM) {
 #pragma unroll
           for (int k = 0; k < EV; ++k) t_lin[k] += da[k];
@@ -234,20 +247,13 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
 #pragma unroll
           for (int k = 0; k < EV; ++k) t_sym[k] += da[k];
         } else if (code == EGC_AGGR_MAX || code == EGC_AGGR_MIN) {
-          const int* args = sarg + p.arg_slot[a] * BD + p0;
-#pragma unroll
-          for (int k = 0; k < EV; ++k) {
-            const int arg = args[k];
-            if (arg >= 0) {
-              float v = da[k];
-              if (LINW) v *= __ldg(p.val_lin + arg);
-              atomicAdd(p.d_bases + static_cast<int64_t>(__ldg(p.col + arg)) * BD + p0 + k, v);
-            }
-          }
+          // routed to the single winning source by k_route_minmax (feature-slab order keeps its atomics in the L2)
+          float* tr = p.t_route + (static_cast<int64_t>(row) * GB::n_arg(p) + GB::arg_slot(p, a)) * BD + p0;
+          if constexpr (EV == 4) stg_stream_f4(tr, da); else st_row<EV>(tr, da);
         } else {   // VAR / STD
           float sa[EV], mean[EV];
           ld_plain<EV>(sa, sv + a * BD + p0);
-          ld_plain<EV>(mean, sv + p.A * BD + p0);
+          ld_plain<EV>(mean, sv + GB::A(p) * BD + p0);
 #pragma unroll
           for (int k = 0; k < EV; ++k) {
             float dv = da[k];
@@ -259,13 +265,13 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
         }
       }
       if constexpr (EV == 4) {
-        if (p.ts_sym >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_sym) * p.ts_stream_stride + p0, t_sym);
-        if (p.ts_lin >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_lin) * p.ts_stream_stride + p0, t_lin);
-        if (p.ts_sq >= 0) stg_stream_f4(ts + static_cast<int64_t>(p.ts_sq) * p.ts_stream_stride + p0, t_sq);
+        if (GB::ts_sym(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
+        if (GB::ts_lin(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
+        if (GB::ts_sq(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
       } else {
-        if (p.ts_sym >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_sym) * p.ts_stream_stride + p0, t_sym);
-        if (p.ts_lin >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_lin) * p.ts_stream_stride + p0, t_lin);
-        if (p.ts_sq >= 0) st_row<EV>(ts + static_cast<int64_t>(p.ts_sq) * p.ts_stream_stride + p0, t_sq);
+        if (GB::ts_sym(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
+        if (GB::ts_lin(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
+        if (GB::ts_sq(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
       }
     }
     __syncwarp();     // the next row overwrites this warp's staging area
@@ -312,6 +318,61 @@ __global__ void k_colsum_partials(const float* __restrict__ part, int n_cta, int
   }
 }
 
+
+// =============================================================================================
+// min/max gradient routing: d_bases[col[arg[i][s][p]]][p] += t_route[i][s][p]   (x val_lin[arg] when weighted)
+// One warp task = 32 consecutive features of kRouteRows consecutive target rows; tasks are ordered
+// feature-slab-major, so at any moment the whole grid adds into one 32-float column slab of d_bases
+// (n_src x 128 B - L2-resident) instead of missing to DRAM all over the [n_src, BD] matrix.
+// =============================================================================================
+constexpr int kRouteRows = 4;
+
+struct RouteParams {
+  const int32_t* saved_arg;    // [n_rows][n_arg][BD] winning nnz position (-1: none)
+  const float* t_route;        // [n_rows][n_arg][BD]
+  const int32_t* col;
+  const float* val_lin;        // or null
+  float* d_bases;              // [n_src][BD]
+  int n_rows, n_arg, BD, n_slabs;
+};
+
+__global__ void __launch_bounds__(256) k_route_minmax(const __grid_constant__ RouteParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int row_groups = (p.n_rows + kRouteRows - 1) / kRouteRows;
+  const int64_t n_tasks = static_cast<int64_t>(p.n_slabs) * p.n_arg * row_groups;
+  const int64_t row_stride = static_cast<int64_t>(p.n_arg) * p.BD;
+  for (int64_t task = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += warps_total) {
+    const int slab_slot = static_cast<int>(task / row_groups);          // slab-major: (slab, slot) outer, rows inner
+    const int rg = static_cast<int>(task - static_cast<int64_t>(slab_slot) * row_groups);
+    const int slab = slab_slot / p.n_arg, slot = slab_slot - slab * p.n_arg;
+    const int f = slab * 32 + lane;
+    if (f >= p.BD) continue;
+    const int64_t base = static_cast<int64_t>(slot) * p.BD + f;
+    int arg[kRouteRows];
+    float v[kRouteRows];
+#pragma unroll
+    for (int r = 0; r < kRouteRows; ++r) {
+      const int row = rg * kRouteRows + r;
+      arg[r] = -1;
+      v[r] = 0.f;
+      if (row < p.n_rows) {
+        arg[r] = __ldcs(p.saved_arg + row * row_stride + base);
+        v[r] = __ldcs(p.t_route + row * row_stride + base);
+      }
+    }
+    int j[kRouteRows];
+#pragma unroll
+    for (int r = 0; r < kRouteRows; ++r) {
+      j[r] = arg[r] >= 0 ? __ldg(p.col + arg[r]) : -1;
+      if (p.val_lin != nullptr && arg[r] >= 0) v[r] *= __ldg(p.val_lin + arg[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kRouteRows; ++r)
+      if (j[r] >= 0) atomicAdd(p.d_bases + static_cast<int64_t>(j[r]) * p.BD + f, v[r]);
+  }
+}
+
 // =============================================================================================
 // backward pass 2: per source column (CSC), gather of the target-side streams, atomic-free
 // =============================================================================================
@@ -331,8 +392,10 @@ struct ScatterParams {
   const float* bases;       // [n_cols, BD]
   float* d_bases;           // [n_cols, BD]
   int n_ts, ts_sym, ts_lin, ts_sq;
+  int64_t ts_row_stride;    // floats between the t-streams of consecutive target rows
+  int64_t off_sym, off_lin, off_sq;   // float offset of each stream inside a row (interleaved) or of its table (stream-major)
   int BD, nvec, G, n_pass;
-  int routed;               // d_bases already holds atomically routed min/max gradients
+  int routed;               // d_bases already holds a partial result (routed min/max gradients, earlier sweeps): accumulate
   int mode;
 };
 
@@ -364,7 +427,8 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
     end = p.colptr[colj + 1];
   }
   const int G = p.G, NG = 32 / G, g = lane / G;
-  const int64_t row_stride = static_cast<int64_t>(p.n_ts) * p.BD;
+  const int64_t row_stride = p.ts_row_stride;
+  const int64_t part_stride = static_cast<int64_t>(p.n_ts) * p.BD;   // chunk partials stay interleaved
 
   for (int pass = 0; pass < p.n_pass; ++pass) {
     const int piece = pass * 32 + (lane & (G - 1));
@@ -393,9 +457,9 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
 #pragma unroll
         for (int u = 0; u < kScatterUnroll; ++u) {
           const float* r = src + i[u] * row_stride;
-          if constexpr ((TSMASK & 1) != 0) ld_row<VEC>(xs[u], r + p.ts_sym * p.BD);
-          if constexpr ((TSMASK & 2) != 0) ld_row<VEC>(xl[u], r + p.ts_lin * p.BD);
-          if constexpr ((TSMASK & 4) != 0) ld_row<VEC>(xq[u], r + p.ts_sq * p.BD);
+          if constexpr ((TSMASK & 1) != 0) ld_row<VEC>(xs[u], r + p.off_sym);
+          if constexpr ((TSMASK & 2) != 0) ld_row<VEC>(xl[u], r + p.off_lin);
+          if constexpr ((TSMASK & 4) != 0) ld_row<VEC>(xq[u], r + p.off_sq);
         }
 #pragma unroll
         for (int u = 0; u < kScatterUnroll; ++u) {
@@ -419,7 +483,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
       const int c0 = p.long_chunk_ptr[long_idx], c1 = p.long_chunk_ptr[long_idx + 1];
 #pragma unroll 4
       for (int c = c0; c < c1; ++c) {
-        const float* q = p.partials + static_cast<int64_t>(c) * row_stride + foff;
+        const float* q = p.partials + static_cast<int64_t>(c) * part_stride + foff;
         float t[VEC];
         if constexpr ((TSMASK & 1) != 0) {
           ld_plain<VEC>(t, q + p.ts_sym * p.BD);
@@ -442,7 +506,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
     const bool writer = active && lane < G;
     if (!writer) continue;
     if (chunk_id >= 0) {
-      float* q = p.partials + static_cast<int64_t>(chunk_id) * row_stride + foff;
+      float* q = p.partials + static_cast<int64_t>(chunk_id) * part_stride + foff;
       if constexpr ((TSMASK & 1) != 0) st_row<VEC>(q + p.ts_sym * p.BD, a_sym);
       if constexpr ((TSMASK & 2) != 0) st_row<VEC>(q + p.ts_lin * p.BD, a_lin);
       if constexpr ((TSMASK & 4) != 0) st_row<VEC>(q + p.ts_sq * p.BD, a_sq);
@@ -518,7 +582,7 @@ static int stream_mask_of(const egc_layer_desc& d, bool& has_route) {
 static int combine_bwd_grid(int n_rows) { return std::max(1, std::min(ceil_div(n_rows, kAggWarps), sm_count() * 4)); }
 
 struct BwdLayout {
-  size_t ts_bytes, csc_part_bytes, colsum_bytes, total;
+  size_t ts_bytes, csc_part_bytes, colsum_bytes, route_bytes, total;
   int n_ts, ts_sym, ts_lin, ts_sq, tsmask;
   bool has_route;
 };
@@ -539,7 +603,8 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   const size_t fused = static_cast<size_t>(combine_bwd_grid(d.n_dst)) * (hd + hab) * sizeof(float) + 256;
   L.colsum_bytes = align_up(std::max(fused, std::max(colsum_workspace_bytes(d.n_dst, static_cast<int>(hd)),
                                                      colsum_workspace_bytes(d.n_dst, static_cast<int>(hab)))), 256);
-  L.total = L.ts_bytes + L.csc_part_bytes + L.colsum_bytes + 256;
+  L.route_bytes = align_up(static_cast<size_t>(d.n_dst) * n_arg_slots(d) * bd * 4, 256);
+  L.total = L.ts_bytes + L.csc_part_bytes + L.colsum_bytes + L.route_bytes + 256;
   return L;
 }
 
@@ -601,7 +666,10 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int hd = desc->heads * desc->dim;
   const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
                     hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) && (desc->dim % 4 != 0 || aligned16(bias));
-  if (fast) {
+  const int static_idx = fast ? static_cfg_index(*desc) : -1;
+  if (static_idx >= 0) {
+    if (int rc = launch_aggregate_fast_static(static_idx, p, want_arg, smem, st)) return rc;
+  } else if (fast) {
     if (int rc = (p.G == 32 ? launch_aggregate_fast_g32 : launch_aggregate_fast_g16)(p, mask, want_arg, smem, st)) return rc;
   } else {
     if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
@@ -646,6 +714,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   float* tstreams = reinterpret_cast<float*>(ws);
   float* csc_part = reinterpret_cast<float*>(ws + L.ts_bytes);
   void* colsum_ws = ws + L.ts_bytes + L.csc_part_bytes;
+  float* t_route = reinterpret_cast<float*>(ws + L.ts_bytes + L.csc_part_bytes + L.colsum_bytes);
 
   const int bd = desc->bases * desc->dim, hd = desc->heads * desc->dim;
   const int hab = desc->heads * desc->n_aggr * desc->bases;
@@ -653,6 +722,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 
   if (L.has_route || L.tsmask == 0)
     EGC_CUDA(cudaMemsetAsync(d_bases, 0, static_cast<size_t>(desc->n_src) * bd * sizeof(float), st));
+
+  // Target-side stream layout.  When the streams together overflow the L2 but one of them fits, they are stored
+  // stream-major ([L][N][BD]) and pass 2 sweeps them one at a time, so every sweep gathers from an L2-resident
+  // table (the partial d_bases is re-read by the later sweeps); otherwise interleaved ([N][L][BD]), one sweep.
+  const size_t one_stream = static_cast<size_t>(desc->n_dst) * bd * sizeof(float);
+  const bool stream_major = L.n_ts >= 2 && one_stream * L.n_ts > (size_t{72} << 20) && one_stream <= (size_t{100} << 20) &&
+                            (flags & EGC_BWD_STREAM_SWEEPS) != 0;
 
   // ---- pass 1: streaming over target nodes
   bool fuse_colsum = false;
@@ -680,8 +756,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     c.sm_per_warp = off;
     const int smem = (off * kAggWarps + 3 * hab) * static_cast<int>(sizeof(float));    // staging areas + index tables
     EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
-    c.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;
-    c.ts_stream_stride = bd;
+    c.ts_row_stride = stream_major ? bd : static_cast<int64_t>(L.n_ts) * bd;
+    c.ts_stream_stride = stream_major ? static_cast<int64_t>(desc->n_dst) * bd : bd;
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
                aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
@@ -691,18 +767,35 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     fuse_colsum = (d_bias != nullptr || d_lin_colsum != nullptr) && hab <= 32 * kCbColIt &&
                   hd <= 32 * kCbColIt * (ev4 ? 4 : 1);
     c.colsum_part = fuse_colsum ? static_cast<float*>(colsum_ws) : nullptr;
-#define EGC_LAUNCH_COMBINE(EV, LW)                                                                             \
+    c.skip_route = (flags & EGC_BWD_SKIP_ROUTING) ? 1 : 0;
+    c.t_route = t_route;
+#define EGC_LAUNCH_COMBINE_CFG(CFG, EV, LW)                                                                    \
     {                                                                                                          \
-      auto kern = k_combine_bwd<EV, LW>;                                                                       \
+      auto kern = k_combine_bwd<CFG, EV, LW>;                                                                    \
       if (smem > 48 * 1024) EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       LaunchScope egc_ls_("k_combine_bwd", st);                                                                \
       kern<<<grid, kAggThreads, smem, st>>>(c);                                                                \
     }
-    if (ev4 && !linw) EGC_LAUNCH_COMBINE(4, false)
-    else if (ev4 && linw) EGC_LAUNCH_COMBINE(4, true)
-    else if (!linw) EGC_LAUNCH_COMBINE(1, false)
-    else EGC_LAUNCH_COMBINE(1, true)
-#undef EGC_LAUNCH_COMBINE
+    using Dyn = DynCfg<0, 32>;
+    const int static_idx = (ev4 && !linw && c.vec16) ? static_cfg_index(*desc) : -1;
+    bool launched = false;
+#define X(I, ...)                                                                                              \
+    if (!launched && static_idx == I) {                                                                        \
+      using SC = StaticCfg<__VA_ARGS__>;                                                                       \
+      EGC_REQUIRE(SC::bsm_per_warp == c.sm_per_warp && SC::bsm_saved == c.sm_saved && SC::bsm_arg == c.sm_arg && \
+                  SC::ts_sym == c.ts_sym && SC::ts_lin == c.ts_lin && SC::ts_sq == c.ts_sq,                    \
+                  "egc_aggregate_bwd: static configuration %d disagrees with the host layout", I);             \
+      EGC_LAUNCH_COMBINE_CFG(SC, 4, false)                                                                     \
+      launched = true;                                                                                         \
+    }
+    EGC_STATIC_CFGS(X)
+#undef X
+    if (launched) {
+    } else if (ev4 && !linw) EGC_LAUNCH_COMBINE_CFG(Dyn, 4, false)
+    else if (ev4 && linw) EGC_LAUNCH_COMBINE_CFG(Dyn, 4, true)
+    else if (!linw) EGC_LAUNCH_COMBINE_CFG(Dyn, 1, false)
+    else EGC_LAUNCH_COMBINE_CFG(Dyn, 1, true)
+#undef EGC_LAUNCH_COMBINE_CFG
     EGC_LAUNCH_CHECK("k_combine_bwd");
     if (fuse_colsum) {
       {
@@ -711,6 +804,20 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       }
       EGC_LAUNCH_CHECK("k_colsum_partials");
     }
+  }
+
+  // ---- min/max routing (feature-slab-major atomics)
+  if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
+    RouteParams r{};
+    r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
+    r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);
+    const int64_t tasks = static_cast<int64_t>(r.n_slabs) * n_arg * ceil_div(desc->n_dst, kRouteRows);
+    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(tasks, 8), static_cast<int64_t>(sm_count()) * 8));
+    {
+      LaunchScope egc_ls_("k_route_minmax", st);
+      k_route_minmax<<<grid, 256, 0, st>>>(r);
+    }
+    EGC_LAUNCH_CHECK("k_route_minmax");
   }
 
   // ---- pass 2: per source column (CSC), atomic-free
@@ -729,12 +836,23 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
-    s.routed = L.has_route ? 1 : 0;
-    s.mode = 0;
-    if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
-    if (s.n_long > 0) {
-      s.mode = 1;
-      if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
+    const int64_t table = static_cast<int64_t>(desc->n_dst) * bd;
+    s.ts_row_stride = stream_major ? bd : static_cast<int64_t>(L.n_ts) * bd;
+    s.off_sym = L.ts_sym < 0 ? 0 : (stream_major ? L.ts_sym * table : static_cast<int64_t>(L.ts_sym) * bd);
+    s.off_lin = L.ts_lin < 0 ? 0 : (stream_major ? L.ts_lin * table : static_cast<int64_t>(L.ts_lin) * bd);
+    s.off_sq = L.ts_sq < 0 ? 0 : (stream_major ? L.ts_sq * table : static_cast<int64_t>(L.ts_sq) * bd);
+    bool accumulate = L.has_route;
+    for (int bit = 1; bit <= 4; bit <<= 1) {
+      const int sweep_mask = stream_major ? (L.tsmask & bit) : (bit == 1 ? L.tsmask : 0);
+      if (sweep_mask == 0) continue;
+      s.routed = accumulate ? 1 : 0;
+      s.mode = 0;
+      if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
+      if (s.n_long > 0) {
+        s.mode = 1;
+        if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
+      }
+      accumulate = true;
     }
   }
 
