@@ -20,6 +20,8 @@
 // (CTA c serves group c % n_split); the groups walk the row tiles in lockstep, so the second read of an A
 // tile is an L2 hit.  The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile t
 // overlaps the main loop of tile t+1.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "project.cuh"
@@ -33,8 +35,10 @@ constexpr int kChunkK = 16;                                   // floats of K per
 constexpr int kChunkBytes = kTileM * kChunkK * 4;             // 8 KB (raw / hi, or lo)
 constexpr int kLoStages = 4;
 constexpr int kMaxRawStages = 16;
-constexpr int kCopyThreads = 64;
-constexpr int kConvThreads = 128;
+constexpr int kCopyWarps = 2;
+constexpr int kConvWarps = 4;                                 // == kLoStages: converter warp w owns lo slot w
+constexpr int kEpiRowBytes = 144;                             // 32 floats + 16 B pad: conflict-free row-per-thread stores
+constexpr int kEpiStageBytes = 4 * 32 * kEpiRowBytes;         // one 32 x 32 staging tile per epilogue warp
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kTmemCols = 512;
 
@@ -74,7 +78,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   uint8_t* b_hi = smem;
   uint8_t* b_lo = smem + b_half_bytes;
   uint8_t* lo_ring = smem + 2 * b_half_bytes;
-  uint8_t* raw_ring = lo_ring + kLoStages * kChunkBytes;
+  uint8_t* epi_stage = lo_ring + kLoStages * kChunkBytes;
+  uint8_t* raw_ring = epi_stage + kEpiStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + static_cast<size_t>(R) * kChunkBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxRawStages + kLoStages + 4);
   const uint32_t bar0 = smem_u32(bars);
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * R + kLoStages + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), kCopyThreads); mbar_init(raw_empty(s), 1); mbar_init(conv_full(s), kConvThreads); }
+    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), 32); mbar_init(raw_empty(s), 1); mbar_init(conv_full(s), 32); }
     for (int s = 0; s < kLoStages; ++s) mbar_init(lo_empty(s), 1);
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
     fence_barrier_init();
@@ -137,60 +142,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
 
   const int n_chunks = p.k_pad / kChunkK;
   const int first_tile = blockIdx.x / p.n_split, tile_step = gridDim.x / p.n_split;
+  const int my_tiles = first_tile < p.num_tiles ? (p.num_tiles - first_tile + tile_step - 1) / tile_step : 0;
+  const int total_chunks = my_tiles * n_chunks;
   const uint32_t raw_addr = smem_u32(raw_ring), lo_addr = smem_u32(lo_ring);
 
   if (warp >= 9) {
-    // ================= copy producers: raw A chunks, global -> shared ring =================
-    const int pt = tid - 9 * 32;
-    const int c = pt & 3, r0 = pt >> 2;                       // 16-byte K piece, first row (rows r0 + 16 i)
-    int stage = 0;
+    // ================= copy producers: each warp owns every other chunk =================
+    const int pw = warp - 9;
+    const int c4 = lane & 3, r0 = lane >> 2;                   // 16-byte K piece, first row (rows r0 + 8 i)
+    int stage = pw % R;
     uint32_t phase = 0;
-    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-      const int64_t row_base = static_cast<int64_t>(tile) * kTileM;
-      for (int j = 0; j < n_chunks; ++j) {
-        const int k = j * kChunkK + 4 * c;
-        const float* base;
-        int64_t ld;
-        if (k < p.k1) { base = p.a1 + k; ld = p.lda1; } else { base = p.a2 + (k - p.k1); ld = p.lda2; }
-        const bool k_ok = k < K;
-        mbar_wait(raw_empty(stage), phase ^ 1u);
-        const uint32_t dst = raw_addr + stage * kChunkBytes + c * (kTileM * 16) + r0 * 16;
+    int t = 0, j = pw;                                         // chunk -> (local tile, chunk in tile)
+    while (j >= n_chunks) { j -= n_chunks; ++t; }
+    for (int c = pw; c < total_chunks; c += kCopyWarps) {
+      const int64_t row_base = static_cast<int64_t>(first_tile + t * tile_step) * kTileM;
+      const int k = j * kChunkK + 4 * c4;
+      const float* base;
+      int64_t ld;
+      if (k < p.k1) { base = p.a1 + k; ld = p.lda1; } else { base = p.a2 + (k - p.k1); ld = p.lda2; }
+      const bool k_ok = k < K;
+      mbar_wait(raw_empty(stage), phase ^ 1u);
+      const uint32_t dst = raw_addr + stage * kChunkBytes + c4 * (kTileM * 16) + r0 * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t row = row_base + r0 + 16 * i;
-          const bool ok = k_ok && row < p.M;
-          cp_async_16_zfill(dst + i * 256, ok ? base + row * ld : p.a1, ok ? 16u : 0u);
-        }
-        cp_async_mbar_arrive_noinc(raw_full(stage));
-        if (++stage == R) { stage = 0; phase ^= 1u; }
+      for (int i = 0; i < 16; ++i) {
+        const int64_t row = row_base + r0 + 8 * i;
+        const bool ok = k_ok && row < p.M;
+        cp_async_16_zfill(dst + i * 128, ok ? base + row * ld : p.a1, ok ? 16u : 0u);
       }
+      cp_async_mbar_arrive_noinc(raw_full(stage));
+      stage += kCopyWarps;
+      if (stage >= R) { stage -= R; phase ^= 1u; }
+      j += kCopyWarps;
+      while (j >= n_chunks) { j -= n_chunks; ++t; }
     }
   } else if (warp >= 5) {
-    // ================= converters: raw -> hi (in place) + lo =================
-    const int ct = tid - 5 * 32;
-    int stage = 0, lo = 0;
+    // ================= converters: each warp owns every 4th chunk and one lo slot =================
+    // kind::tf32 ignores the 13 low mantissa bits of its operands, so the raw chunk IS the hi operand:
+    // only lo = a - (a & 0xffffe000) has to be produced.
+    const int cw = warp - 5;
+    int stage = cw % R;
     uint32_t phase = 0, lo_phase = 0;
-    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-      for (int j = 0; j < n_chunks; ++j) {
-        mbar_wait(raw_full(stage), phase);
-        const uint32_t src = raw_addr + stage * kChunkBytes + ct * 16;
-        float4 v[4];
+    for (int c = cw; c < total_chunks; c += kConvWarps) {
+      mbar_wait(raw_full(stage), phase);
+      const uint32_t src = raw_addr + stage * kChunkBytes + lane * 16;
+      float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = lds128(src + i * 2048);
-        mbar_wait(lo_empty(lo), lo_phase ^ 1u);
-        const uint32_t dlo = lo_addr + lo * kChunkBytes + ct * 16;
+      for (int i = 0; i < 16; ++i) v[i] = lds128(src + i * 512);
+      mbar_wait(lo_empty(cw), lo_phase ^ 1u);
+      const uint32_t dlo = lo_addr + cw * kChunkBytes + lane * 16;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-          const float4 l = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-          sts128(src + i * 2048, h);
-          sts128(dlo + i * 2048, l);
-        }
-        fence_proxy_async();
-        mbar_arrive(conv_full(stage));
-        if (++stage == R) { stage = 0; phase ^= 1u; }
-        if (++lo == kLoStages) { lo = 0; lo_phase ^= 1u; }
+      for (int i = 0; i < 16; ++i) {
+        const float4 l = make_float4(v[i].x - tf32_hi(v[i].x), v[i].y - tf32_hi(v[i].y), v[i].z - tf32_hi(v[i].z),
+                                     v[i].w - tf32_hi(v[i].w));
+        sts128(dlo + i * 512, l);
       }
+      fence_proxy_async();
+      mbar_arrive(conv_full(stage));
+      stage += kConvWarps;
+      if (stage >= R) { stage -= R; phase ^= 1u; }
+      lo_phase ^= 1u;
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -201,8 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       const uint32_t b_hi_addr = smem_u32(b_hi), b_lo_addr = smem_u32(b_lo);
       int stage = 0, lo = 0;
       uint32_t phase = 0;
-      int t = 0;
-      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
+      for (int t = 0; t < my_tiles; ++t) {
         const int acc = t & 1;
         mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
               umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
             }
           }
-          umma_commit(raw_empty(stage));          // frees the raw / hi slot once these MMAs have read it
+          umma_commit(raw_empty(stage));          // frees the raw (= hi) slot once these MMAs have read it
           umma_commit(lo_empty(lo));
           if (++stage == R) { stage = 0; phase ^= 1u; }
           if (++lo == kLoStages) lo = 0;
@@ -234,42 +243,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
     }
     __syncwarp();
   } else {
-    // ================= epilogue: TMEM -> registers -> global =================
+    // ================= epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global stores =====
+    // tcgen05.ld gives one accumulator row per thread; storing that directly would touch 32 different 128-byte
+    // lines per instruction.  Each warp bounces 32 rows x 32 columns through a padded staging tile so that
+    // every store instruction writes 4 rows x 128 contiguous bytes.
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const int n_end = n_begin + n_count;
-    int t = 0;
-    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, ++t) {
+    const uint32_t stage_addr = smem_u32(epi_stage) + warp * (32 * kEpiRowBytes);
+    const int rr = lane >> 3, piece = lane & 7;                 // read-back geometry: 4 rows x 8 pieces per instruction
+    for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
       mbar_wait(tfull_bar(acc), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(tile) * kTileM + tid;
-      const bool valid = row < p.M;
-      float* o1 = p.c1 + row * p.ldc1;
-      float* o2 = p.c2 != nullptr ? p.c2 + row * p.ldc2 : nullptr;
-      for (int col0 = 0; col0 < n_pad; col0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + static_cast<uint32_t>(acc) * 256u + static_cast<uint32_t>(col0), r);
-        tmem_ld_wait();
-        if (valid) {
+      const int64_t row0 = static_cast<int64_t>(first_tile + t * tile_step) * kTileM + warp * 32;
+      for (int col0 = 0; col0 < n_pad; col0 += 32) {
+        const int width = min(32, n_pad - col0);              // 16 or 32 columns in this block
+        uint32_t r[32];
+        {
+          uint32_t (&ra)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+          uint32_t (&rb)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
+          const uint32_t taddr = tmem_base + lane_base + static_cast<uint32_t>(acc) * 256u + static_cast<uint32_t>(col0);
+          tmem_ld16(taddr, ra);
+          if (width > 16) tmem_ld16(taddr + 16u, rb);
+          tmem_ld_wait();
+        }
+        __syncwarp();                                          // previous block fully read back
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = n_begin + col0 + 4 * q;
-            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (col >= n_end) {
-            } else if (col < p.n1) {
-              __stcs(reinterpret_cast<float4*>(o1 + col), v);
-            } else {
-              const int c2 = col - p.n1;
-              if (p.bias2 != nullptr) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + c2));
+        for (int q = 0; q < 8; ++q)
+          if (4 * q < width)
+            sts128(stage_addr + lane * kEpiRowBytes + q * 16,
+                   make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                               __uint_as_float(r[4 * q + 3])));
+        __syncwarp();
+        const int col = n_begin + col0 + 4 * piece;
+        if (4 * piece < width && col < n_end) {
+          const bool to_c1 = col < p.n1;
+          const int c2 = col - p.n1;
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!to_c1 && p.bias2 != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + c2));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + rr;
+            const int64_t row = row0 + rl;
+            float4 v = lds128(stage_addr + rl * kEpiRowBytes + piece * 16);
+            if (row < p.M) {
+              if (to_c1) {
+                __stcs(reinterpret_cast<float4*>(p.c1 + row * p.ldc1 + col), v);
+              } else {
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                if (p.sigmoid2) {
+                  v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
+                  v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
+                }
+                __stcs(reinterpret_cast<float4*>(p.c2 + row * p.ldc2 + c2), v);
               }
-              if (p.sigmoid2) {
-                v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
-                v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
-              }
-              __stcs(reinterpret_cast<float4*>(o2 + c2), v);
             }
           }
         }
@@ -294,7 +321,7 @@ struct TcPlan { int n_split, cols_per_group, raw_stages; size_t smem; };
 // smallest column split that leaves a deep A ring next to the resident weights
 static bool tc_plan(int k, int n, TcPlan& out) {
   const int k_pad = round16(k);
-  const size_t fixed = static_cast<size_t>(kLoStages) * kChunkBytes + (3 * kMaxRawStages + kLoStages + 4) * 8 + 64;
+  const size_t fixed = static_cast<size_t>(kLoStages) * kChunkBytes + kEpiStageBytes + (3 * kMaxRawStages + kLoStages + 4) * 8 + 64;
   TcPlan best{0, 0, 0, 0};
   for (int s = 1; s <= 4; ++s) {
     const int cpg = round16(ceil_div(n, s));
@@ -306,7 +333,7 @@ static bool tc_plan(int k, int n, TcPlan& out) {
     if (r >= 8) break;
   }
   out = best;
-  return best.raw_stages >= 2;
+  return best.raw_stages >= kConvWarps;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
