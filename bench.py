@@ -99,18 +99,34 @@ def algorithmic_bytes(n, e, f_in, heads, bases, dim, aggrs):
 
 
 def kernel_algorithmic_bytes(n, e, f_in, heads, bases, dim, aggrs):
-    """Unique bytes each kernel of the step must move (DESIGN.md 'kernels'); same accounting as above."""
+    """Unique bytes each kernel of the step must move PER LAUNCH (DESIGN.md 'kernels'); same accounting as above."""
     a, bd, f_out = len(aggrs), bases * dim, heads * dim
     hab = heads * a * bases
     sym, lin, sq, n_arg = stream_counts(aggrs)
     L = sym + lin + sq
+    s_saved = a + (1 if sq else 0)
     csr = 4 * (e + n + 1)
     return {
-        "k_gemm_f32": None,   # several launches of different shapes; reported through the step total
-        "k_aggregate_fwd": 4 * n * (bd + hab + f_out) + csr + 4 * n * sym,
-        "k_aggregate_bwd": 4 * n * (bd + hab + f_out + hab + L * bd) + csr + 4 * n * sym,
-        "k_scatter_bwd": 4 * n * (L * bd + bd + (bd if sq else 0) + (bd if n_arg else 0)) + csr,
+        # x (or [d_bases | d_lin]) in, [bases | weightings] (or d_x) out: both launches move the same bytes
+        "k_project_tc": 4 * n * (f_in + bd + hab),
+        "k_wgrad_tc": 4 * n * (f_in + bd + hab),
+        # training forward: gather table + weightings in, out + saved aggregates + saved argmax out, CSR + symnorm weights
+        "k_aggregate_fwd": 4 * n * (bd + hab + f_out + s_saved * bd + n_arg * bd) + csr + 4 * e * sym,
+        # per target: grad_out, weightings, saved in; d_weightings, t-streams, routed min/max gradients out
+        "k_combine_bwd": 4 * n * (f_out + hab + s_saved * bd + hab + L * bd + n_arg * bd),
+        "k_route_minmax": 4 * n * n_arg * bd * 2 + (8 * n * bd if n_arg else 0),
+        # per source (CSC): t-streams in, d_bases out (+ bases for the var/std term, + the routed partial), CSC + weights
+        "k_scatter_bwd": 4 * n * (L * bd + bd + (bd if sq else 0) + (bd if n_arg else 0)) + csr + 4 * e * sym,
     }
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -336,7 +352,7 @@ def run_single_gpu(args, w, n, edge_index):
         per_launch_ms = prof[dom][1] / prof[dom][0]
         achieved = kbytes[dom] / (per_launch_ms * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": measured_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kbytes[dom], "ms_per_launch": per_launch_ms}
     step_gbs = (bf + bb) / (ms * 1e-3) / 1e9
 

@@ -2,6 +2,7 @@
 
 Public surface (mirrors the reference operator API, /root/reference/experiments/optimized_layers.py):
     EGConv            drop-in layer
+    EfficientGraphConv  the paper variant (reference experiments/layers.py) as an adapter over the same kernels
     SparseTensor      minimal `torch_sparse.SparseTensor` container accepted by EGConv.forward
     GraphStructure    prepared device graph (CSR / CSC / symnorm weights / long-row plan)
     egconv            functional form on a prepared graph
@@ -9,6 +10,7 @@ Public surface (mirrors the reference operator API, /root/reference/experiments/
 """
 from ._lib import (BWD_DETERMINISTIC, GEMM_3XTF32, GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, EGCError, build,  # noqa: F401
                    load)
+from .compat import EfficientGraphConv, convert_paper_state_dict, paper_to_egconv_perm  # noqa: F401
 from .conv import EGConv  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
 from .graph import GraphStructure, SparseTensor  # noqa: F401

@@ -42,6 +42,7 @@ struct AggParams {
   const int32_t* chunk_begin;
   float* partials;
   int n_slots;
+  int* long_counter;         // [n_long] zero on entry: chunk warps count in, the last one merges (fast kernel)
   // features
   const float* bases;        // [n_src, BD]
   const float* weightings;   // [n_rows, HAB]
@@ -88,6 +89,18 @@ __device__ __forceinline__ void ld_plain(float (&v)[VEC], const float* p) {
   } else {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) v[k] = p[k];
+  }
+}
+
+// L2-only load (data written by other SMs during this kernel)
+template <int VEC>
+__device__ __forceinline__ void ld_cg(float (&v)[VEC], const float* p) {
+  if constexpr (VEC == 4) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = __ldcg(p + k);
   }
 }
 
@@ -233,34 +246,34 @@ struct Acc {
     int s = 0;
     float t[VEC], u[VEC];
     if constexpr (MASK & P_SUM) {
-      ld_plain<VEC>(t, p + s * BD); ++s;
+      ld_cg<VEC>(t, p + s * BD); ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) sum[k] = __fadd_rn(sum[k], t[k]);
     }
     if constexpr (MASK & P_SYM) {
-      ld_plain<VEC>(t, p + s * BD); ++s;
+      ld_cg<VEC>(t, p + s * BD); ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) sym[k] = __fadd_rn(sym[k], t[k]);
     }
     if constexpr (MASK & P_SQ) {
-      ld_plain<VEC>(t, p + s * BD); ++s;
+      ld_cg<VEC>(t, p + s * BD); ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) sq[k] = __fadd_rn(sq[k], t[k]);
     }
     if constexpr (MASK & P_MAX) {
-      ld_plain<VEC>(t, p + s * BD); ++s;
+      ld_cg<VEC>(t, p + s * BD); ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) u[k] = 0.f;
-      if constexpr (ARG) ld_plain<VEC>(u, p + s * BD);
+      if constexpr (ARG) ld_cg<VEC>(u, p + s * BD);
       ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) merge_max(k, t[k], __float_as_int(u[k]));
     }
     if constexpr (MASK & P_MIN) {
-      ld_plain<VEC>(t, p + s * BD); ++s;
+      ld_cg<VEC>(t, p + s * BD); ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) u[k] = 0.f;
-      if constexpr (ARG) ld_plain<VEC>(u, p + s * BD);
+      if constexpr (ARG) ld_cg<VEC>(u, p + s * BD);
       ++s;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) merge_min(k, t[k], __float_as_int(u[k]));

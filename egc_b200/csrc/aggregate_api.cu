@@ -264,15 +264,10 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
           }
         }
       }
-      if constexpr (EV == 4) {
-        if (GB::ts_sym(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
-        if (GB::ts_lin(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
-        if (GB::ts_sq(p) >= 0) stg_stream_f4(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
-      } else {
-        if (GB::ts_sym(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
-        if (GB::ts_lin(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
-        if (GB::ts_sq(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
-      }
+      // plain (L2 write-back) stores: pass 2 gathers these rows next, whatever part of them survives in the L2 is a hit
+      if (GB::ts_sym(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
+      if (GB::ts_lin(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
+      if (GB::ts_sq(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
     }
     __syncwarp();     // the next row overwrites this warp's staging area
   }
@@ -397,12 +392,14 @@ struct ScatterParams {
   int BD, nvec, G, n_pass;
   int routed;               // d_bases already holds a partial result (routed min/max gradients, earlier sweeps): accumulate
   int mode;
+  int* long_counter;        // [n_long] zero on entry, or null: long columns are merged by a second launch (mode 1)
 };
 
 constexpr int kScatterUnroll = 4;
 
+// single-stream instances are lean enough for 4 resident CTAs (<= 64 registers); multi-stream ones get 3
 template <int TSMASK, int VEC, bool LINW>
-__global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_constant__ ScatterParams p) {
+__global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 : 3) k_scatter_bwd(const __grid_constant__ ScatterParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kAggWarps + warp;
   int colj, begin, end, chunk_id = -1, long_idx = -1;
@@ -427,7 +424,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
     end = p.colptr[colj + 1];
   }
   const int G = p.G, NG = 32 / G, g = lane / G;
-  const int64_t row_stride = p.ts_row_stride;
+  const uint32_t row_stride = static_cast<uint32_t>(p.ts_row_stride);   // n_dst * row_stride < 2^32 (checked by the host)
   const int64_t part_stride = static_cast<int64_t>(p.n_ts) * p.BD;   // chunk partials stay interleaved
 
   for (int pass = 0; pass < p.n_pass; ++pass) {
@@ -439,7 +436,9 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
     for (int k = 0; k < VEC; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
 
     if (p.mode == 0) {
-      const float* __restrict__ src = p.tstreams + foff;
+      const float* __restrict__ src_sym = p.tstreams + p.off_sym + foff;
+      const float* __restrict__ src_lin = p.tstreams + p.off_lin + foff;
+      const float* __restrict__ src_sq = p.tstreams + p.off_sq + foff;
       const int last = end - 1;
       for (int e0 = begin + g; e0 < end + g; e0 += kScatterUnroll * NG) {
         int i[kScatterUnroll];
@@ -456,10 +455,10 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
         float xs[kScatterUnroll][VEC], xl[kScatterUnroll][VEC], xq[kScatterUnroll][VEC];
 #pragma unroll
         for (int u = 0; u < kScatterUnroll; ++u) {
-          const float* r = src + i[u] * row_stride;
-          if constexpr ((TSMASK & 1) != 0) ld_row<VEC>(xs[u], r + p.off_sym);
-          if constexpr ((TSMASK & 2) != 0) ld_row<VEC>(xl[u], r + p.off_lin);
-          if constexpr ((TSMASK & 4) != 0) ld_row<VEC>(xq[u], r + p.off_sq);
+          const size_t r = static_cast<size_t>(static_cast<uint32_t>(i[u]) * row_stride);
+          if constexpr ((TSMASK & 1) != 0) ld_row<VEC>(xs[u], src_sym + r);
+          if constexpr ((TSMASK & 2) != 0) ld_row<VEC>(xl[u], src_lin + r);
+          if constexpr ((TSMASK & 4) != 0) ld_row<VEC>(xq[u], src_sq + r);
         }
 #pragma unroll
         for (int u = 0; u < kScatterUnroll; ++u) {
@@ -504,14 +503,53 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_bwd(const __grid_con
     }
 
     const bool writer = active && lane < G;
-    if (!writer) continue;
     if (chunk_id >= 0) {
-      float* q = p.partials + static_cast<int64_t>(chunk_id) * part_stride + foff;
-      if constexpr ((TSMASK & 1) != 0) st_row<VEC>(q + p.ts_sym * p.BD, a_sym);
-      if constexpr ((TSMASK & 2) != 0) st_row<VEC>(q + p.ts_lin * p.BD, a_lin);
-      if constexpr ((TSMASK & 4) != 0) st_row<VEC>(q + p.ts_sq * p.BD, a_sq);
-      continue;
+      if (writer) {
+        float* q = p.partials + static_cast<int64_t>(chunk_id) * part_stride + foff;
+        if constexpr ((TSMASK & 1) != 0) st_row<VEC>(q + p.ts_sym * p.BD, a_sym);
+        if constexpr ((TSMASK & 2) != 0) st_row<VEC>(q + p.ts_lin * p.BD, a_lin);
+        if constexpr ((TSMASK & 4) != 0) st_row<VEC>(q + p.ts_sq * p.BD, a_sq);
+      }
+      if (p.long_counter == nullptr) continue;               // separate merge launch (mode 1) sums the partials
+      // single-pass rows: the last chunk warp of the column to arrive sums all partials in chunk order
+      __threadfence();
+      __syncwarp();
+      int lo = 0, hi = p.n_long;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.long_chunk_ptr + mid) <= chunk_id) lo = mid; else hi = mid;
+      }
+      const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
+      int last = 0;
+      if (lane == 0) last = atomicAdd(p.long_counter + lo, 1) == c1 - c0 - 1 ? 1 : 0;
+      last = __shfl_sync(kFull, last, 0);
+      if (!last) continue;
+      __threadfence();
+      if (lane == 0) p.long_counter[lo] = 0;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
+      for (int c = c0; c < c1; ++c) {
+        const float* q = p.partials + static_cast<int64_t>(c) * part_stride + foff;
+        float t[VEC];
+        if constexpr ((TSMASK & 1) != 0) {
+          ld_cg<VEC>(t, q + p.ts_sym * p.BD);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a_sym[k] += t[k];
+        }
+        if constexpr ((TSMASK & 2) != 0) {
+          ld_cg<VEC>(t, q + p.ts_lin * p.BD);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a_lin[k] += t[k];
+        }
+        if constexpr ((TSMASK & 4) != 0) {
+          ld_cg<VEC>(t, q + p.ts_sq * p.BD);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) a_sq[k] += t[k];
+        }
+      }
+      chunk_id = -1;                                         // falls through to the final write of column colj
     }
+    if (!writer) continue;
     float* dst = p.d_bases + static_cast<int64_t>(colj) * p.BD + foff;
     float r[VEC];
 #pragma unroll
@@ -597,7 +635,8 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   L.n_ts = s;
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
-  L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256);
+  L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256) +
+                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * sizeof(int), 256);
   // per-CTA column-sum partials of the fused pass-1 kernel, or the two-stage colsum scratch when it cannot fuse
   const size_t hd = static_cast<size_t>(d.heads) * d.dim, hab = static_cast<size_t>(d.heads) * d.n_aggr * d.bases;
   const size_t fused = static_cast<size_t>(combine_bwd_grid(d.n_dst)) * (hd + hab) * sizeof(float) + 256;
@@ -622,7 +661,8 @@ size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
   const int mask = prim_mask_of(*desc);
   if (mask <= 0) return 0;
   const size_t bd = static_cast<size_t>(desc->bases) * desc->dim;
-  return align_up(static_cast<size_t>(plan ? plan->n_chunks : 0) * n_slots_of_mask(mask) * bd * 4, 256) + 256;
+  return align_up(static_cast<size_t>(plan ? plan->n_chunks : 0) * n_slots_of_mask(mask) * bd * 4, 256) +
+         align_up(static_cast<size_t>(plan ? plan->n_long : 0) * sizeof(int), 256) + 256;
 }
 
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_sym,
@@ -655,6 +695,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   set_plan(p, plan);
   p.partials = static_cast<float*>(workspace);
   p.n_slots = n_slots_of_mask(mask);
+  p.long_counter = reinterpret_cast<int*>(static_cast<char*>(workspace) +
+                                          align_up(static_cast<size_t>(p.n_chunks) * p.n_slots * bd * 4, 256));
   p.bases = bases; p.weightings = weightings; p.bias = bias;
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
@@ -667,6 +709,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
                     hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) && (desc->dim % 4 != 0 || aligned16(bias));
   const int static_idx = fast ? static_cfg_index(*desc) : -1;
+  if (fast && p.n_long > 0) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, static_cast<size_t>(p.n_long) * sizeof(int), st));
   if (static_idx >= 0) {
     if (int rc = launch_aggregate_fast_static(static_idx, p, want_arg, smem, st)) return rc;
   } else if (fast) {
@@ -674,7 +717,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   } else {
     if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
   }
-  if (p.n_long > 0) {
+  if (p.n_long > 0 && !fast) {                  // the fast kernels merge long rows themselves
     p.mode = 1;
     if (int rc = launch(p, mask, val_lin != nullptr, want_arg, smem, st)) return rc;
   }
@@ -709,6 +752,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   EGC_REQUIRE((val_lin == nullptr) == (csc_val_lin == nullptr), "egc_aggregate_bwd: val_lin and csc_val_lin must come together");
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_bwd: val_lin cannot be combined with symnorm");
   EGC_REQUIRE(workspace_bytes >= L.total, "egc_aggregate_bwd: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  EGC_REQUIRE(L.ts_bytes / 4 < (size_t{1} << 32), "egc_aggregate_bwd: target-side streams exceed 2^32 floats");
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   float* tstreams = reinterpret_cast<float*>(ws);
@@ -833,6 +877,11 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
     s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
     s.partials = csc_part;
+    const bool fuse_merge = geo.n_pass == 1 && s.n_long > 0;
+    s.long_counter = fuse_merge ? reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
+                                                        align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256))
+                                : nullptr;
+    if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * sizeof(int), st));
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
@@ -848,7 +897,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       s.routed = accumulate ? 1 : 0;
       s.mode = 0;
       if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
-      if (s.n_long > 0) {
+      if (s.n_long > 0 && !fuse_merge) {
         s.mode = 1;
         if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
       }

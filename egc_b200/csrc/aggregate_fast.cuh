@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_aggregate_fast(const __grid_
 
   for (int task = blockIdx.x * kAggWarps + warp; task < n_tasks; task += warps_total) {
     int row, begin, end;
-    const bool is_chunk = task < p.n_chunks;
+    bool is_chunk = task < p.n_chunks;
     if (is_chunk) {
       row = __ldg(p.chunk_row + task);
       begin = __ldg(p.chunk_begin + task);
@@ -227,9 +227,10 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_aggregate_fast(const __grid_
       row = p.row_map != nullptr ? __ldg(p.row_map + idx) : idx;
       begin = __ldg(p.rowptr + row);
       end = __ldg(p.rowptr + row + 1);
-      if (end - begin > EGC_CHUNK_EDGES) continue;            // long row: chunk tasks + the merge kernel do it
+      if (end - begin > EGC_CHUNK_EDGES) continue;            // long row: its chunk tasks do it
     }
-    if (!is_chunk && p.out != nullptr) {                       // stage this row's combination weights asynchronously
+    const bool stage_w = p.out != nullptr;
+    if (!is_chunk && stage_w) {                                // stage this row's combination weights asynchronously
       const float* wsrc = p.weightings + static_cast<int64_t>(row) * GC::HAB(p);
       for (int t = lane; t < GC::HAB(p); t += 32) cp_async_4(sm + GC::sm_w(p) + t, wsrc + t);
     }
@@ -283,8 +284,32 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_aggregate_fast(const __grid_
     }
 
     if (is_chunk) {
+      // a chunk of a long row: publish the partial; the LAST chunk warp of the row to arrive merges all of them
+      // in chunk order (same result whichever warp it is) and goes on to finalize the row
       if (writer) acc.store(p.partials + (static_cast<int64_t>(task) * p.n_slots) * BD + foff, BD);
-      continue;
+      __threadfence();
+      __syncwarp();
+      int lo = 0, hi = p.n_long;                               // long row of this chunk: last l with long_chunk_ptr[l] <= task
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.long_chunk_ptr + mid) <= task) lo = mid; else hi = mid;
+      }
+      const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
+      int last = 0;
+      if (lane == 0) last = atomicAdd(p.long_counter + lo, 1) == c1 - c0 - 1 ? 1 : 0;
+      last = __shfl_sync(kFull, last, 0);
+      if (!last) continue;
+      __threadfence();
+      if (lane == 0) p.long_counter[lo] = 0;                   // ready for the next launch
+      acc.init();
+      for (int c = c0; c < c1; ++c) acc.merge_from(p.partials + (static_cast<int64_t>(c) * p.n_slots) * BD + foff, BD);
+      begin = __ldg(p.rowptr + row);
+      end = __ldg(p.rowptr + row + 1);
+      is_chunk = false;
+      if (stage_w) {
+        const float* wsrc = p.weightings + static_cast<int64_t>(row) * GC::HAB(p);
+        for (int t = lane; t < GC::HAB(p); t += 32) cp_async_4(sm + GC::sm_w(p) + t, wsrc + t);
+      }
     }
     if (writer) {
       const bool nonempty = end > begin;

@@ -187,3 +187,73 @@ def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: 
     """Differentiable EGConv layer body on a prepared graph."""
     return _EGConvFunction.apply(x, bases_weight, comb_weight, comb_bias, bias, graph, num_heads, num_bases,
                                  tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags))
+
+
+class _ProjectFunction(torch.autograd.Function):
+    """bases, pre-activation weightings = project(x)  (ref :180-182) as its own autograd node - used by callers
+    that post-process the weightings with ordinary torch ops (the paper-variant layer, `compat.py`)."""
+
+    @staticmethod
+    def forward(ctx, x, bases_weight, comb_weight, comb_bias, algo):
+        x = _require_cuda_f32("x", x)
+        bases_weight = _require_cuda_f32("bases_weight", bases_weight)
+        comb_weight = _require_cuda_f32("comb_weight", comb_weight)
+        comb_bias = _require_cuda_f32("comb_bias", comb_bias)
+        with torch.cuda.device(x.device):
+            bases, lin = project(x, bases_weight, comb_weight, comb_bias, False, algo)
+        ctx.save_for_backward(x, bases_weight, comb_weight)
+        ctx.algo, ctx.has_comb_bias = algo, comb_bias is not None
+        return bases, lin
+
+    @staticmethod
+    def backward(ctx, d_bases, d_lin):
+        x, bases_weight, comb_weight = ctx.saved_tensors
+        need_x, need_wb, need_wc, need_bc = ctx.needs_input_grad[:4]
+        d_bases = _require_cuda_f32("d_bases", d_bases)
+        d_lin = _require_cuda_f32("d_lin", d_lin)
+        with torch.cuda.device(x.device):
+            d_x, d_wb, d_wc, d_bc = project_backward(x, bases_weight, comb_weight, d_bases, d_lin, need_x, need_wb,
+                                                     need_wc, need_bc and ctx.has_comb_bias, ctx.algo)
+        return d_x, d_wb, d_wc, d_bc, None
+
+
+class _AggregateCombineFunction(torch.autograd.Function):
+    """out = combine(aggregate(bases), weightings) + bias  (ref :191-208) as its own autograd node; `weightings`
+    is whatever the caller made of the comb-weight projection (column order h * (A * B) + a * B + b)."""
+
+    @staticmethod
+    def forward(ctx, bases, weightings, bias, graph, heads, num_bases, aggrs, bwd_flags):
+        bases = _require_cuda_f32("bases", bases)
+        weightings = _require_cuda_f32("weightings", weightings)
+        bias = _require_cuda_f32("bias", bias)
+        dim = bases.size(1) // num_bases
+        desc = make_desc(graph, heads, num_bases, dim, aggrs, False)
+        needs_grad = any(ctx.needs_input_grad[:3])
+        with torch.cuda.device(bases.device):
+            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias, want_saved=needs_grad)
+        if needs_grad:
+            ctx.save_for_backward(bases, weightings, saved, saved_arg)
+        ctx.graph, ctx.desc, ctx.bwd_flags, ctx.has_bias = graph, desc, bwd_flags, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        bases, weightings, saved, saved_arg = ctx.saved_tensors
+        grad_out = _require_cuda_f32("grad_out", grad_out)
+        with torch.cuda.device(bases.device):
+            d_w, d_bases, d_bias = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg, grad_out,
+                                                      ctx.needs_input_grad[2] and ctx.has_bias, ctx.bwd_flags)
+        return d_bases, d_w, d_bias, None, None, None, None, None
+
+
+def project_autograd(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
+                     algo: int = _lib.GEMM_AUTO):
+    """Differentiable (bases, comb-weight pre-activations)."""
+    return _ProjectFunction.apply(x, bases_weight, comb_weight, comb_bias, int(algo))
+
+
+def aggregate_combine_autograd(bases: Tensor, weightings: Tensor, bias: Optional[Tensor], graph: GraphStructure,
+                               num_heads: int, num_bases: int, aggrs: Sequence[str], bwd_flags: int = 0) -> Tensor:
+    """Differentiable fused aggregation + combination on a prepared graph."""
+    return _AggregateCombineFunction.apply(bases, weightings, bias, graph, num_heads, num_bases, tuple(aggrs),
+                                           int(bwd_flags))

@@ -115,9 +115,64 @@ def run_case(ref, name, n, e, f_in, f_out, h, b, aggrs, loops, sigmoid, bias, ki
     return rec
 
 
+# paper variant (experiments/layers.py EfficientGraphConv): name, N, E, F_in, F_out, H, B, aggrs, add_self_loops,
+# weight post-processing, bias, input kind
+PAPER_CASES = [
+    ("paper_softmax_mixed", 120, 600, 24, 128, 4, 4, ["symadd", "max", "mean"], True,  "softmax",  True,  "edge_index"),
+    ("paper_sigmoid_std",   100, 500, 16,  64, 4, 4, ["symadd", "std", "max"],  True,  "sigmoid",  True,  "edge_index"),
+    ("paper_hardtanh_mol",   90, 400, 20,  64, 8, 4, ["add", "max", "mean"],    True,  "hardtanh", False, "edge_index"),
+    ("paper_symadd_adj",     96, 400, 24,  32, 8, 4, ["symadd"],                True,  "none",     True,  "adj_t"),
+    ("paper_code_noloop",    80, 450, 16,  64, 4, 4, ["symadd", "max", "min"],  False, "none",     True,  "adj_t"),
+]
+
+
+def run_paper_case(ref, name, n, e, f_in, f_out, h, b, aggrs, loops, post, bias, kind):
+    gen = torch.Generator().manual_seed(sum(ord(c) for c in name))
+    ei = make_graph(n, e, 0, gen)
+    x = torch.randn(n, f_in, generator=gen)
+    grad_out = torch.randn(n, f_out, generator=gen)
+    kw = dict(softmax_weights=post == "softmax", sigmoid_weights=post == "sigmoid", hardtanh_weights=post == "hardtanh",
+              add_self_loops=loops, bias=bias, aggrs=aggrs)
+    torch.manual_seed(4321)
+    conv = ref.EfficientGraphConv(f_in, f_out, h, b, **kw)
+    if bias:
+        with torch.no_grad():
+            conv.bias.uniform_(-0.5, 0.5)
+    if kind == "edge_index":
+        graph_in = ei
+    else:
+        perm = (ei[1] * n + ei[0]).argsort(stable=True)
+        graph_in = ref.SparseTensor(row=ei[1][perm], col=ei[0][perm], sparse_sizes=(n, n), is_sorted=True)
+    rec = {"name": name, "n": n, "f_in": f_in, "f_out": f_out, "heads": h, "bases": b, "aggrs": aggrs,
+           "add_self_loops": loops, "post": post, "bias": bias, "kind": kind, "edge_index": ei, "x": x,
+           "grad_out": grad_out, "state_dict": {k: v.clone() for k, v in conv.state_dict().items()}}
+    if kind != "edge_index":
+        rowptr, col_, _ = graph_in.csr()
+        rec["adj_rowptr"], rec["adj_col"] = rowptr.clone(), col_.clone()
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        m = ref.EfficientGraphConv(f_in, f_out, h, b, **kw).to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in rec["state_dict"].items()})
+        xx = x.to(dt).requires_grad_(True)
+        out = m(xx, graph_in)
+        params = list(m.named_parameters())
+        grads = torch.autograd.grad(out, [xx] + [p for _, p in params], grad_out.to(dt))
+        rec[f"out_{tag}"] = out.detach()
+        rec[f"grad_x_{tag}"] = grads[0]
+        for (pn, _), g in zip(params, grads[1:]):
+            rec[f"grad_{pn}_{tag}"] = g
+    return rec
+
+
 def main():
     ref = rl.load()
     os.makedirs(OUT_DIR, exist_ok=True)
+    for case in PAPER_CASES:
+        rec = run_paper_case(ref, *case)
+        path = os.path.join(OUT_DIR, f"{case[0]}.pt")
+        torch.save(rec, path)
+        print(f"{case[0]:24s} out|max|={rec['out_f32'].abs().max():.4f}  {os.path.getsize(path) / 1024:.0f} KiB")
+    if os.environ.get("EGC_GOLDEN_PAPER_ONLY"):
+        return
     for case in CASES:
         rec = run_case(ref, *case)
         path = os.path.join(OUT_DIR, f"{case[0]}.pt")

@@ -369,3 +369,46 @@ class EGConvOracle(torch.nn.Module):
 
     def __repr__(self):
         return "{}({}, {}, {})".format("EGConv", self.in_channels, self.out_channels, self.aggregators)
+
+
+# ---------------------------------------------------------------------------------------------------
+# paper variant  (/root/reference/experiments/layers.py:11-228 `EfficientGraphConv` + `_AggLayer`)
+# ---------------------------------------------------------------------------------------------------
+PAPER_NAMES = {"symadd": "symnorm", "add": "sum", "mean": "mean", "min": "min", "max": "max", "var": "var", "std": "std"}
+
+
+def paper_forward(x: Tensor, graph_in, bases_weights: Sequence[Tensor], comb_weight: Tensor, comb_bias: Tensor,
+                  bias: Optional[Tensor], aggrs: Sequence[str], num_heads: int, add_self_loops: bool = True,
+                  post: str = "none", graph_dtype=None) -> Tensor:
+    """CPU restatement of the paper layer on top of the EGConv restatement above.
+    `graph_in`: edge_index [2, E] or (rowptr, col, value) of adj_t.  `post`: none | softmax | sigmoid | hardtanh.
+    Self-loops / gcn_norm only for `symadd` (layers.py:167-188); every other aggregator sees the raw graph;
+    comb-weight columns are ordered h * (B * A) + b * A + a (layers.py:106-129)."""
+    n, b, a = x.size(0), len(bases_weights), len(aggrs)
+    gdt = graph_dtype or x.dtype          # gcn_norm on a value-less SparseTensor materialises fp32 ones in the reference
+    bases = torch.cat([x @ w for w in bases_weights], dim=1)                     # layers.py:97-101
+    lin = x @ comb_weight.t() + comb_bias                                        # layers.py:109
+    if post == "softmax":
+        w = lin.view(n, num_heads, b * a).softmax(dim=-1)                        # layers.py:112-120
+    elif post == "sigmoid":
+        w = torch.sigmoid(lin)
+    elif post == "hardtanh":
+        w = torch.nn.functional.hardtanh(lin)
+    else:
+        w = lin
+    w = w.reshape(n, num_heads, b, a)
+
+    def make_graph(symnorm: bool) -> OracleGraph:
+        loops = add_self_loops and symnorm
+        if isinstance(graph_in, Tensor):
+            return graph_from_edge_index(graph_in, n, symnorm, loops, dtype=gdt)
+        rowptr, col, value = graph_in
+        return graph_from_csr(rowptr, col, value, n, symnorm, loops, False, dtype=gdt)
+
+    cols = []
+    for name in aggrs:                                                           # one _AggLayer per aggregator
+        agg, _ = aggregate(make_graph(name == "symadd"), bases, [PAPER_NAMES[name]])
+        cols.append(agg[:, 0].reshape(n, b, -1))                                 # [N, B, D]
+    y = torch.stack(cols, dim=2)                                                 # [N, B, A, D]  layers.py:108
+    z = (w.unsqueeze(-1) * y.unsqueeze(1)).sum(dim=(2, 3)).reshape(n, -1)        # layers.py:131-135
+    return z + bias if bias is not None else z

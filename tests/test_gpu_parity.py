@@ -264,6 +264,50 @@ def test_layer_matches_reference_golden(name):
         assert rel_err(g, rec[f"grad_{pn}_f64"]) < tolerance(rec[f"grad_{pn}_f32"], rec[f"grad_{pn}_f64"]), pn
 
 
+# ------------------------------------------------------------------------------------------------
+# paper variant `EfficientGraphConv` (reference experiments/layers.py) through the adapter
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_cases("paper_"))
+def test_paper_variant_matches_reference_golden(name):
+    rec = load_golden(name)
+    post = rec["post"]
+    c = egc_b200.EfficientGraphConv(rec["f_in"], rec["f_out"], rec["heads"], rec["bases"], post == "softmax",
+                                    add_self_loops=rec["add_self_loops"], bias=rec["bias"], aggrs=rec["aggrs"],
+                                    sigmoid_weights=post == "sigmoid", hardtanh_weights=post == "hardtanh")
+    c.load_state_dict(rec["state_dict"])            # the reference's own keys: comb_weights.*, bases_weight.<b>, bias
+    c = c.to(DEV)
+    if rec["kind"] == "edge_index":
+        gi = rec["edge_index"].to(DEV)
+    else:
+        gi = egc_b200.SparseTensor(rowptr=rec["adj_rowptr"].to(DEV), col=rec["adj_col"].to(DEV),
+                                   sparse_sizes=(rec["n"], rec["n"]), is_sorted=True)
+    x = rec["x"].to(DEV).requires_grad_(True)
+    out = c(x, gi)
+    names = [n for n, _ in c.named_parameters()]
+    grads = torch.autograd.grad(out, [x] + list(c.parameters()), rec["grad_out"].to(DEV))
+    assert rel_err(out, rec["out_f64"]) < tolerance(rec["out_f32"], rec["out_f64"])
+    assert rel_err(grads[0], rec["grad_x_f64"]) < tolerance(rec["grad_x_f32"], rec["grad_x_f64"])
+    for pn, g in zip(names, grads[1:]):
+        assert rel_err(g, rec[f"grad_{pn}_f64"]) < tolerance(rec[f"grad_{pn}_f32"], rec[f"grad_{pn}_f64"]), pn
+
+
+def test_paper_checkpoint_converts_to_egconv():
+    """App. B: with add_self_loops=False the two layers coincide under the block / row permutation."""
+    n = 400
+    ei = random_graph(n, 3000, seed=77)
+    aggrs_p, aggrs_e = ["symadd", "max", "mean"], ["symnorm", "max", "mean"]
+    torch.manual_seed(5)
+    paper = egc_b200.EfficientGraphConv(48, 64, 4, 4, False, add_self_loops=False, aggrs=aggrs_p).to(DEV)
+    conv = egc_b200.EGConv(48, 64, aggrs=aggrs_e, num_heads=4, num_bases=4, add_self_loops=False).to(DEV)
+    conv.load_state_dict(egc_b200.convert_paper_state_dict(paper.state_dict(), 4, 4, 3))
+    x = torch.randn(n, 48, device=DEV)
+    assert rel_err(conv(x, ei.to(DEV)), paper(x, ei.to(DEV)).double().cpu()) < TOL
+    with pytest.raises(NotImplementedError):        # ref layers.py:222-224
+        rowptr, col, _ = to_adj_csr(ei, n)
+        egc_b200.EfficientGraphConv(48, 64, 4, 4, False, aggrs=["std"]).to(DEV)(
+            x, egc_b200.SparseTensor(rowptr=rowptr.to(DEV), col=col.to(DEV), sparse_sizes=(n, n), is_sorted=True))
+
+
 CONFIGS = [  # f_in, f_out, aggrs, heads, bases
     (128, 128, ["symnorm", "max", "std"], 4, 4),          # BASELINE cfg2/3 (EGC-M arxiv)
     (128, 128, ["symnorm"], 8, 4),                        # cfg4 (EGC-S mag)

@@ -7,8 +7,12 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+def golden_cases(prefix=None):
+    """EGConv fixtures by default; `prefix="paper_"` selects the EfficientGraphConv (paper variant) fixtures."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    if prefix is None:
+        return [n for n in names if not n.startswith("paper_")]
+    return [n for n in names if n.startswith(prefix)]
 
 
 def load_golden(name):
