@@ -393,7 +393,7 @@ def run_multi_gpu(args, w):
 
     import egc_b200
     from egc_b200 import _lib
-    from egc_b200.dist import PartitionedGraph, partitioned_egconv
+    from egc_b200.dist import GraphedStep, PartitionedGraph, partitioned_egconv
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
@@ -409,7 +409,7 @@ def run_multi_gpu(args, w):
         rowptr, col = to_adj_t(ei, n)
         g = egc_b200.GraphStructure.from_csr(rowptr.to(dev), col.to(dev), None, n, sym, True)
     nnz = g.nnz
-    pg = PartitionedGraph.from_global(g, rank, world, dev)
+    pg = PartitionedGraph.from_global(g, rank, world, dev, transport=args.transport)
     del g
     b, e = pg.part.row_begin, pg.part.row_end
     gen = torch.Generator().manual_seed(1)
@@ -418,16 +418,28 @@ def run_multi_gpu(args, w):
     x_host = x_loc.detach().cpu().pin_memory()
     params = list(conv.parameters())
 
-    def step():
+    def step_eager():
         out = partitioned_egconv(x_loc, pg, conv)
-        torch.autograd.grad(out, [x_loc] + params, go_loc)
+        return (out,) + torch.autograd.grad(out, [x_loc] + params, go_loc)
+
+    # One step = ONE CUDA-graph launch: projections, aggregation passes, NVLink pushes, flag signals / waits and the
+    # one-shot parameter-gradient all-reduce are all nodes of the captured graph (peer transport only).
+    use_graph = args.transport == "peer" and not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        l0 = _lib.launch_count()
+        step_eager()
+        launches_per_step = _lib.launch_count() - l0
+        graphed = GraphedStep(step_eager, warmup=2)
+        step = graphed.replay
+    else:
+        step = step_eager
 
     def step_e2e():
-        xs = x_host.to(dev, non_blocking=True).requires_grad_(True)
-        out = partitioned_egconv(xs, pg, conv)
-        loss = (out * go_loc).sum()
-        torch.autograd.grad(loss, [xs] + params)
-        return float(loss.item())
+        with torch.no_grad():
+            x_loc.copy_(x_host, non_blocking=True)
+        res = step()
+        return float((res[0].detach() * go_loc).sum().item())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -444,11 +456,21 @@ def run_multi_gpu(args, w):
         dist.barrier()
         t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks
-        return float(t.item()), _lib.launch_count() - l0
+        n_launch = launches_per_step * steps if launches_per_step is not None else _lib.launch_count() - l0
+        return float(t.item()), n_launch
 
     with ClockSampler(dev.index or 0) as clocks:
         ms, launches = timed(step, args.steps, args.warmup)
         ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    pg.check()
+    # per-kernel CUDA-event times of rank 0 (eager launches, separate pass; waits include the time spent on peers)
+    _lib.profile_enable(True)
+    for _ in range(args.steps):
+        step_eager()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t / args.steps} for k, (c, t) in prof.items()}
     stats = torch.tensor([pg.part.n_halo, pg.part.n_local, pg.part.interior_rows.numel(), launches], device=dev,
                          dtype=torch.float64)
     gathered = [torch.zeros_like(stats) for _ in range(world)]
@@ -467,6 +489,10 @@ def run_multi_gpu(args, w):
                        "nodes": n, "nnz": nnz, "locality_p_intra": p_intra, "blocks": 8,
                        "halo_rows_total": halo_rows, "interior_rows_total": sum(int(t[2]) for t in gathered),
                        "nvlink_bytes_per_step": 2 * halo_rows * bd * 4,
+                       "transport": ("NVLink peer-memory kernels (posted stores + epoch flags), whole step replayed "
+                                     "from one CUDA graph" if use_graph else
+                                     ("NVLink peer-memory kernels, eager launches" if args.transport == "peer" else
+                                      "NCCL batch_isend_irecv + all_reduce, eager launches")),
                        "l2": "no flush: working set >> L2", "algorithmic_bytes_per_step": bf + bb},
             "clocks": clocks.summary(),
             "e2e": {"value": nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
@@ -474,9 +500,10 @@ def run_multi_gpu(args, w):
             "gpu_launches": sum(int(t[3]) for t in gathered),
             "step_roofline": {"achieved": (bf + bb) / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                               "frac": (bf + bb) / (ms * 1e-3) / 1e9 / (peak * world), "peak_source": peak_src + f" x {world}"},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": None, "cpu_baseline": None, "kernels_rank0": kernels,
         }
         print(json.dumps(line))
+    pg.close()
     dist.destroy_process_group()
 
 
@@ -489,6 +516,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo exchange: our NVLink peer-memory kernels (default) or the NCCL baseline")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--locality", type=float, default=-1.0,
                     help="p_intra of the synthetic generator (default: 0 on one GPU, 0.8 when row-partitioned)")
     args = ap.parse_args()

@@ -10,7 +10,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libegc_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 EGC_MAX_AGGR = 8
 EGC_CHUNK_EDGES = 256
 META_SLOTS = 8
@@ -66,6 +66,16 @@ SIGNATURES = {
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
+    "egc_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), _P]),
+    "egc_peer_free": (c_int32, [_P]),
+    "egc_peer_open": (c_int32, [_P, POINTER(c_void_p)]),
+    "egc_peer_close": (c_int32, [_P]),
+    "egc_peer_push_rows": (c_int32, [c_int32, _P, _P, _P, _P, c_int32, _P, c_int32, c_int32, ctypes.c_uint32, _P, _P, _P]),
+    "egc_peer_epoch_advance": (c_int32, [_P, _P]),
+    "egc_peer_signal": (c_int32, [_P, c_int32, c_int32, ctypes.c_uint32, _P, _P]),
+    "egc_peer_wait": (c_int32, [_P, c_int32, c_int32, c_int32, _P, ctypes.c_uint32, c_int32, ctypes.c_uint64, _P, _P]),
+    "egc_peer_reduce_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, _P, _P]),
+    "egc_peer_sum_slots": (c_int32, [_P, c_int32, c_int32, _P, _P]),
 }
 
 _lib = None

@@ -12,7 +12,9 @@ Scheme (one process per GPU, torch.distributed; NCCL over NVLink on the B200 box
               their owners (reverse exchange) and are added in fixed peer order (deterministic);
               parameter gradients are all-reduced.
 `PartitionPlan` and `HaloExchange` are pure index / communication plumbing (any device, any backend);
-`PartitionedEGConv` binds them to the CUDA kernels.
+`PartitionedGraph` + `partitioned_egconv` bind them to the CUDA kernels.  On the B200 box the data path does not
+go through NCCL: `transport="peer"` moves halo rows, halo gradient partial sums and the replicated parameter
+gradients with our own kernels over NVLink peer memory (`egc_b200/peer.py`, `csrc/peer.cu`).
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -202,83 +204,182 @@ class CudaHaloExchange(HaloExchange):
 # ---------------------------------------------------------------------------------------------------
 class PartitionedGraph:
     """Device-side state of one rank: the rectangular local CSR ([own rows] x [own | halo] columns), the
-    interior / boundary row split and the halo exchange."""
+    interior / boundary row split and the halo exchange.
 
-    def __init__(self, part: LocalPartition, device, group=None):
+    transport = "peer" (default): our own kernels over NVLink peer memory (`egc_b200.peer`, csrc/peer.cu) - posted
+    stores into the consumer's memory ordered by epoch flags, graph-capturable, no NCCL on the data path;
+    transport = "nccl": point-to-point `batch_isend_irecv` + all-reduce (kept as the library baseline)."""
+
+    def __init__(self, part: LocalPartition, device, group=None, transport: str = "peer"):
         from .graph import GraphStructure
+        if transport not in ("peer", "nccl"):
+            raise ValueError(f"unknown transport {transport!r}")
         self.part = part
         self.device = torch.device(device)
         self.graph = GraphStructure.from_prepared(part.rowptr, part.col, part.n_local + part.n_halo,
                                                   val_sym=part.val_sym, val_lin=part.val_lin, device=self.device)
+        self.transport = transport if part.world_size > 1 else "nccl"
         self.exchange = CudaHaloExchange(part, self.device, group)
         self.interior = part.interior_rows.to(self.device, torch.int32)
         self.boundary = part.boundary_rows.to(self.device, torch.int32)
         self.group = group
+        self._peer_ctx = {}
 
     @staticmethod
-    def from_global(graph, rank: int, world_size: int, device, group=None) -> "PartitionedGraph":
+    def from_global(graph, rank: int, world_size: int, device, group=None, transport: str = "peer") -> "PartitionedGraph":
         """Partition a prepared single-device `GraphStructure` (every rank builds the same plan)."""
         plan = PartitionPlan(graph.rowptr.cpu(), graph.col.cpu(), world_size,
                              val_sym=graph.val_sym.cpu() if graph.val_sym is not None else None,
                              val_lin=graph.val_lin.cpu() if graph.val_lin is not None else None)
-        return PartitionedGraph(plan.local(rank), device, group)
+        return PartitionedGraph(plan.local(rank), device, group, transport)
+
+    def peer_context(self, key, bd: int, n_flat: int):
+        """Exchange state of one layer (collective on first use: every rank must reach it in the same order)."""
+        k = (key, int(bd), int(n_flat))
+        ctx = self._peer_ctx.get(k)
+        if ctx is None:
+            from .peer import PeerLayerContext
+            ctx = PeerLayerContext(self.part, bd, n_flat, self.device, self.group)
+            self._peer_ctx[k] = ctx
+        return ctx
+
+    def check(self):
+        """Raise if any exchange of this graph timed out on the device (synchronises)."""
+        for ctx in self._peer_ctx.values():
+            ctx.check()
+
+    def close(self):
+        for ctx in self._peer_ctx.values():
+            ctx.close()
+        self._peer_ctx = {}
 
 
 class _PartitionedEGConvFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, pg, heads, num_bases, aggrs, sigmoid, algo):
+    def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, pg, heads, num_bases, aggrs, sigmoid, algo, key,
+                grad_mode=True):
         from . import functional as F
+        from . import peer as P
         part, g = pg.part, pg.graph
         x = F._require_cuda_f32("x", x)
         bd = bases_weight.size(1)
         desc = F.make_desc(g, heads, num_bases, bd // num_bases, aggrs, sigmoid)
-        needs_grad = any(ctx.needs_input_grad[:5])
+        needs_grad = grad_mode and any(ctx.needs_input_grad[:5])       # needs_input_grad ignores torch.no_grad()
+        peer = None
         with torch.cuda.device(x.device):
-            bases_ext = torch.empty((part.n_local + part.n_halo, bd), dtype=torch.float32, device=x.device)
+            if pg.transport == "peer":
+                n_flat = bases_weight.numel() + comb_weight.numel() + comb_weight.size(0) + heads * (bd // num_bases)
+                peer = pg.peer_context(key, bd, n_flat)
+                # new epoch; every peer is done with the halo rows of my previous step
+                peer.wait(P.SLOT_CONS, lag=1, advance=True)
+                bases_ext = peer.bases_ext
+            else:
+                bases_ext = torch.empty((part.n_local + part.n_halo, bd), dtype=torch.float32, device=x.device)
             _, weightings = F.project(x, bases_weight.contiguous(), comb_weight.contiguous(), comb_bias, sigmoid, algo,
                                       bases_out=bases_ext[:part.n_local])
-            # halo exchange runs on the communication stream while interior rows are aggregated here
-            halo, handle = pg.exchange.start_forward(bases_ext[:part.n_local])
             outs = F.alloc_aggregate_outputs(desc, x.device, want_out=True, want_saved=needs_grad)
-            F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
-                                outputs=outs)
-            pg.exchange.finish(handle)
-            bases_ext[part.n_local:].copy_(halo)
+            if peer is not None:
+                peer.push_forward()                        # posted stores into the peers' halo regions, then FWD flag
+                F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
+                                    outputs=outs)
+                peer.wait(P.SLOT_FWD)
+            else:
+                # halo exchange runs on the communication stream while interior rows are aggregated here
+                halo, handle = pg.exchange.start_forward(bases_ext[:part.n_local])
+                F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
+                                    outputs=outs)
+                pg.exchange.finish(handle)
+                bases_ext[part.n_local:].copy_(halo)
             F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.boundary, use_plan=True,
                                 outputs=outs)
+            if peer is not None and not needs_grad:
+                peer.signal(P.SLOT_CONS)
         out, _, _, saved, saved_arg = outs
         if needs_grad:
             ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg)
-        ctx.pg, ctx.desc, ctx.algo = pg, desc, algo
+        ctx.pg, ctx.desc, ctx.algo, ctx.peer = pg, desc, algo, peer
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         from . import functional as F
+        from . import peer as P
         x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg = ctx.saved_tensors
-        pg, part = ctx.pg, ctx.pg.part
+        pg, part, peer = ctx.pg, ctx.pg.part, ctx.peer
         grad_out = F._require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
+        want_b = bool(need_b and ctx.has_bias)
+        want_bc = bool(need_bc and ctx.has_comb_bias)
         with torch.cuda.device(x.device):
-            d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
-                                                                  saved_arg, grad_out, need_b and ctx.has_bias,
-                                                                  want_lin_colsum=True)
+            if peer is None:
+                d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
+                                                                      saved_arg, grad_out, want_b, want_lin_colsum=True)
+                d_bases = d_bases_ext[:part.n_local]
+                pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
+                d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
+                                                        d_w, need_x, need_wb, need_wc, False, ctx.algo)
+                if not want_bc:
+                    d_bc = None
+                for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
+                    if t is not None:
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)
+                return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
+            # ---- peer transport: flat parameter-gradient vector [d_wb | d_wc | d_bc | d_bias] in the exchange context
+            n_wb, n_wc, hab = bases_weight.numel(), comb_weight.numel(), comb_weight.size(0)
+            hd = ctx.desc.heads * ctx.desc.dim
+            flat = peer.flat
+            v_wb = flat[:n_wb].view_as(bases_weight)
+            v_wc = flat[n_wb:n_wb + n_wc].view_as(comb_weight)
+            v_bc = flat[n_wb + n_wc:n_wb + n_wc + hab]
+            v_b = flat[n_wb + n_wc + hab:n_wb + n_wc + hab + hd]
+            if not (need_wb and need_wc and want_b):
+                flat.zero_()
+            d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
+                                                          grad_out, want_b, want_lin_colsum=True, out_bias=v_b,
+                                                          out_lin_colsum=v_bc)
+            peer.push_backward(d_bases_ext)                # halo partial sums go home (posted stores), BWD + CONS flags
+            peer.wait(P.SLOT_BWD)
             d_bases = d_bases_ext[:part.n_local]
-            pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
-            d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
-                                                    d_w, need_x, need_wb, need_wc, False, ctx.algo)
-            if not (need_bc and ctx.has_comb_bias):
-                d_bc = None
-            for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
-                if t is not None:
-                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)
-        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None
+            peer.reduce_into(d_bases)                      # fixed peer order: deterministic
+            d_x, _, _, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases, d_w,
+                                              need_x, need_wb, need_wc, False, ctx.algo, out_wb=v_wb, out_wc=v_wc)
+            total = peer.allreduce_flat()
+            d_wb = total[:n_wb].view_as(bases_weight).clone() if need_wb else None
+            d_wc = total[n_wb:n_wb + n_wc].view_as(comb_weight).clone() if need_wc else None
+            d_bc = total[n_wb + n_wc:n_wb + n_wc + hab].clone() if want_bc else None
+            d_bias = total[n_wb + n_wc + hab:n_wb + n_wc + hab + hd].clone() if want_b else None
+        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
 
 
 def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv) -> Tensor:
     """Run `conv` (an `egc_b200.EGConv` with replicated parameters) on this rank's rows of a partitioned graph.
-    Output rows / input gradients are local; parameter gradients are all-reduced (= single-GPU values)."""
+    Output rows / input gradients are local; parameter gradients are summed over the ranks (= single-GPU values).
+    With the peer transport every layer keeps its own exchange buffers (keyed by the module), one step in flight."""
     return _PartitionedEGConvFunction.apply(x_local, conv.bases_weight, conv.comb_weight.weight, conv.comb_weight.bias,
                                             conv.bias, pg, conv.num_heads, conv.num_bases, tuple(conv.aggregators),
-                                            bool(conv.sigmoid), int(conv.gemm_algo))
+                                            bool(conv.sigmoid), int(conv.gemm_algo), id(conv), torch.is_grad_enabled())
+
+
+class GraphedStep:
+    """Capture `fn(*static_inputs)` - typically one forward + backward of a partitioned layer stack, exchange kernels
+    and flags included - into a CUDA graph after `warmup` eager calls; `replay()` re-runs it with the current
+    contents of the static input tensors.  `outputs` are the tensors `fn` returned at capture time (static too)."""
+
+    def __init__(self, fn, warmup: int = 3):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # thread_local: CUDA calls of other threads (the NCCL watchdog polling its events, pinned-memory helpers)
+        # must not invalidate the capture; the autograd worker thread still launches into the capturing stream
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.outputs = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

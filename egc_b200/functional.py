@@ -97,7 +97,8 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
 
 def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Tensor, saved: Tensor,
                        saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
-                       want_lin_colsum: bool = False):
+                       want_lin_colsum: bool = False, out_bias: Optional[Tensor] = None,
+                       out_lin_colsum: Optional[Tensor] = None):
     """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
     with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias)."""
     lib = _lib.load()
@@ -106,8 +107,10 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
     d_w = torch.empty((desc.n_dst, hab), dtype=torch.float32, device=dev)
     d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev)
-    d_bias = torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev) if want_bias else None
-    d_lin_sum = torch.empty(hab, dtype=torch.float32, device=dev) if want_lin_colsum else None
+    d_bias = (out_bias if out_bias is not None else
+              torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev)) if want_bias else None
+    d_lin_sum = (out_lin_colsum if out_lin_colsum is not None else
+                 torch.empty(hab, dtype=torch.float32, device=dev)) if want_lin_colsum else None
     nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
     ws = _ws(nbytes, dev)
     check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
@@ -122,15 +125,16 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
 
 
 def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bases: Tensor, d_lin: Tensor,
-                     need_x: bool, need_wb: bool, need_wc: bool, need_bc: bool, algo: int = _lib.GEMM_AUTO):
+                     need_x: bool, need_wb: bool, need_wc: bool, need_bc: bool, algo: int = _lib.GEMM_AUTO,
+                     out_wb: Optional[Tensor] = None, out_wc: Optional[Tensor] = None):
     """Autograd of `project`: returns (d_x, d_bases_weight, d_comb_weight, d_comb_bias), None where not needed."""
     lib = _lib.load()
     dev = x.device
     n, f_in = x.shape
     bd, hab = bases_weight.shape[1], comb_weight.shape[0]
     d_x = torch.empty_like(x) if need_x else None
-    d_wb = torch.empty_like(bases_weight) if need_wb else None
-    d_wc = torch.empty_like(comb_weight) if need_wc else None
+    d_wb = (out_wb if out_wb is not None else torch.empty_like(bases_weight)) if need_wb else None
+    d_wc = (out_wc if out_wc is not None else torch.empty_like(comb_weight)) if need_wc else None
     d_bc = torch.empty(hab, dtype=torch.float32, device=dev) if need_bc else None
     nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
     ws = _ws(nbytes, dev)
@@ -143,7 +147,7 @@ def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bas
 class _EGConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, graph, heads, num_bases, aggrs, sigmoid, algo,
-                bwd_flags):
+                bwd_flags, grad_mode=True):
         x = _require_cuda_f32("x", x)
         bases_weight = _require_cuda_f32("bases_weight", bases_weight)
         comb_weight = _require_cuda_f32("comb_weight.weight", comb_weight)
@@ -153,7 +157,8 @@ class _EGConvFunction(torch.autograd.Function):
             raise ValueError(f"x must be [num_nodes, in_channels] with num_nodes == {graph.n_src}")
         dim = bases_weight.size(1) // num_bases
         desc = make_desc(graph, heads, num_bases, dim, aggrs, sigmoid)
-        needs_grad = any(ctx.needs_input_grad[:5])
+        # needs_input_grad ignores torch.no_grad(); the caller samples the grad mode before apply()
+        needs_grad = grad_mode and any(ctx.needs_input_grad[:5])
         with torch.cuda.device(x.device):
             bases, weightings = project(x, bases_weight, comb_weight, comb_bias, sigmoid, algo)
             out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias,
@@ -178,7 +183,7 @@ class _EGConvFunction(torch.autograd.Function):
                                                   need_wc, False, ctx.algo)
             if not want_bc:
                 d_bc = None
-        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None
+        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
 
 
 def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
@@ -186,7 +191,7 @@ def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: 
            algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0) -> Tensor:
     """Differentiable EGConv layer body on a prepared graph."""
     return _EGConvFunction.apply(x, bases_weight, comb_weight, comb_bias, bias, graph, num_heads, num_bases,
-                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags))
+                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags), torch.is_grad_enabled())
 
 
 class _ProjectFunction(torch.autograd.Function):
@@ -222,13 +227,13 @@ class _AggregateCombineFunction(torch.autograd.Function):
     is whatever the caller made of the comb-weight projection (column order h * (A * B) + a * B + b)."""
 
     @staticmethod
-    def forward(ctx, bases, weightings, bias, graph, heads, num_bases, aggrs, bwd_flags):
+    def forward(ctx, bases, weightings, bias, graph, heads, num_bases, aggrs, bwd_flags, grad_mode=True):
         bases = _require_cuda_f32("bases", bases)
         weightings = _require_cuda_f32("weightings", weightings)
         bias = _require_cuda_f32("bias", bias)
         dim = bases.size(1) // num_bases
         desc = make_desc(graph, heads, num_bases, dim, aggrs, False)
-        needs_grad = any(ctx.needs_input_grad[:3])
+        needs_grad = grad_mode and any(ctx.needs_input_grad[:3])
         with torch.cuda.device(bases.device):
             out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias, want_saved=needs_grad)
         if needs_grad:
@@ -243,7 +248,7 @@ class _AggregateCombineFunction(torch.autograd.Function):
         with torch.cuda.device(bases.device):
             d_w, d_bases, d_bias = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg, grad_out,
                                                       ctx.needs_input_grad[2] and ctx.has_bias, ctx.bwd_flags)
-        return d_bases, d_w, d_bias, None, None, None, None, None
+        return d_bases, d_w, d_bias, None, None, None, None, None, None
 
 
 def project_autograd(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
@@ -256,4 +261,4 @@ def aggregate_combine_autograd(bases: Tensor, weightings: Tensor, bias: Optional
                                num_heads: int, num_bases: int, aggrs: Sequence[str], bwd_flags: int = 0) -> Tensor:
     """Differentiable fused aggregation + combination on a prepared graph."""
     return _AggregateCombineFunction.apply(bases, weightings, bias, graph, num_heads, num_bases, tuple(aggrs),
-                                           int(bwd_flags))
+                                           int(bwd_flags), torch.is_grad_enabled())

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EGC_ABI_VERSION 2
+#define EGC_ABI_VERSION 3
 #define EGC_MAX_AGGR 8          /* len(aggrs) accepted by one layer */
 #define EGC_CHUNK_EDGES 256     /* rows longer than this are split into chunks of this many nnz */
 
@@ -235,6 +235,52 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 
 /* dst[k, :] = src[index[k], :]  (pack halo rows before a send / all-gather), width floats per row */
 int egc_gather_rows(const float* src, const int32_t* index, int32_t n_index, int32_t width, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NVLink peer-memory exchange (one process per GPU of a node; csrc/peer.cu).  No reference counterpart.
+ * A rank allocates ONE peer segment, exports its IPC handle, and maps the segments of the other ranks.
+ * Data moves by posted stores into a mapped segment (egc_peer_push_rows); ordering is by epoch flags:
+ * flags of a rank = uint32 [n_slots][world] inside its segment, entry [slot][q] written by rank q only.
+ * The epoch is a device-resident counter advanced by a kernel, so a step can be replayed from a CUDA graph.
+ * ---------------------------------------------------------------------------------------- */
+#define EGC_MAX_PEERS 8
+typedef struct egc_ipc_handle { unsigned char bytes[64]; } egc_ipc_handle;
+
+/* cudaMalloc + zero-fill + cudaIpcGetMemHandle (setup time; synchronises) */
+int egc_peer_alloc(size_t bytes, void** ptr, egc_ipc_handle* handle);
+int egc_peer_free(void* ptr);
+/* map another rank's segment into this process (enables peer access lazily) / unmap it */
+int egc_peer_open(const egc_ipc_handle* handle, void** ptr);
+int egc_peer_close(void* ptr);
+
+/* For each segment s < n_seg (HOST arrays src/dst/seg_ptr, n_seg <= EGC_MAX_PEERS): rows k in
+ * [seg_ptr[s], seg_ptr[s+1]) of the concatenated list:  dst[s][(k - seg_ptr[s]), :] = src[s][index[k], :]
+ * (index == NULL: src[s][k - seg_ptr[s], :]).  dst may point into a mapped peer segment.
+ * Fused signal (flags != NULL, slot_mask != 0): the last CTA to finish, after a system-scope fence, raises
+ * flags[q][slot * world + rank] = *epoch for every peer q and every slot bit of slot_mask; `counter` is a
+ * device word that is zero between calls. */
+int egc_peer_push_rows(int32_t n_seg, const float* const* src, float* const* dst, const int32_t* seg_ptr,
+                       const int32_t* index, int32_t width, uint32_t* const* flags, int32_t world, int32_t rank,
+                       uint32_t slot_mask, const uint32_t* epoch, uint32_t* counter, void* stream);
+
+/* *epoch += 1 (device counter) */
+int egc_peer_epoch_advance(uint32_t* epoch, void* stream);
+/* flags[q][slot * world + rank] = *epoch for every peer q != rank and every slot bit of slot_mask (HOST array of
+ * mapped flag arrays); release at system scope: everything earlier on the stream is visible to a peer that
+ * observes the flag */
+int egc_peer_signal(uint32_t* const* flags, int32_t world, int32_t rank, uint32_t slot_mask, const uint32_t* epoch,
+                    void* stream);
+/* (advance != 0: *epoch += 1 first - a new step starts.)  Block the stream until my_flags[slot * world + q] >=
+ * *epoch - lag for every q != rank; after timeout_ns the kernel gives up and sets *err = 1 + slot (device word,
+ * checked by the host when it next synchronises) */
+int egc_peer_wait(const uint32_t* my_flags, int32_t world, int32_t rank, int32_t slot, uint32_t* epoch,
+                  uint32_t lag, int32_t advance, uint64_t timeout_ns, uint32_t* err, void* stream);
+
+/* into[rows[r], :] += sum_{t in [ptr[r], ptr[r+1])} staging[entry[t], :]   (fixed order: deterministic) */
+int egc_peer_reduce_rows(const float* staging, const int32_t* rows, const int32_t* ptr, const int32_t* entry,
+                         int32_t n_rows, int32_t width, float* into, void* stream);
+/* out[i] = sum_q slots[q * n + i] in rank order (the one-shot all-reduce of the replicated parameter gradients) */
+int egc_peer_sum_slots(const float* slots, int32_t world, int32_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

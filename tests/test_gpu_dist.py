@@ -1,4 +1,6 @@
-"""Multi-GPU parity: the row-partitioned layer over 2 ranks (NCCL) == the single-GPU layer.
+"""Multi-GPU parity: the row-partitioned layer over 2 ranks == the single-GPU layer, for both transports
+(our NVLink peer-memory kernels and the NCCL baseline), across repeated steps, under no_grad, for a two-layer
+stack, and when the whole step is replayed from a CUDA graph.
 Needs >= 2 GPUs (`gpurun --gpus 2`); skipped otherwise."""
 import os
 import socket
@@ -20,39 +22,116 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, ei, x, go, ret):
+def check_two_layers(conv, conv2, params2, pg, x, go, eid, b, e, dev):
+    from egc_b200.dist import partitioned_egconv
+    xs = x.to(dev).requires_grad_(True)
+    ref2 = conv2(torch.relu(conv(xs, eid)), eid)
+    gref2 = torch.autograd.grad(ref2, [xs] + params2, go.to(dev))
+    xl = x[b:e].to(dev).requires_grad_(True)
+    out2 = partitioned_egconv(torch.relu(partitioned_egconv(xl, pg, conv)), pg, conv2)
+    g2 = torch.autograd.grad(out2, [xl] + params2, go[b:e].to(dev))
+    assert rel_err(out2, ref2[b:e]) < 1e-5
+    assert rel_err(g2[0], gref2[0][b:e]) < 2e-5
+    for a, r in zip(g2[1:], gref2[1:]):
+        assert rel_err(a, r) < 2e-5
+
+
+def _worker(rank, world, port, n, ei, x, go, transport, ret):
     import egc_b200
-    from egc_b200.dist import PartitionedGraph, partitioned_egconv
+    from egc_b200.dist import GraphedStep, PartitionedGraph, partitioned_egconv
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pg = None
     try:
         torch.manual_seed(0)
         conv = egc_b200.EGConv(64, 128, aggrs=AGGRS, num_heads=4, num_bases=4).to(dev)
+        conv2 = egc_b200.EGConv(128, 128, aggrs=AGGRS, num_heads=4, num_bases=4).to(dev)
         params = list(conv.parameters())
-        # single-GPU reference on this rank's device
-        xs = x.to(dev).requires_grad_(True)
-        out_ref = conv(xs, ei.to(dev))
-        grads_ref = torch.autograd.grad(out_ref, [xs] + params, go.to(dev))
-        g = egc_b200.GraphStructure.from_edge_index(ei.to(dev), n, True, True)
-        pg = PartitionedGraph.from_global(g, rank, world, dev)
+        params2 = params + list(conv2.parameters())
+        eid = ei.to(dev)
+        g = egc_b200.GraphStructure.from_edge_index(eid, n, True, True)
+        pg = PartitionedGraph.from_global(g, rank, world, dev, transport=transport)
+        assert pg.transport == transport
         b, e = pg.part.row_begin, pg.part.row_end
-        xl = x[b:e].to(dev).requires_grad_(True)
-        out = partitioned_egconv(xl, pg, conv)
-        grads = torch.autograd.grad(out, [xl] + params, go[b:e].to(dev))
-        assert rel_err(out, out_ref[b:e]) < 1e-6
-        assert rel_err(grads[0], grads_ref[0][b:e]) < 1e-5
-        for a, r in zip(grads[1:], grads_ref[1:]):
-            assert rel_err(a, r) < 1e-5
         assert pg.part.interior_rows.numel() > 0 and pg.part.n_halo > 0
+
+        def check_step(x_full, go_full, tag):
+            xs = x_full.to(dev).requires_grad_(True)
+            out_ref = conv(xs, eid)
+            grads_ref = torch.autograd.grad(out_ref, [xs] + params, go_full.to(dev))
+            xl = x_full[b:e].to(dev).requires_grad_(True)
+            out = partitioned_egconv(xl, pg, conv)
+            grads = torch.autograd.grad(out, [xl] + params, go_full[b:e].to(dev))
+            assert rel_err(out, out_ref[b:e]) < 1e-6, tag
+            assert rel_err(grads[0], grads_ref[0][b:e]) < 1e-5, tag
+            for a, r in zip(grads[1:], grads_ref[1:]):
+                assert rel_err(a, r) < 1e-5, tag
+
+        # repeated steps with fresh data: exercises the epoch flags and the buffer-reuse ordering
+        for it in range(3):
+            gen = torch.Generator().manual_seed(10 + it)
+            check_step(torch.randn(x.shape, generator=gen), torch.randn(go.shape, generator=gen), f"step {it}")
+        pg.check()
+        # inference under no_grad, twice in a row, then a training step again
+        with torch.no_grad():
+            for _ in range(2):
+                out_ref = conv(x.to(dev), eid)
+                out = partitioned_egconv(x[b:e].to(dev), pg, conv)
+                assert rel_err(out, out_ref[b:e]) < 1e-6
+        pg.check()
+        check_step(x, go, "after no_grad")
+        pg.check()
+
+        def two_layers():      # two stacked layers (each keeps its own exchange buffers)
+            check_two_layers(conv, conv2, params2, pg, x, go, eid, b, e, dev)
+
+        two_layers()
+        pg.check()
+        import gc
+        gc.collect()           # no autograd graph of the eager steps may stay alive across the capture below
+
+        if transport == "peer":
+            # the whole step (exchange kernels and flags included) replayed from a CUDA graph
+            x_static = x[b:e].to(dev).requires_grad_(True)
+            go_static = go[b:e].to(dev)
+
+            def step():
+                o = partitioned_egconv(x_static, pg, conv)
+                return (o,) + torch.autograd.grad(o, [x_static] + params, go_static)
+
+            graphed = GraphedStep(step, warmup=2)
+            pg.check()
+            for it in range(3):
+                gen = torch.Generator().manual_seed(50 + it)
+                xf, gf = torch.randn(x.shape, generator=gen), torch.randn(go.shape, generator=gen)
+                with torch.no_grad():
+                    x_static.copy_(xf[b:e].to(dev))
+                    go_static.copy_(gf[b:e].to(dev))
+                res = graphed.replay()
+                xs = xf.to(dev).requires_grad_(True)
+                out_ref = conv(xs, eid)
+                grads_ref = torch.autograd.grad(out_ref, [xs] + params, gf.to(dev))
+                assert rel_err(res[0], out_ref[b:e]) < 1e-6
+                assert rel_err(res[1], grads_ref[0][b:e]) < 1e-5
+                for a, r in zip(res[2:], grads_ref[1:]):
+                    assert rel_err(a, r) < 1e-5
+            pg.check()
+        torch.cuda.synchronize()
         ret[rank] = "ok"
     finally:
+        if pg is not None:
+            try:
+                pg.close()
+            except Exception:
+                pass
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_partitioned_layer_matches_single_gpu_nccl_world2():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_partitioned_layer_matches_single_gpu_world2(transport):
     n = 4000
     ei = random_graph(n, 30000, seed=5, hub=900)
     blk = torch.randint(0, n // 2, (2, 15000))
@@ -61,5 +140,5 @@ def test_partitioned_layer_matches_single_gpu_nccl_world2():
     x, go = torch.randn(n, 64), torch.randn(n, 128)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
