@@ -264,6 +264,7 @@ def run_single_gpu(args, w, n, edge_index):
     torch.manual_seed(0)
     conv = egc_b200.EGConv(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"],
                            cached=True).to(dev)
+    conv.bwd_flags = args.bwd_flags
     x_host = torch.randn(n, w["f_in"]).pin_memory()
     go = torch.randn(n, w["f_out"], device=dev)
     if w["kind"] == "edge_index":
@@ -519,6 +520,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo exchange: our NVLink peer-memory kernels (default) or the NCCL baseline")
     ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--bwd-flags", type=int, default=0, help="EGC_BWD_* tuning bits passed to egc_aggregate_bwd (A/B runs)")
     ap.add_argument("--locality", type=float, default=-1.0,
                     help="p_intra of the synthetic generator (default: 0 on one GPU, 0.8 when row-partitioned)")
     args = ap.parse_args()

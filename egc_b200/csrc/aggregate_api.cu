@@ -316,11 +316,19 @@ __global__ void k_colsum_partials(const float* __restrict__ part, int n_cta, int
 
 // =============================================================================================
 // min/max gradient routing: d_bases[col[arg[i][s][p]]][p] += t_route[i][s][p]   (x val_lin[arg] when weighted)
-// One warp task = 32 consecutive features of kRouteRows consecutive target rows; tasks are ordered
-// feature-slab-major, so at any moment the whole grid adds into one 32-float column slab of d_bases
+// One warp task = 32 consecutive features of kRouteRows consecutive target rows.  The grid walks the
+// (feature slab, slot) phases together, so at any moment it adds into one 32-float column slab of d_bases
 // (n_src x 128 B - L2-resident) instead of missing to DRAM all over the [n_src, BD] matrix.
+// Hub sources (the long columns of the CSC plan: a power-law hub sits in thousands of rows and wins a share of
+// the features in each) would serialise tens of thousands of fp32 REDs on ONE 128-byte line per phase - the L2
+// atomic unit retires about one lane per cycle per line - so every CTA privatises them: a shared-memory hash
+// maps the hub ids to slots, their contributions go to shared-memory accumulators (ATOMS), and each CTA flushes
+// one RED per (hub, feature) at the end of the phase.
 // =============================================================================================
-constexpr int kRouteRows = 4;
+constexpr int kRouteRows = 8;
+constexpr int kRouteThreads = 1024;
+constexpr int kRouteMaxHubs = 1024;
+constexpr int kRouteHashSize = 2 * kRouteMaxHubs;           // open addressing, load factor <= 0.5
 
 struct RouteParams {
   const int32_t* saved_arg;    // [n_rows][n_arg][BD] winning nnz position (-1: none)
@@ -328,43 +336,85 @@ struct RouteParams {
   const int32_t* col;
   const float* val_lin;        // or null
   float* d_bases;              // [n_src][BD]
+  const int32_t* hubs;         // [n_hubs] source ids privatised in shared memory (or null)
+  int n_hubs;
   int n_rows, n_arg, BD, n_slabs;
 };
 
-__global__ void __launch_bounds__(256) k_route_minmax(const __grid_constant__ RouteParams p) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
+__device__ __forceinline__ uint32_t route_hash(int j) { return (static_cast<uint32_t>(j) * 2654435761u) >> (32 - 11); }
+static_assert(kRouteHashSize == 1 << 11, "route_hash yields 11 bits");
+
+__global__ void __launch_bounds__(kRouteThreads, 1) k_route_minmax(const __grid_constant__ RouteParams p) {
+  extern __shared__ __align__(16) float route_smem[];
+  int* hash_key = reinterpret_cast<int*>(route_smem);                       // [kRouteHashSize] source id or -1
+  int* hash_slot = hash_key + kRouteHashSize;                               // [kRouteHashSize]
+  float* acc = reinterpret_cast<float*>(hash_slot + kRouteHashSize);        // [n_hubs][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_cta = blockDim.x >> 5;
+  const int warps_total = gridDim.x * warps_cta;
   const int row_groups = (p.n_rows + kRouteRows - 1) / kRouteRows;
-  const int64_t n_tasks = static_cast<int64_t>(p.n_slabs) * p.n_arg * row_groups;
   const int64_t row_stride = static_cast<int64_t>(p.n_arg) * p.BD;
-  for (int64_t task = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += warps_total) {
-    const int slab_slot = static_cast<int>(task / row_groups);          // slab-major: (slab, slot) outer, rows inner
-    const int rg = static_cast<int>(task - static_cast<int64_t>(slab_slot) * row_groups);
-    const int slab = slab_slot / p.n_arg, slot = slab_slot - slab * p.n_arg;
+  const bool hubs_on = p.n_hubs > 0;
+  if (hubs_on) {
+    for (int t = threadIdx.x; t < kRouteHashSize; t += blockDim.x) hash_key[t] = -1;
+    for (int t = threadIdx.x; t < p.n_hubs * 32; t += blockDim.x) acc[t] = 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.n_hubs; t += blockDim.x) {
+      const int j = __ldg(p.hubs + t);
+      uint32_t h = route_hash(j);
+      while (atomicCAS(hash_key + h, -1, j) != -1) h = (h + 1) & (kRouteHashSize - 1);   // hub ids are distinct
+      hash_slot[h] = t;
+    }
+    __syncthreads();
+  }
+  for (int phase = 0; phase < p.n_slabs * p.n_arg; ++phase) {
+    const int slab = phase / p.n_arg, slot = phase - slab * p.n_arg;
     const int f = slab * 32 + lane;
-    if (f >= p.BD) continue;
+    const bool f_ok = f < p.BD;
     const int64_t base = static_cast<int64_t>(slot) * p.BD + f;
-    int arg[kRouteRows];
-    float v[kRouteRows];
+    for (int rg = blockIdx.x * warps_cta + warp; rg < row_groups; rg += warps_total) {
+      int arg[kRouteRows];
+      float v[kRouteRows];
 #pragma unroll
-    for (int r = 0; r < kRouteRows; ++r) {
-      const int row = rg * kRouteRows + r;
-      arg[r] = -1;
-      v[r] = 0.f;
-      if (row < p.n_rows) {
-        arg[r] = __ldcs(p.saved_arg + row * row_stride + base);
-        v[r] = __ldcs(p.t_route + row * row_stride + base);
+      for (int r = 0; r < kRouteRows; ++r) {
+        const int row = rg * kRouteRows + r;
+        arg[r] = -1;
+        v[r] = 0.f;
+        if (row < p.n_rows && f_ok) {
+          arg[r] = __ldcs(p.saved_arg + row * row_stride + base);
+          v[r] = __ldcs(p.t_route + row * row_stride + base);
+        }
+      }
+      int j[kRouteRows];
+#pragma unroll
+      for (int r = 0; r < kRouteRows; ++r) {
+        j[r] = arg[r] >= 0 ? __ldg(p.col + arg[r]) : -1;
+        if (p.val_lin != nullptr && arg[r] >= 0) v[r] *= __ldg(p.val_lin + arg[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRouteRows; ++r) {
+        if (j[r] < 0) continue;
+        int hub = -1;
+        if (hubs_on) {
+          uint32_t h = route_hash(j[r]);
+          int k = hash_key[h];
+          while (k != -1 && k != j[r]) { h = (h + 1) & (kRouteHashSize - 1); k = hash_key[h]; }
+          if (k == j[r]) hub = hash_slot[h];
+        }
+        if (hub >= 0) atomicAdd(acc + hub * 32 + lane, v[r]);
+        else atomicAdd(p.d_bases + static_cast<int64_t>(j[r]) * p.BD + f, v[r]);
       }
     }
-    int j[kRouteRows];
-#pragma unroll
-    for (int r = 0; r < kRouteRows; ++r) {
-      j[r] = arg[r] >= 0 ? __ldg(p.col + arg[r]) : -1;
-      if (p.val_lin != nullptr && arg[r] >= 0) v[r] *= __ldg(p.val_lin + arg[r]);
+    if (hubs_on) {                                           // flush this CTA's hub partials of the phase
+      __syncthreads();
+      for (int t = threadIdx.x; t < p.n_hubs * 32; t += blockDim.x) {
+        const float a = acc[t];
+        const int ff = slab * 32 + (t & 31);
+        if (a != 0.f && ff < p.BD) atomicAdd(p.d_bases + static_cast<int64_t>(__ldg(p.hubs + (t >> 5))) * p.BD + ff, a);
+        acc[t] = 0.f;
+      }
+      __syncthreads();
     }
-#pragma unroll
-    for (int r = 0; r < kRouteRows; ++r)
-      if (j[r] >= 0) atomicAdd(p.d_bases + static_cast<int64_t>(j[r]) * p.BD + f, v[r]);
   }
 }
 
@@ -855,11 +905,16 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     RouteParams r{};
     r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
     r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);
-    const int64_t tasks = static_cast<int64_t>(r.n_slabs) * n_arg * ceil_div(desc->n_dst, kRouteRows);
-    const int grid = static_cast<int>(std::min<int64_t>(ceil_div(tasks, 8), static_cast<int64_t>(sm_count()) * 8));
+    // hubs = the long columns of the CSC plan (more than EGC_CHUNK_EDGES entries), privatised per CTA
+    r.n_hubs = (csc_plan != nullptr && !(flags & EGC_BWD_NO_HUB_PRIVATISATION)) ? std::min(csc_plan->n_long, kRouteMaxHubs) : 0;
+    r.hubs = r.n_hubs > 0 ? csc_plan->long_rows : nullptr;
+    const int row_groups = ceil_div(desc->n_dst, kRouteRows);
+    const int grid = std::max(1, std::min(ceil_div(row_groups, kRouteThreads / 32), sm_count()));
+    const int smem = r.n_hubs > 0 ? 2 * kRouteHashSize * static_cast<int>(sizeof(int)) + r.n_hubs * 32 * static_cast<int>(sizeof(float)) : 0;
+    if (smem > 48 * 1024) EGC_CUDA(cudaFuncSetAttribute(k_route_minmax, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     {
       LaunchScope egc_ls_("k_route_minmax", st);
-      k_route_minmax<<<grid, 256, 0, st>>>(r);
+      k_route_minmax<<<grid, kRouteThreads, smem, st>>>(r);
     }
     EGC_LAUNCH_CHECK("k_route_minmax");
   }

@@ -204,44 +204,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n_pad >> 3) << 17) |
-                             (static_cast<uint32_t>(kTileM >> 4) << 24);
-      const uint32_t a_lbo = kTileM * 16, sbo = 128;
-      const uint32_t b_hi_addr = smem_u32(b_hi), b_lo_addr = smem_u32(b_lo);
-      int stage = 0, lo = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int acc = t & 1;
-        mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+    // The whole warp walks the loop converged (every operand below is warp-uniform, so the descriptors are
+    // built in uniform registers); one elected lane issues the tcgen05 instructions.
+    const uint32_t tmem_u = __shfl_sync(kFull, tmem_base, 0);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n_pad >> 3) << 17) |
+                           (static_cast<uint32_t>(kTileM >> 4) << 24);
+    constexpr uint32_t a_lbo = kTileM * 16, sbo = 128;
+    // descriptors advance by adding (byte offset >> 4) to the 14-bit start-address field
+    const uint64_t da_raw0 = make_desc(raw_addr, a_lbo, sbo), da_lo0 = make_desc(lo_addr, a_lbo, sbo);
+    const uint64_t db_hi0 = make_desc(smem_u32(b_hi), lbo_b, sbo), db_lo0 = make_desc(smem_u32(b_lo), lbo_b, sbo);
+    const uint32_t b_kstep = (2 * lbo_b) >> 4;
+    const bool three = p.n_terms == 3;
+    const bool leader = elect_one();              // the same lane issues every MMA and commit
+    int stage = 0, lo = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int acc = t & 1;
+      mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc) * 256u;
+      for (int j = 0; j < n_chunks; ++j) {
+        mbar_wait(conv_full(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
-        for (int j = 0; j < n_chunks; ++j) {
-          mbar_wait(conv_full(stage), phase);
-          tc_fence_after();
-          const uint32_t a_hi_addr = raw_addr + stage * kChunkBytes, a_lo_addr = lo_addr + lo * kChunkBytes;
+        if (leader) {
+          const uint64_t da_hi = da_raw0 + static_cast<uint32_t>(stage * (kChunkBytes >> 4));
+          const uint64_t da_lo = da_lo0 + static_cast<uint32_t>(lo * (kChunkBytes >> 4));
+          const uint64_t db_hi = db_hi0 + static_cast<uint32_t>(2 * j) * b_kstep;
+          const uint64_t db_lo = db_lo0 + static_cast<uint32_t>(2 * j) * b_kstep;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const uint32_t ks = static_cast<uint32_t>(2 * j + s);
-            const uint64_t da_hi = make_desc(a_hi_addr + s * 2 * a_lbo, a_lbo, sbo);
-            const uint64_t db_hi = make_desc(b_hi_addr + ks * 2 * lbo_b, lbo_b, sbo);
-            umma_tf32(d_tmem, da_hi, db_hi, idesc, (j | s) != 0 ? 1u : 0u);
-            if (p.n_terms == 3) {
-              const uint64_t da_lo = make_desc(a_lo_addr + s * 2 * a_lbo, a_lbo, sbo);
-              const uint64_t db_lo = make_desc(b_lo_addr + ks * 2 * lbo_b, lbo_b, sbo);
-              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+            const uint32_t ao = s * ((2 * a_lbo) >> 4), bo = s * b_kstep;
+            umma_tf32(d_tmem, da_hi + ao, db_hi + bo, idesc, (j | s) != 0 ? 1u : 0u);
+            if (three) {
+              umma_tf32(d_tmem, da_hi + ao, db_lo + bo, idesc, 1u);
+              umma_tf32(d_tmem, da_lo + ao, db_hi + bo, idesc, 1u);
             }
           }
           umma_commit(raw_empty(stage));          // frees the raw (= hi) slot once these MMAs have read it
           umma_commit(lo_empty(lo));
-          if (++stage == R) { stage = 0; phase ^= 1u; }
-          if (++lo == kLoStages) lo = 0;
+          if (j == n_chunks - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == R) { stage = 0; phase ^= 1u; }
+        if (++lo == kLoStages) lo = 0;
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global stores =====
     // tcgen05.ld gives one accumulator row per thread; storing that directly would touch 32 different 128-byte

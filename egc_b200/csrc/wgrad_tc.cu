@@ -5,8 +5,9 @@
 // in memory (MN-major).  kind::tf32 MMAs only accept MN-major operands in the 128B/32B-atom swizzle
 // (tools/umma_probe.cu: the no-swizzle MN-major bits yield zeros), so the operands are transposed on the
 // way through shared memory instead, and the MMA sees the plain K-major no-swizzle layout:
-//   warps 9-10  copy      cp.async (16 B) of raw node rows [x | d_bases | d_lin] into a deep row-major ring
-//                         (mbarrier-tracked, ~130 KB in flight per SM)
+//   warp  9     copy      one lane issues three TMA bulk copies per 16-node chunk (the x, d_bases and d_lin rows of
+//                         16 consecutive nodes are each one contiguous span) into a deep ring of
+//                         [x | d_bases | d_lin] blocks; completion lands on an mbarrier as transaction bytes
 //   warps 5-8   convert   4 nodes x 4 features register transposes -> hi / lo split -> the canonical K-major
 //                         layout (8 rows x 16 B core matrices, K = node), conflict-free rotated stores
 //   warp  4     MMA       one elected lane, 3-term split into a 128 x N_pad fp32 accumulator in TMEM
@@ -22,14 +23,13 @@
 
 namespace egc {
 
-constexpr int kWgThreads = 352;          // warps 0-3 epilogue, 4 MMA, 5-8 converters, 9-10 copy producers
+constexpr int kWgThreads = 320;          // warps 0-3 epilogue, 4 MMA, 5-8 converters, 9 copy producer
 constexpr int kWgChunk = 16;             // nodes per chunk (2 UMMA k-steps)
 constexpr int kWgM = 128;                // feature rows of the accumulator tile (F_in padded)
 constexpr int kWgMaxSmem = 227 * 1024;
 constexpr int kWgOpStages = 2;
 constexpr int kWgMaxRaw = 12;
 constexpr int kSegChunks = 24;           // chunks accumulated in TMEM between two flushes (384 nodes)
-constexpr int kWgCopyThreads = 64;
 constexpr int kWgConvThreads = 128;
 
 struct WgParams {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * R + 6 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), kWgCopyThreads); mbar_init(raw_empty(s), kWgConvThreads); }
+    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), kWgConvThreads); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(op_full(s), kWgConvThreads); mbar_init(op_empty(s), 1);
       mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128);
@@ -92,34 +92,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
   const uint32_t raw_addr = smem_u32(raw_ring), op_addr = smem_u32(op_ring);
 
   if (warp >= 9) {
-    // ================= copy producers: raw node rows, global -> shared ring =================
-    const int pt = tid - 9 * 32;
-    const int n_pieces = kWgChunk * ppn;
+    // ================= copy producer: three bulk copies per chunk =================
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int c = c_begin; c < c_end; ++c) {
-      const int node0 = c * kWgChunk;
+      const int64_t node0 = static_cast<int64_t>(c) * kWgChunk;
+      const uint32_t valid = static_cast<uint32_t>(min(static_cast<int64_t>(kWgChunk), p.n_nodes - node0));
+      const uint32_t bx = valid * p.f_in * 4, b1 = valid * p.n1 * 4, b2 = valid * p.n2 * 4;
       mbar_wait(raw_empty(stage), phase ^ 1u);
-      const uint32_t dst = raw_addr + stage * raw_bytes;
-      for (int piece = pt; piece < n_pieces; piece += kWgCopyThreads) {
-        const int i = static_cast<int>(__umulhi(static_cast<uint32_t>(piece), p.ppn_magic));   // piece / ppn
-        const int f = (piece - i * ppn) * 4;
-        const int64_t node = node0 + i;
-        const float* src;
-        if (f < p.f_in) src = p.x + node * p.f_in + f;
-        else if (f < p.f_in + p.n1) src = p.d1 + node * p.n1 + (f - p.f_in);
-        else src = p.d2 + node * p.n2 + (f - p.f_in - p.n1);
-        const bool ok = node < p.n_nodes;
-        cp_async_16_zfill(dst + piece * 16, ok ? src : p.x, ok ? 16u : 0u);
+      if (leader) {
+        const uint32_t dst = raw_addr + stage * raw_bytes;
+        mbar_arrive_expect_tx(raw_full(stage), bx + b1 + b2);
+        bulk_g2s(dst, p.x + node0 * p.f_in, bx, raw_full(stage));
+        bulk_g2s(dst + kWgChunk * p.f_in * 4, p.d1 + node0 * p.n1, b1, raw_full(stage));
+        if (b2 > 0) bulk_g2s(dst + kWgChunk * (p.f_in + p.n1) * 4, p.d2 + node0 * p.n2, b2, raw_full(stage));
       }
-      cp_async_mbar_arrive_noinc(raw_full(stage));
+      __syncwarp();
       if (++stage == R) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= 5) {
     // ================= converters: transpose 4 nodes x 4 features, hi / lo split =================
     const int ct = tid - 5 * 32;
     const int n_blocks = 4 * ppn;                          // (node quad, feature quad) blocks per chunk
-    const uint32_t row_bytes = static_cast<uint32_t>(W) * 4;
+    const uint32_t off_d1 = kWgChunk * p.f_in * 4, off_d2 = kWgChunk * (p.f_in + p.n1) * 4;
     int stage = 0, op = 0;
     uint32_t phase = 0, op_phase = 0;
     for (int c = 0; c < n_chunks; ++c) {
@@ -127,19 +123,33 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
       mbar_wait(op_empty(op), op_phase ^ 1u);
       const uint32_t src0 = raw_addr + stage * raw_bytes;
       const uint32_t dst0 = op_addr + op * op_bytes;
+      // nodes of this chunk that exist (the bulk copies of the last chunk stop at the end of the arrays)
+      const int valid = min(kWgChunk, p.n_nodes - (c_begin + c) * kWgChunk);
       for (int b = ct; b < n_blocks; b += kWgConvThreads) {
         const int quad = static_cast<int>(__umulhi(static_cast<uint32_t>(b), p.ppn_magic));    // b / ppn
         const int fq = b - quad * ppn;
-        const uint32_t src = src0 + static_cast<uint32_t>(quad) * 4 * row_bytes + fq * 16;
-        const float4 v0 = lds128(src), v1 = lds128(src + row_bytes), v2 = lds128(src + 2 * row_bytes),
-                     v3 = lds128(src + 3 * row_bytes);
+        const int f = fq * 4;
+        uint32_t src, row_bytes;                           // block of 4 nodes x 4 features inside its region
+        if (f < p.f_in) { row_bytes = p.f_in * 4; src = src0 + f * 4; }
+        else if (f < p.f_in + p.n1) { row_bytes = p.n1 * 4; src = src0 + off_d1 + (f - p.f_in) * 4; }
+        else { row_bytes = p.n2 * 4; src = src0 + off_d2 + (f - p.f_in - p.n1) * 4; }
+        src += static_cast<uint32_t>(quad) * 4 * row_bytes;
+        float4 v0 = lds128(src), v1 = lds128(src + row_bytes), v2 = lds128(src + 2 * row_bytes),
+               v3 = lds128(src + 3 * row_bytes);
+        if (valid < kWgChunk) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int n0 = quad * 4;
+          if (n0 >= valid) v0 = z;
+          if (n0 + 1 >= valid) v1 = z;
+          if (n0 + 2 >= valid) v2 = z;
+          if (n0 + 3 >= valid) v3 = z;
+        }
         float4 o[4] = {make_float4(v0.x, v1.x, v2.x, v3.x), make_float4(v0.y, v1.y, v2.y, v3.y),
                        make_float4(v0.z, v1.z, v2.z, v3.z), make_float4(v0.w, v1.w, v2.w, v3.w)};
         // rotate the store order by (fq / 2) % 4 so that the 8 lanes of a store phase hit 8 distinct 16-byte bank groups
         const int rot = (fq >> 1) & 3;
         if (rot & 1) { const float4 t = o[0]; o[0] = o[1]; o[1] = o[2]; o[2] = o[3]; o[3] = t; }
         if (rot & 2) { float4 t = o[0]; o[0] = o[2]; o[2] = t; t = o[1]; o[1] = o[3]; o[3] = t; }
-        const int f = fq * 4;
         uint32_t dst, lo_off;
         if (f < p.f_in) { dst = dst0 + quad * a_lbo + f * 16; lo_off = a_half; }
         else { dst = dst0 + 2 * a_half + quad * b_lbo + (f - p.f_in) * 16; lo_off = b_half; }
@@ -159,43 +169,45 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
       if (++op == kWgOpStages) { op = 0; op_phase ^= 1u; }
     }
   } else if (warp == 4) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
-                             (static_cast<uint32_t>(kWgM >> 4) << 24);
-      int op = 0;
-      uint32_t op_phase = 0;
-      int seg = 0;
-      for (int c = 0; c < n_chunks; ++seg) {
-        const int acc = seg & 1;
-        mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(seg) >> 1) & 1u) ^ 1u);
+    // ================= MMA issuer: converged warp, uniform descriptors, one elected lane issues =================
+    const uint32_t tmem_u = __shfl_sync(kFull, tmem_base, 0);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.n_pad >> 3) << 17) |
+                           (static_cast<uint32_t>(kWgM >> 4) << 24);
+    const uint64_t da0 = make_desc(op_addr, a_lbo, 128), db0 = make_desc(op_addr + 2 * a_half, b_lbo, 128);
+    const uint32_t a_lo_off = a_half >> 4, b_lo_off = b_half >> 4;
+    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
+    const bool three = p.n_terms == 3;
+    const bool leader = elect_one();
+    int op = 0;
+    uint32_t op_phase = 0;
+    int seg = 0;
+    for (int c = 0; c < n_chunks; ++seg) {
+      const int acc = seg & 1;
+      mbar_wait(tempty_bar(acc), ((static_cast<uint32_t>(seg) >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(acc) * 256u;
+      const int seg_end = min(c + kSegChunks, n_chunks);
+      for (int first = 1; c < seg_end; ++c, first = 0) {
+        mbar_wait(op_full(op), op_phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
-        const int seg_end = min(c + kSegChunks, n_chunks);
-        for (int first = 1; c < seg_end; ++c, first = 0) {
-          mbar_wait(op_full(op), op_phase);
-          tc_fence_after();
-          const uint32_t a_hi = op_addr + op * op_bytes, a_lo = a_hi + a_half;
-          const uint32_t b_hi = a_hi + 2 * a_half, b_lo = b_hi + b_half;
+        if (leader) {
+          const uint32_t so = static_cast<uint32_t>(op) * (op_bytes >> 4);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const uint64_t da_hi = make_desc(a_hi + s * 2 * a_lbo, a_lbo, 128);
-            const uint64_t db_hi = make_desc(b_hi + s * 2 * b_lbo, b_lbo, 128);
+            const uint64_t da_hi = da0 + (so + s * a_kstep), db_hi = db0 + (so + s * b_kstep);
             umma_tf32(d_tmem, da_hi, db_hi, idesc, (first && s == 0) ? 0u : 1u);
-            if (p.n_terms == 3) {
-              const uint64_t da_lo = make_desc(a_lo + s * 2 * a_lbo, a_lbo, 128);
-              const uint64_t db_lo = make_desc(b_lo + s * 2 * b_lbo, b_lbo, 128);
-              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+            if (three) {
+              umma_tf32(d_tmem, da_hi, db_hi + b_lo_off, idesc, 1u);
+              umma_tf32(d_tmem, da_hi + a_lo_off, db_hi, idesc, 1u);
             }
           }
           umma_commit(op_empty(op));
-          if (++op == kWgOpStages) { op = 0; op_phase ^= 1u; }
+          if (c + 1 == seg_end) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++op == kWgOpStages) { op = 0; op_phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue: flush each segment into this CTA's partial tile =================
     float* dst = p.partial + (static_cast<int64_t>(blockIdx.x) * kWgM + tid) * p.n_pad;

@@ -221,6 +221,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 #define EGC_BWD_STREAM_SWEEPS 2 /* tuning: store the target-side streams stream-major and gather them in one CSC sweep each
                                    (measured slower on B200 at the arxiv shape: 0.85 vs 0.60 ms) */
 #define EGC_BWD_SKIP_ROUTING 4  /* diagnostics only: drop the min/max gradient routing (results are then incomplete) */
+#define EGC_BWD_NO_HUB_PRIVATISATION 8 /* tuning: route min/max gradients of hub sources (long CSC columns) with global
+                                   fp32 atomics like every other source instead of per-CTA shared-memory accumulators */
 size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags);
 int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
                       const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
