@@ -18,6 +18,7 @@ META_NNZ, META_MAX_DEG, META_N_LONG, META_N_CHUNKS, META_N_LOOPS, META_ERRFLAGS 
 LOOPS_NONE, LOOPS_ALL_NODES, LOOPS_UP_TO_MAX_ID = 0, 1, 2
 GEMM_AUTO, GEMM_FP32_SIMT, GEMM_3XTF32, GEMM_TF32 = 0, 1, 2, 3
 BWD_DETERMINISTIC, BWD_STREAM_SWEEPS, BWD_SKIP_ROUTING, BWD_NO_HUB_PRIVATISATION = 1, 2, 4, 8
+BWD_SLAB16, BWD_SLAB32, BWD_NO_SLABS = 16, 32, 64
 
 AGGR_CODES = {"sum": 0, "mean": 1, "symnorm": 2, "min": 3, "max": 4, "var": 5, "std": 6}
 

@@ -90,6 +90,8 @@ struct CombineBwdParams {
   int sm_w, sm_g, sm_saved, sm_arg, sm_per_warp;
   int vec16;
   int64_t ts_row_stride, ts_stream_stride;   // floats between the streams of consecutive rows / between streams of a row
+  int ts_slab_w;                             // features per slab (== BD: one slab, the plain interleaved / stream-major layouts)
+  int64_t ts_slab_stride;                    // floats between consecutive feature slabs ([slab][row][stream][ts_slab_w])
   float* colsum_part;                        // [grid][HD + HAB] or null
   int skip_route;                            // diagnostics: drop the min/max routing
   float* t_route;                            // [n_rows][n_arg][BD] gradients of the min/max slots, routed by k_route_minmax
@@ -264,10 +266,13 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
           }
         }
       }
-      // plain (L2 write-back) stores: pass 2 gathers these rows next, whatever part of them survives in the L2 is a hit
-      if (GB::ts_sym(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride + p0, t_sym);
-      if (GB::ts_lin(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride + p0, t_lin);
-      if (GB::ts_sq(p) >= 0) st_row<EV>(ts + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride + p0, t_sq);
+      // plain (L2 write-back) stores: pass 2 gathers these rows next, whatever part of them survives in the L2 is a hit.
+      // Slab layout: feature p0 lives in slab p0 / W at offset p0 % W (an EV-wide piece never straddles slabs).
+      const int slab = p0 / p.ts_slab_w;
+      float* tsp = ts + static_cast<int64_t>(slab) * p.ts_slab_stride + (p0 - slab * p.ts_slab_w);
+      if (GB::ts_sym(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride, t_sym);
+      if (GB::ts_lin(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride, t_lin);
+      if (GB::ts_sq(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride, t_sq);
     }
     __syncwarp();     // the next row overwrites this warp's staging area
   }
@@ -443,6 +448,9 @@ struct ScatterParams {
   int routed;               // d_bases already holds a partial result (routed min/max gradients, earlier sweeps): accumulate
   int mode;
   int* long_counter;        // [n_long] zero on entry, or null: long columns are merged by a second launch (mode 1)
+  // feature-slab layout (k_scatter_slab): tstreams = [n_slabs][n_dst][n_ts][slab_w]; long_counter = [n_slabs][n_long]
+  int slab_w, n_slabs;
+  int64_t slab_stride;
 };
 
 constexpr int kScatterUnroll = 4;
@@ -652,6 +660,233 @@ static int launch_scatter(const ScatterParams& p, int tsmask, bool vec4, bool li
   return linw ? launch_scatter_mask<1, true>(p, tsmask, st) : launch_scatter_mask<1, false>(p, tsmask, st);
 }
 
+
+// =============================================================================================
+// backward pass 2, feature-slab variant.  When the target-side streams overflow the L2 (cfg2: 3 x 87 MB),
+// pass 1 stores them slab-major - [slab][target][stream][W floats], W = 16 or 32 - and this kernel sweeps
+// the CSC once per slab, so every sweep gathers from a table of n_dst x n_ts x W x 4 bytes that stays
+// L2-resident (cfg2, W = 16: 32.5 MB) instead of missing to HBM on nearly every entry.
+//   * persistent warps; each owns a CONTIGUOUS range of columns (and of the long columns' 256-entry chunks)
+//     of equal key mass, key = first entry + column id, found by two 32-ary searches of colptr.  Every warp
+//     does the same amount of work per slab, so the grid moves from slab to slab together, and a warp's
+//     index reads (colptr, rowidx, val_sym) are sequential;
+//   * G = W / 4 lanes cover one entry (all streams: n_ts consecutive 16-byte pieces W floats apart), the
+//     32 / G lane groups walk different entries and are merged with xor-shuffles per column;
+//   * row ids / symnorm weights of 32 consecutive entries sit in one register per lane (one coalesced load)
+//     and are broadcast with shuffles, whatever column boundaries fall inside.
+// Requires a plan whose chunks are ordered by first entry (egc_plan_build's order).
+// =============================================================================================
+constexpr int kSlabMaxSlabs = 16;
+
+// first i in [0, n] with key(i) >= target (key non-decreasing, key(n) = +inf): 32 probes per round
+template <class KeyF>
+__device__ __forceinline__ int warp_lower_bound(KeyF key, int n, int64_t target, int lane) {
+  int lo = 0, hi = n;                                   // the answer lies in [lo, hi]
+  while (lo < hi) {
+    const int step = (hi - lo + 31) >> 5;
+    const int probe = lo + lane * step;
+    const bool ge = probe >= hi || key(probe) >= target;
+    const unsigned m = __ballot_sync(kFull, ge);
+    const int f = m != 0u ? __ffs(m) - 1 : 32;          // first probe at or past the target
+    if (f == 0) {
+      hi = lo;
+    } else {
+      const int nlo = lo + (f - 1) * step + 1, nhi = min(lo + f * step, hi);
+      lo = nlo;
+      hi = nhi;
+    }
+  }
+  return lo;
+}
+
+template <int TSMASK, int W>
+__global__ void __launch_bounds__(kAggThreads, 4) k_scatter_slab(const __grid_constant__ ScatterParams p) {
+  constexpr int G = W / 4, NG = 32 / G;
+  constexpr int NS = ((TSMASK & 1) ? 1 : 0) + ((TSMASK & 2) ? 1 : 0) + ((TSMASK & 4) ? 1 : 0);
+  constexpr int U = NS >= 2 ? 2 : 4;
+  constexpr int BATCH = U * NG;
+  static_assert(BATCH <= 32, "one batch must fit the 32-entry index buffer");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kAggWarps + warp, warps_total = gridDim.x * kAggWarps;
+  const int g = lane / G, foff = (lane & (G - 1)) * 4;
+  const int nnz = __ldg(p.colptr + p.n_cols);
+
+  // ---- this warp's share: keys [k_begin, k_end) of the (first entry + column id) axis
+  const int64_t total_key = static_cast<int64_t>(nnz) + p.n_cols;
+  const int64_t q = (total_key + warps_total - 1) / warps_total;
+  const int64_t k_begin = q * gw, k_end = k_begin + q;
+  auto col_key = [&](int c) { return static_cast<int64_t>(__ldg(p.colptr + c)) + c; };
+  const int c_lo = warp_lower_bound(col_key, p.n_cols, k_begin, lane);
+  const int c_hi = warp_lower_bound(col_key, p.n_cols, k_end, lane);
+  int k_lo = 0, k_hi = 0;
+  if (p.n_chunks > 0) {
+    auto chunk_key = [&](int k) { return static_cast<int64_t>(__ldg(p.chunk_begin + k)) + __ldg(p.chunk_row + k); };
+    k_lo = warp_lower_bound(chunk_key, p.n_chunks, k_begin, lane);
+    k_hi = warp_lower_bound(chunk_key, p.n_chunks, k_end, lane);
+  }
+  const int n_my_chunks = k_hi - k_lo, n_my = n_my_chunks + (c_hi - c_lo);
+  if (n_my == 0) return;
+
+  const uint64_t pol_keep = l2_policy_keep();
+  const uint32_t row_stride = static_cast<uint32_t>(p.n_ts) * W;
+  const int64_t part_stride = static_cast<int64_t>(p.n_ts) * p.BD;
+  int buf_base = -(1 << 30), my_i = 0;                   // entries [buf_base, buf_base + 32): row ids / symnorm weights
+  float my_vs = 0.f;
+  int cp_base = -(1 << 30), cp0 = 0, cp1 = 0;            // colptr of columns [cp_base, cp_base + 32] (begin / end)
+
+  for (int slab = 0; slab < p.n_slabs; ++slab) {
+    const float* __restrict__ ts = p.tstreams + static_cast<int64_t>(slab) * p.slab_stride + foff;
+    const float* __restrict__ src_sym = ts + max(p.ts_sym, 0) * W;
+    const float* __restrict__ src_lin = ts + max(p.ts_lin, 0) * W;
+    const float* __restrict__ src_sq = ts + max(p.ts_sq, 0) * W;
+    const int fcol = slab * W + foff;                    // this lane's first feature inside a [BD] row
+
+    for (int t = 0; t < n_my; ++t) {
+      int colj, begin, end, chunk_id = -1;
+      if (t < n_my_chunks) {
+        chunk_id = k_lo + t;
+        colj = __ldg(p.chunk_row + chunk_id);
+        begin = __ldg(p.chunk_begin + chunk_id);
+        end = min(begin + EGC_CHUNK_EDGES, __ldg(p.colptr + colj + 1));
+      } else {
+        colj = c_lo + (t - n_my_chunks);
+        if (colj < cp_base || colj >= cp_base + 32) {
+          cp_base = colj;
+          cp0 = __ldg(p.colptr + min(colj + lane, p.n_cols));
+          cp1 = __ldg(p.colptr + min(colj + lane + 1, p.n_cols));
+        }
+        begin = __shfl_sync(kFull, cp0, colj - cp_base);
+        end = __shfl_sync(kFull, cp1, colj - cp_base);
+        if (end - begin > EGC_CHUNK_EDGES) continue;       // long column: its chunk tasks do it
+      }
+
+      float a_sym[4] = {0.f, 0.f, 0.f, 0.f}, a_lin[4] = {0.f, 0.f, 0.f, 0.f}, a_sq[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int e0 = begin; e0 < end; e0 += BATCH) {
+        if (e0 < buf_base || e0 + BATCH > buf_base + 32) {
+          buf_base = e0;
+          const int ec = min(e0 + lane, nnz - 1);
+          my_i = __ldg(p.rowidx + ec);
+          if constexpr ((TSMASK & 1) != 0) my_vs = __ldg(p.val_sym + ec);
+        }
+        uint32_t iu[U];
+        float vsu[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int e = e0 + u * NG + g;
+          ok[u] = e < end;
+          const int sl = min(e, end - 1) - buf_base;
+          iu[u] = static_cast<uint32_t>(__shfl_sync(kFull, my_i, sl));
+          vsu[u] = 0.f;
+          if constexpr ((TSMASK & 1) != 0) vsu[u] = __shfl_sync(kFull, my_vs, sl);
+        }
+        float4 xs[U], xl[U], xq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          xs[u] = xl[u] = xq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e0 + u * NG < end) {                         // warp-uniform: some group has a real entry in this slot
+            const size_t r = static_cast<size_t>(iu[u] * row_stride);
+            if constexpr ((TSMASK & 1) != 0) xs[u] = ldg_f4_hint(src_sym + r, pol_keep);
+            if constexpr ((TSMASK & 2) != 0) xl[u] = ldg_f4_hint(src_lin + r, pol_keep);
+            if constexpr ((TSMASK & 4) != 0) xq[u] = ldg_f4_hint(src_sq + r, pol_keep);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ok[u]) {
+            if constexpr ((TSMASK & 1) != 0) {
+              a_sym[0] = __fadd_rn(a_sym[0], __fmul_rn(xs[u].x, vsu[u])); a_sym[1] = __fadd_rn(a_sym[1], __fmul_rn(xs[u].y, vsu[u]));
+              a_sym[2] = __fadd_rn(a_sym[2], __fmul_rn(xs[u].z, vsu[u])); a_sym[3] = __fadd_rn(a_sym[3], __fmul_rn(xs[u].w, vsu[u]));
+            }
+            if constexpr ((TSMASK & 2) != 0) { a_lin[0] += xl[u].x; a_lin[1] += xl[u].y; a_lin[2] += xl[u].z; a_lin[3] += xl[u].w; }
+            if constexpr ((TSMASK & 4) != 0) { a_sq[0] += xq[u].x; a_sq[1] += xq[u].y; a_sq[2] += xq[u].z; a_sq[3] += xq[u].w; }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr ((TSMASK & 1) != 0) a_sym[k] += __shfl_xor_sync(kFull, a_sym[k], off);
+          if constexpr ((TSMASK & 2) != 0) a_lin[k] += __shfl_xor_sync(kFull, a_lin[k], off);
+          if constexpr ((TSMASK & 4) != 0) a_sq[k] += __shfl_xor_sync(kFull, a_sq[k], off);
+        }
+      }
+
+      const bool writer = lane < G;
+      if (chunk_id >= 0) {
+        // a chunk of a long column: publish the partial; the LAST chunk warp of (slab, column) to arrive sums all of
+        // them in chunk order and writes the column
+        if (writer) {
+          float* qd = p.partials + static_cast<int64_t>(chunk_id) * part_stride + fcol;
+          if constexpr ((TSMASK & 1) != 0) st_row<4>(qd + p.ts_sym * p.BD, a_sym);
+          if constexpr ((TSMASK & 2) != 0) st_row<4>(qd + p.ts_lin * p.BD, a_lin);
+          if constexpr ((TSMASK & 4) != 0) st_row<4>(qd + p.ts_sq * p.BD, a_sq);
+        }
+        __threadfence();
+        __syncwarp();
+        int lo = 0, hi = p.n_long;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(p.long_chunk_ptr + mid) <= chunk_id) lo = mid; else hi = mid;
+        }
+        const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
+        int* counter = p.long_counter + static_cast<int64_t>(slab) * p.n_long + lo;
+        int last = 0;
+        if (lane == 0) last = atomicAdd(counter, 1) == c1 - c0 - 1 ? 1 : 0;
+        last = __shfl_sync(kFull, last, 0);
+        if (!last) continue;
+        __threadfence();
+        if (lane == 0) *counter = 0;                         // ready for the next launch
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
+        if (writer) {
+          for (int c = c0; c < c1; ++c) {
+            const float* qs = p.partials + static_cast<int64_t>(c) * part_stride + fcol;
+            float tv[4];
+            if constexpr ((TSMASK & 1) != 0) { ld_cg<4>(tv, qs + p.ts_sym * p.BD); for (int k = 0; k < 4; ++k) a_sym[k] += tv[k]; }
+            if constexpr ((TSMASK & 2) != 0) { ld_cg<4>(tv, qs + p.ts_lin * p.BD); for (int k = 0; k < 4; ++k) a_lin[k] += tv[k]; }
+            if constexpr ((TSMASK & 4) != 0) { ld_cg<4>(tv, qs + p.ts_sq * p.BD); for (int k = 0; k < 4; ++k) a_sq[k] += tv[k]; }
+          }
+        }
+      }
+      if (!writer) continue;
+      float* dst = p.d_bases + static_cast<int64_t>(colj) * p.BD + fcol;
+      float r[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.routed) ld_plain<4>(r, dst);
+      if constexpr ((TSMASK & 4) != 0) {
+        float xj[4];
+        ld_row<4>(xj, p.bases + static_cast<int64_t>(colj) * p.BD + fcol);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] += 2.f * xj[k] * a_sq[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr ((TSMASK & 1) != 0) r[k] += a_sym[k];
+        if constexpr ((TSMASK & 2) != 0) r[k] += a_lin[k];
+      }
+      st_row<4>(dst, r);
+    }
+  }
+}
+
+template <int W>
+static int launch_scatter_slab(const ScatterParams& p, int tsmask, cudaStream_t st) {
+  const int grid = sm_count() * 4;
+  LaunchScope egc_ls_("k_scatter_bwd", st);
+  switch (tsmask) {
+    case 1: k_scatter_slab<1, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 2: k_scatter_slab<2, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 3: k_scatter_slab<3, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 4: k_scatter_slab<4, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 5: k_scatter_slab<5, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 6: k_scatter_slab<6, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    case 7: k_scatter_slab<7, W><<<grid, kAggThreads, 0, st>>>(p); break;
+    default: set_error("scatter_bwd: bad stream mask %d", tsmask); return EGC_ERR_UNSUPPORTED;
+  }
+  return EGC_OK;
+}
+
 // which target-side streams does this aggregator list need?  bit0 sym, bit1 lin, bit2 sq
 static int stream_mask_of(const egc_layer_desc& d, bool& has_route) {
   int m = 0;
@@ -686,7 +921,7 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
   L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256) +
-                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * sizeof(int), 256);
+                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * kSlabMaxSlabs * sizeof(int), 256);
   // per-CTA column-sum partials of the fused pass-1 kernel, or the two-stage colsum scratch when it cannot fuse
   const size_t hd = static_cast<size_t>(d.heads) * d.dim, hab = static_cast<size_t>(d.heads) * d.n_aggr * d.bases;
   const size_t fused = static_cast<size_t>(combine_bwd_grid(d.n_dst)) * (hd + hab) * sizeof(float) + 256;
@@ -824,6 +1059,25 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const bool stream_major = L.n_ts >= 2 && one_stream * L.n_ts > (size_t{72} << 20) && one_stream <= (size_t{100} << 20) &&
                             (flags & EGC_BWD_STREAM_SWEEPS) != 0;
 
+  // Feature-slab layout ([slab][N][L][W], see k_scatter_slab): chosen when the streams overflow the L2; W is the widest
+  // of 32 / 16 floats whose slab (n_dst x L x W x 4 bytes) stays well inside it.  EGC_BWD_SLAB16 / SLAB32 force a width,
+  // EGC_BWD_NO_SLABS keeps the plain interleaved layout.
+  int slab_w = 0;
+  {
+    const size_t ts_total = one_stream * L.n_ts;
+    const bool eligible = vec4 && val_lin == nullptr && !stream_major && L.tsmask != 0 && (flags & EGC_BWD_NO_SLABS) == 0;
+    auto fits = [&](int w) { return bd % w == 0 && bd / w >= 2 && bd / w <= kSlabMaxSlabs; };
+    if (eligible) {
+      if ((flags & EGC_BWD_SLAB32) && fits(32)) slab_w = 32;
+      else if ((flags & EGC_BWD_SLAB16) && fits(16)) slab_w = 16;
+      else if (!(flags & (EGC_BWD_SLAB16 | EGC_BWD_SLAB32)) && ts_total > (size_t{80} << 20)) {
+        const size_t per_float = static_cast<size_t>(desc->n_dst) * L.n_ts * sizeof(float);
+        if (fits(32) && per_float * 32 <= (size_t{48} << 20)) slab_w = 32;
+        else if (fits(16)) slab_w = 16;
+      }
+    }
+  }
+
   // ---- pass 1: streaming over target nodes
   bool fuse_colsum = false;
   {
@@ -852,6 +1106,14 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
     c.ts_row_stride = stream_major ? bd : static_cast<int64_t>(L.n_ts) * bd;
     c.ts_stream_stride = stream_major ? static_cast<int64_t>(desc->n_dst) * bd : bd;
+    c.ts_slab_w = bd;
+    c.ts_slab_stride = 0;
+    if (slab_w > 0) {
+      c.ts_row_stride = static_cast<int64_t>(L.n_ts) * slab_w;
+      c.ts_stream_stride = slab_w;
+      c.ts_slab_w = slab_w;
+      c.ts_slab_stride = static_cast<int64_t>(desc->n_dst) * L.n_ts * slab_w;
+    }
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
                aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
@@ -932,11 +1194,11 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
     s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
     s.partials = csc_part;
-    const bool fuse_merge = geo.n_pass == 1 && s.n_long > 0;
+    const bool fuse_merge = (geo.n_pass == 1 || slab_w > 0) && s.n_long > 0;
     s.long_counter = fuse_merge ? reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
                                                         align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256))
                                 : nullptr;
-    if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * sizeof(int), st));
+    if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
@@ -946,6 +1208,15 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.off_lin = L.ts_lin < 0 ? 0 : (stream_major ? L.ts_lin * table : static_cast<int64_t>(L.ts_lin) * bd);
     s.off_sq = L.ts_sq < 0 ? 0 : (stream_major ? L.ts_sq * table : static_cast<int64_t>(L.ts_sq) * bd);
     bool accumulate = L.has_route;
+    if (slab_w > 0) {
+      s.slab_w = slab_w;
+      s.n_slabs = bd / slab_w;
+      s.slab_stride = static_cast<int64_t>(desc->n_dst) * L.n_ts * slab_w;
+      s.routed = accumulate ? 1 : 0;
+      s.mode = 0;
+      if (int rc = slab_w == 32 ? launch_scatter_slab<32>(s, L.tsmask, st) : launch_scatter_slab<16>(s, L.tsmask, st)) return rc;
+      EGC_LAUNCH_CHECK("k_scatter_slab");
+    } else
     for (int bit = 1; bit <= 4; bit <<= 1) {
       const int sweep_mask = stream_major ? (L.tsmask & bit) : (bit == 1 ? L.tsmask : 0);
       if (sweep_mask == 0) continue;

@@ -335,7 +335,8 @@ static bool tc_plan(int k, int n, TcPlan& out) {
     if (cpg < 16 || cpg > 256) continue;
     const size_t b_bytes = static_cast<size_t>(2) * cpg * k_pad * 4;
     if (b_bytes + fixed + 2 * kChunkBytes > static_cast<size_t>(kMaxSmem)) continue;
-    const int r = static_cast<int>(std::min<size_t>(kMaxRawStages, (kMaxSmem - b_bytes - fixed) / kChunkBytes));
+    int r = static_cast<int>(std::min<size_t>(kMaxRawStages, (kMaxSmem - b_bytes - fixed) / kChunkBytes));
+    if (const char* cap = getenv("EGC_TC_MAX_RAW_STAGES")) r = std::max(kConvWarps, std::min(r, atoi(cap)));   // diagnostics
     if (r > best.raw_stages) best = TcPlan{s, cpg, r, b_bytes + fixed + static_cast<size_t>(r) * kChunkBytes};
     if (r >= 8) break;
   }
