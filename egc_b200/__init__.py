@@ -6,10 +6,12 @@ Public surface (mirrors the reference operator API, /root/reference/experiments/
     SparseTensor      minimal `torch_sparse.SparseTensor` container accepted by EGConv.forward
     GraphStructure    prepared device graph (CSR / CSC / symnorm weights / long-row plan)
     egconv            functional form on a prepared graph
+    collate / Batch / global_{add,mean,max}_pool   device-side mini-batch collation and graph readout
     build / load      compile / load libegc_b200.so (C ABI in include/egc_b200.h)
 """
 from ._lib import (BWD_DETERMINISTIC, GEMM_3XTF32, GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, EGCError, build,  # noqa: F401
                    load)
+from .batch import Batch, collate, collate_arrays, global_add_pool, global_max_pool, global_mean_pool, segment_ptr  # noqa: F401
 from .compat import EfficientGraphConv, convert_paper_state_dict, paper_to_egconv_perm  # noqa: F401
 from .conv import EGConv  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401

@@ -20,6 +20,7 @@ GEMM_AUTO, GEMM_FP32_SIMT, GEMM_3XTF32, GEMM_TF32 = 0, 1, 2, 3
 BWD_DETERMINISTIC, BWD_STREAM_SWEEPS, BWD_SKIP_ROUTING, BWD_NO_HUB_PRIVATISATION = 1, 2, 4, 8
 BWD_SLAB16, BWD_SLAB32, BWD_NO_SLABS = 16, 32, 64
 
+POOL_CODES = {"sum": 0, "add": 0, "mean": 1, "max": 2}
 AGGR_CODES = {"sum": 0, "mean": 1, "symnorm": 2, "min": 3, "max": 4, "var": 5, "std": 6}
 
 
@@ -77,6 +78,10 @@ SIGNATURES = {
     "egc_peer_wait": (c_int32, [_P, c_int32, c_int32, c_int32, _P, ctypes.c_uint32, c_int32, ctypes.c_uint64, _P, _P]),
     "egc_peer_reduce_rows": (c_int32, [_P, _P, _P, _P, c_int32, c_int32, _P, _P]),
     "egc_peer_sum_slots": (c_int32, [_P, c_int32, c_int32, _P, _P]),
+    "egc_collate_edges": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "egc_segment_ptr": (c_int32, [_P, c_int64, c_int32, _P, _P, _P]),
+    "egc_segment_pool_fwd": (c_int32, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "egc_segment_pool_bwd": (c_int32, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
 }
 
 _lib = None

@@ -287,6 +287,33 @@ int egc_peer_reduce_rows(const float* staging, const int32_t* rows, const int32_
 /* out[i] = sum_q slots[q * n + i] in rank order (the one-shot all-reduce of the replicated parameter gradients) */
 int egc_peer_sum_slots(const float* slots, int32_t world, int32_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Mini-batch plumbing (csrc/batch.cu).  Replaces, on the device, what the reference
+ * gets from PyG on the CPU: DataLoader / Batch.from_data_list collation (experiments/zinc/configs.py:36-45,60-67,
+ * experiments/cifar/configs.py:42-53) and the graph readout global_{add,mean,max}_pool
+ * (experiments/zinc/models.py:46-53,73).  Graph g of a collated batch owns the contiguous node range
+ * [node_ptr[g], node_ptr[g+1]).
+ * ---------------------------------------------------------------------------------------- */
+#define EGC_POOL_SUM 0
+#define EGC_POOL_MEAN 1  /* divides by max(count, 1), as scatter(reduce="mean") */
+#define EGC_POOL_MAX 2   /* empty graph -> 0; the gradient goes to the first maximal node, as scatter_max */
+
+/* Block-diagonal collation: edge e of graph g (edge_ptr[g] <= e < edge_ptr[g+1], graph-local node ids) becomes
+ * (src + node_ptr[g], dst + node_ptr[g]); batch_out[i] (may be NULL) = graph of node i.  *flags bit 0 is raised when a
+ * local id lies outside its graph. */
+int egc_collate_edges(const int64_t* src_local, const int64_t* dst_local, const int32_t* edge_ptr, const int32_t* node_ptr,
+                      int32_t n_graphs, int64_t n_edges, int64_t n_nodes, int64_t* src_out, int64_t* dst_out,
+                      int64_t* batch_out, int32_t* flags, void* stream);
+/* node_ptr [n_graphs + 1] from a sorted PyG `batch` vector.  *flags: bit 0 unsorted, bit 1 id outside [0, n_graphs). */
+int egc_segment_ptr(const int64_t* batch, int64_t n, int32_t n_graphs, int32_t* ptr, int32_t* flags, void* stream);
+/* out[g, :] = reduce over the nodes of graph g of x[i, :]  (x [n, f] row-major); arg [n_graphs, f] (EGC_POOL_MAX, may be
+ * NULL in inference) = winning node id or -1 */
+int egc_segment_pool_fwd(const float* x, const int32_t* ptr, int32_t n_graphs, int32_t f, int32_t mode, float* out,
+                         int32_t* arg, void* stream);
+/* d_x[i, :] for every node of every graph (all n rows are written when ptr covers them) */
+int egc_segment_pool_bwd(const float* d_out, const int32_t* ptr, const int32_t* arg, int32_t n_graphs, int32_t f,
+                         int32_t mode, float* d_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,152 @@
+"""Mini-batch plumbing: collation and graph readout.
+CPU part pins oracle/batching.py on hand-computed cases (the reference has no tests for these steps; the semantics are
+PyG 2.0's Batch.from_data_list and torch_scatter's scatter).  GPU part compares csrc/batch.cu with it
+through the C ABI: bit-exact for ids / offsets / argmax routing, fp32 reassociation tolerance for sums."""
+import pytest
+import torch
+
+from oracle import batching as OB
+from tests.util import rel_err
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: the oracle against hand-computed answers
+# ------------------------------------------------------------------------------------------------
+def _three_graphs():
+    g0 = (torch.tensor([[1.], [2.]]), torch.tensor([[0, 1], [1, 0]]), 2)
+    g1 = (torch.tensor([[3.], [4.], [5.]]), torch.tensor([[0, 2], [1, 1]]), 3)
+    g2 = (torch.tensor([[6.]]), torch.zeros((2, 0), dtype=torch.int64), 1)
+    return [g0, g1, g2]
+
+
+def test_oracle_collate_hand_case():
+    x, ei, batch, ptr = OB.collate(_three_graphs())
+    assert x.view(-1).tolist() == [1, 2, 3, 4, 5, 6]
+    assert ei.tolist() == [[0, 1, 2, 4], [1, 0, 3, 3]]
+    assert batch.tolist() == [0, 0, 1, 1, 1, 2]
+    assert ptr.tolist() == [0, 2, 5, 6]
+    with pytest.raises(ValueError):
+        OB.collate([(None, torch.tensor([[0], [2]]), 2)])
+
+
+def test_oracle_pool_hand_case():
+    x = torch.tensor([[1., -1.], [3., -5.], [2., 2.], [2., 7.], [0., 7.]], requires_grad=True)
+    batch = torch.tensor([0, 0, 2, 2, 2])                       # graph 1 is empty
+    assert OB.global_pool(x, batch, 3, "sum").tolist() == [[4., -6.], [0., 0.], [4., 16.]]
+    assert torch.equal(OB.global_pool(x, batch, 3, "mean"),
+                       torch.tensor([[2., -3.], [0., 0.], [4., 16.]]) / torch.tensor([[1.], [1.], [3.]]))
+    mx = OB.global_pool(x, batch, 3, "max")
+    assert mx.tolist() == [[3., -1.], [0., 0.], [2., 7.]]
+    (g,) = torch.autograd.grad(mx, x, torch.tensor([[1., 2.], [3., 4.], [5., 6.]]))
+    # ties go to the first maximal node (x[2,0] == x[3,0] == 2 -> node 2; x[3,1] == x[4,1] == 7 -> node 3)
+    assert g.tolist() == [[0., 2.], [1., 0.], [5., 0.], [0., 6.], [0., 0.]]
+    assert OB.global_pool(x, batch, None, "sum").shape == (3, 2)
+
+
+def test_synthetic_batches_have_the_named_shapes():
+    z = OB.zinc_like_graphs(128, seed=0)
+    n = sum(g[2] for g in z)
+    e = sum(g[1].size(1) for g in z)
+    assert 2600 < n < 3300 and 1.9 < e / n < 2.4                # ~23.2 nodes / graph, mean degree ~2.15
+    for _, ei, k in z[:16]:
+        assert int(ei.min()) >= 0 and int(ei.max()) < k
+        assert torch.equal(ei.flip(0).t().unique(dim=0), ei.t().unique(dim=0))       # both directions present
+    c = OB.cifar_like_graphs(16, seed=0)
+    for _, ei, k in c:
+        assert ei.size(1) == 8 * k and torch.equal(torch.bincount(ei[1], minlength=k), torch.full((k,), 8))
+        assert not bool((ei[0] == ei[1]).any())
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: csrc/batch.cu through the C ABI
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("maker", ["zinc", "cifar", "hand"])
+def test_collate_bit_exact(maker):
+    import egc_b200
+    graphs = {"zinc": lambda: OB.zinc_like_graphs(128, 1), "cifar": lambda: OB.cifar_like_graphs(32, 1),
+              "hand": _three_graphs}[maker]()
+    xo, eio, bo, po = OB.collate(graphs)
+    b = egc_b200.collate(graphs, device="cuda")
+    assert b.num_graphs == len(graphs) and b.num_nodes == int(po[-1])
+    assert torch.equal(b.edge_index.cpu(), eio)
+    assert torch.equal(b.batch.cpu(), bo)
+    assert torch.equal(b.ptr.cpu().long(), po)
+    assert torch.equal(b.x.cpu(), xo)
+    assert torch.equal(egc_b200.segment_ptr(b.batch, b.num_graphs).cpu().long(), po)
+
+
+@pytest.mark.gpu
+def test_collate_and_segment_ptr_errors():
+    import egc_b200
+    with pytest.raises(ValueError):
+        egc_b200.collate([(None, torch.tensor([[0], [2]]), 2)], device="cuda")
+    with pytest.raises(ValueError):
+        egc_b200.segment_ptr(torch.tensor([0, 2, 1], device="cuda"), 3)
+    with pytest.raises(ValueError):
+        egc_b200.segment_ptr(torch.tensor([0, 1, 3], device="cuda"), 3)
+    with pytest.raises(RuntimeError):
+        egc_b200.segment_ptr(torch.tensor([0, 1]), 2)                      # no CPU path
+    # empty graphs in the middle and at the end
+    p = egc_b200.segment_ptr(torch.tensor([0, 0, 3], device="cuda"), 6)
+    assert p.tolist() == [0, 2, 2, 2, 3, 3, 3]
+    assert egc_b200.segment_ptr(torch.zeros(0, dtype=torch.int64, device="cuda"), 2).tolist() == [0, 0, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+@pytest.mark.parametrize("f", [104, 128, 1, 300])
+def test_global_pool_fwd_bwd(mode, f):
+    import egc_b200
+    gen = torch.Generator().manual_seed(f)
+    sizes = torch.randint(0, 40, (37,), generator=gen)
+    sizes[5] = 0
+    sizes[-1] = 0
+    batch = torch.repeat_interleave(torch.arange(37), sizes)
+    n = int(sizes.sum())
+    x = torch.randn((n, f), generator=gen)
+    if mode == "max":                                                      # force ties: first maximal node must win
+        x = (x * 2).round() / 2
+    go = torch.randn((37, f), generator=gen)
+    xo = x.double().requires_grad_(True)
+    oo = OB.global_pool(xo, batch, 37, mode)
+    (gx_o,) = torch.autograd.grad(oo, xo, go.double())
+    xc = x.cuda().requires_grad_(True)
+    fn = {"sum": egc_b200.global_add_pool, "mean": egc_b200.global_mean_pool, "max": egc_b200.global_max_pool}[mode]
+    oc = fn(xc, batch.cuda(), 37)
+    (gx_c,) = torch.autograd.grad(oc, xc, go.cuda())
+    if mode == "max":
+        assert torch.equal(oc.cpu().double(), oo.detach())
+        assert torch.equal(gx_c.cpu().double(), gx_o)
+    else:
+        assert rel_err(oc, oo) < 1e-6 and rel_err(gx_c, gx_o) < 1e-6
+    # size=None (PyG: batch.max() + 1) and the Batch / int32-offset forms
+    assert fn(xc, batch.cuda()).shape[0] == int(batch.max()) + 1
+    ptr = egc_b200.segment_ptr(batch.cuda(), 37)
+    assert torch.equal(fn(xc, ptr), oc)
+
+
+@pytest.mark.gpu
+def test_zinc_shaped_stack_with_pooling_matches_oracle():
+    """EGC-S layer on a collated ZINC-shaped batch followed by the mean readout (zinc/models.py:65-73)."""
+    import egc_b200
+    from oracle import restatement as R
+    graphs = OB.zinc_like_graphs(128, 3)
+    _, eio, bo, po = OB.collate(graphs)
+    n = int(po[-1])
+    torch.manual_seed(0)
+    oracle = R.EGConvOracle(104, 104, aggrs=["sum"], num_heads=8, num_bases=4).double()
+    conv = egc_b200.EGConv(104, 104, aggrs=["sum"], num_heads=8, num_bases=4)
+    conv.load_state_dict({k: v.float() for k, v in oracle.state_dict().items()})
+    conv = conv.cuda()
+    x, go = torch.randn(n, 104), torch.randn(128, 104)
+    xo = x.double().requires_grad_(True)
+    ro = OB.global_pool(oracle(xo, eio), bo, 128, "mean")
+    gro = torch.autograd.grad(ro, [xo] + list(oracle.parameters()), go.double())
+    b = egc_b200.collate(graphs, device="cuda")
+    xc = x.cuda().requires_grad_(True)
+    rc = egc_b200.global_mean_pool(conv(xc, b.edge_index), b)
+    grc = torch.autograd.grad(rc, [xc] + list(conv.parameters()), go.cuda())
+    assert rel_err(rc, ro) < 1e-5
+    for a, c in zip(grc, gro):
+        assert rel_err(a, c) < 1e-5
