@@ -1,6 +1,8 @@
 // extern "C" entry points of the fused aggregation forward / backward, plus the two backward
 // kernels: the per-target streaming pass (gradient of the combination, target-side streams,
 // min/max routing) and the per-source CSC gather pass (atomic-free d_bases).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "aggregate_fast.cuh"
@@ -994,8 +996,16 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
                     hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) && (desc->dim % 4 != 0 || aligned16(bias));
   const int static_idx = fast ? static_cfg_index(*desc) : -1;
-  if (fast && p.n_long > 0) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, static_cast<size_t>(p.n_long) * sizeof(int), st));
-  if (static_idx >= 0) {
+  // row-block kernel: whole-graph calls of the specialised shapes (EGC_FWD_WARP_PER_ROW=1 keeps the warp-per-row kernel)
+  static const bool legacy_rows = getenv("EGC_FWD_WARP_PER_ROW") != nullptr;
+  const bool row_blocks = static_idx >= 0 && row_subset == nullptr && !legacy_rows;
+  const size_t counter_off = align_up(static_cast<size_t>(p.n_long) * sizeof(int), 256);   // inside the trailing 256 B
+  int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(p.long_counter) + counter_off);
+  if (row_blocks) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, counter_off + sizeof(int), st));
+  else if (fast && p.n_long > 0) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, static_cast<size_t>(p.n_long) * sizeof(int), st));
+  if (row_blocks) {
+    if (int rc = launch_aggregate_rows_static(static_idx, p, want_arg, task_counter, st)) return rc;
+  } else if (static_idx >= 0) {
     if (int rc = launch_aggregate_fast_static(static_idx, p, want_arg, smem, st)) return rc;
   } else if (fast) {
     if (int rc = (p.G == 32 ? launch_aggregate_fast_g32 : launch_aggregate_fast_g16)(p, mask, want_arg, smem, st)) return rc;
@@ -1071,9 +1081,11 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       if ((flags & EGC_BWD_SLAB32) && fits(32)) slab_w = 32;
       else if ((flags & EGC_BWD_SLAB16) && fits(16)) slab_w = 16;
       else if (!(flags & (EGC_BWD_SLAB16 | EGC_BWD_SLAB32)) && ts_total > (size_t{80} << 20)) {
-        const size_t per_float = static_cast<size_t>(desc->n_dst) * L.n_ts * sizeof(float);
-        if (fits(32) && per_float * 32 <= (size_t{48} << 20)) slab_w = 32;
-        else if (fits(16)) slab_w = 16;
+        // measured on B200 (profiles/r01e_bwd_layouts.txt): HBM-resident gathers of >= 512 B per entry run at ~6.5 TB/s
+        // (arxiv shape, 3 x 512 B: 0.57 ms plain vs 0.60 ms in 32-float slabs), 256 B entries only at ~4 TB/s (mag shape:
+        // 0.72 ms plain vs 0.54 ms in two 32-float slabs); 16-float slabs (64 B pieces) lose everywhere (0.89 / 0.93 ms).
+        const size_t entry_bytes = static_cast<size_t>(L.n_ts) * bd * sizeof(float);
+        if (fits(32) && entry_bytes <= 256) slab_w = 32;
       }
     }
   }

@@ -1,0 +1,369 @@
+// Row-block forward aggregation + per-head combination (sm_100a): the successor of k_aggregate_fast for whole-graph
+// calls (no row subset).  Same task model for long rows (chunk tasks, last chunk warp merges), same arithmetic and
+// the same bits; what changes is how a warp finds and feeds its rows:
+//
+//   * a task is a block of kRowsPerTask CONSECUTIVE rows handed out by an atomic counter: the row pointers of the
+//     block are one coalesced load, and the block's nnz are one contiguous range of `col` / `val_sym`;
+//   * that range (and the block's combination weights, also contiguous) is staged into the warp's shared memory
+//     with cp.async in windows of kWindow nnz, so the per-row chain  rowptr -> col -> gather  of the warp-per-row
+//     kernel (three dependent global latencies per row) is paid once per window;
+//   * software pipelining across rows: the first gather batch of row r+1 is issued BEFORE row r is finalized and
+//     combined, so the ~400-instruction row epilogue overlaps the gather latency of the next row.
+//
+// The profile that motivated it (profiles/r01d, arxiv shape): 42 % of the issue slots of k_aggregate_fast were spent
+// waiting on the first use of gathered rows, 12 % on the row-pointer / column-index loads.
+#pragma once
+
+#include "aggregate_fast.cuh"
+
+namespace egc {
+
+constexpr int kRowsPerTask = 8;
+constexpr int kWindow = 384;              // nnz staged at a time; >= EGC_CHUNK_EDGES so that every normal row fits
+static_assert(kWindow >= EGC_CHUNK_EDGES, "a normal row must fit the staging window");
+
+struct RowsSmem {                          // per-warp layout in floats, from A * BD and HAB
+  int w, col, val, per_warp;               // aggregate staging starts at 0
+  __host__ __device__ RowsSmem(int abd, int hab) {
+    w = (abd + 3) & ~3;
+    col = w + ((kRowsPerTask * hab + 3) & ~3);
+    val = col + kWindow;
+    per_warp = val + kWindow;
+  }
+};
+
+template <class Cfg, bool ARG>
+__global__ void __launch_bounds__(kAggThreads, 3) k_aggregate_rows(const __grid_constant__ AggParams p, int* __restrict__ task_counter) {
+  extern __shared__ __align__(16) float smem_all[];
+  constexpr int MASK = Cfg::MASK, G = Cfg::G;
+  using GC = Get<Cfg>;
+  constexpr int NG = 32 / G;
+  constexpr int U = kFastUnroll;
+  constexpr int STEP = U * NG;                                  // nnz consumed by one batch of the warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RowsSmem lay(GC::A(p) * GC::BD(p), GC::HAB(p));
+  float* sm = smem_all + warp * lay.per_warp;
+  float* s_agg = sm;
+  float* s_w = sm + lay.w;
+  int* s_col = reinterpret_cast<int*>(sm + lay.col);
+  float* s_val = sm + lay.val;
+  const int g = lane / G, li = lane & (G - 1);
+  const bool writer = li < GC::nvec(p) && lane < G;                  // lanes of group 0 that own a real piece
+  const int foff = min(li, GC::nvec(p) - 1) * 4;                     // idle lanes shadow the last piece, never write
+  const float* __restrict__ src = p.bases + foff;
+  const uint32_t BD = static_cast<uint32_t>(GC::BD(p));
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+  using AccT = Acc<MASK, 4, false, ARG>;
+  const bool stage_w = p.out != nullptr;
+
+  // epilogue geometry of this lane: outputs o = lane * EV + 32 * EV * it  ->  (weight row, offset in the head)
+  const int EV = (GC::D(p) & 3) == 0 ? 4 : 1;
+  int epi_w[kFastMaxIter], epi_d[kFastMaxIter];
+#pragma unroll
+  for (int it = 0; it < kFastMaxIter; ++it) {
+    const int o = lane * EV + 32 * EV * it;
+    const int h = o / GC::D(p);
+    epi_w[it] = h * GC::AB(p);
+    epi_d[it] = o - h * GC::D(p);
+  }
+
+  // ---- all aggregators of one finished row from its primitives, saved state, per-head combination (ref :195-208).
+  // `w` = this row's combination weights in shared memory (cp.async may still be in flight: waited here).
+  auto finalize = [&](int row, int begin, int end, const AccT& acc, const float* w) {
+    if (writer) {
+      const bool nonempty = end > begin;
+      const float cntf = static_cast<float>(max(end - begin, 1));   // mean divides by the nnz count, min 1
+      const float inv = __frcp_rn(cntf);
+      float mean[4] = {0.f, 0.f, 0.f, 0.f}, var[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr ((MASK & P_SUM) != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mean[k] = div_by(acc.sum[k], cntf, inv);
+      }
+      if constexpr ((MASK & P_SQ) != 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)      // mean_sq - mean * mean, ref :242 / :271
+          var[k] = __fsub_rn(div_by(acc.sq[k], cntf, inv), __fmul_rn(mean[k], mean[k]));
+      }
+      const size_t row_s = static_cast<size_t>(row);
+#pragma unroll
+      for (int a = 0; a < GC::A(p); ++a) {
+        const int code = GC::aggr(p, a);
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, sv[4];
+        int arg[4] = {-1, -1, -1, -1};
+        bool gate_sign = false;
+        switch (code) {
+          case EGC_AGGR_SUM:
+            if constexpr ((MASK & P_SUM) != 0) { for (int k = 0; k < 4; ++k) v[k] = acc.sum[k]; }
+            break;
+          case EGC_AGGR_MEAN:
+            if constexpr ((MASK & P_SUM) != 0) { for (int k = 0; k < 4; ++k) v[k] = mean[k]; }
+            break;
+          case EGC_AGGR_SYMNORM:
+            if constexpr ((MASK & P_SYM) != 0) { for (int k = 0; k < 4; ++k) v[k] = acc.sym[k]; }
+            break;
+          case EGC_AGGR_MAX:
+            if constexpr ((MASK & P_MAX) != 0) {
+              for (int k = 0; k < 4; ++k) { v[k] = nonempty ? acc.mx[k] : 0.f; if constexpr (ARG) arg[k] = acc.amx[k]; }
+            }
+            break;
+          case EGC_AGGR_MIN:
+            if constexpr ((MASK & P_MIN) != 0) {
+              for (int k = 0; k < 4; ++k) { v[k] = nonempty ? acc.mn[k] : 0.f; if constexpr (ARG) arg[k] = acc.amn[k]; }
+            }
+            break;
+          case EGC_AGGR_VAR:
+            if constexpr ((MASK & P_SQ) != 0) { for (int k = 0; k < 4; ++k) v[k] = var[k]; }
+            break;
+          case EGC_AGGR_STD:
+            if constexpr ((MASK & P_SQ) != 0) {       // sqrt(relu(var) + 1e-5), ref :244 / :273
+              for (int k = 0; k < 4; ++k) v[k] = sqrtf(__fadd_rn(fmaxf(var[k], 0.f), kStdEps));
+              gate_sign = true;
+            }
+            break;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sv[k] = (gate_sign && !(var[k] > 0.f)) ? -v[k] : v[k];   // sign bit = relu gate closed
+        if (p.out != nullptr) st_row<4>(s_agg + a * BD + foff, v);
+        if (p.agg_out != nullptr) stg_f4_hint(p.agg_out + (row_s * GC::A(p) + a) * BD + foff, v, pol_stream);
+        if (p.saved != nullptr) stg_f4_hint(p.saved + (row_s * GC::n_saved(p) + a) * BD + foff, sv, pol_stream);
+        if constexpr (ARG) {
+          const float t[4] = {__int_as_float(arg[0]), __int_as_float(arg[1]), __int_as_float(arg[2]), __int_as_float(arg[3])};
+          if (p.arg_out != nullptr)
+            stg_f4_hint(reinterpret_cast<float*>(p.arg_out) + (row_s * GC::A(p) + a) * BD + foff, t, pol_stream);
+          if (p.saved_arg != nullptr && GC::arg_slot(p, a) >= 0)
+            stg_f4_hint(reinterpret_cast<float*>(p.saved_arg) + (row_s * GC::n_arg(p) + GC::arg_slot(p, a)) * BD + foff, t, pol_stream);
+        }
+      }
+      if constexpr ((MASK & P_SQ) != 0) {
+        if (p.saved != nullptr && GC::n_saved(p) > GC::A(p)) stg_f4_hint(p.saved + (row_s * GC::n_saved(p) + GC::A(p)) * BD + foff, mean, pol_stream);
+      }
+    }
+    if (p.out == nullptr) return;
+    __syncwarp();
+    float* out = p.out + static_cast<int64_t>(row) * GC::HD(p);
+    const int D = GC::D(p), AB = GC::AB(p);
+#pragma unroll
+    for (int it = 0; it < kFastMaxIter; ++it) {
+      const int o = lane * EV + 32 * EV * it;
+      if (o < GC::HD(p)) {
+        const float* wh = w + epi_w[it];
+        const float* ad = s_agg + epi_d[it];
+        if (EV == 4) {
+          float r[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 12
+          for (int ab = 0; ab < AB; ++ab) {
+            const float wv = wh[ab];
+            const float4 a = *reinterpret_cast<const float4*>(ad + ab * D);
+            r[0] = fmaf(wv, a.x, r[0]); r[1] = fmaf(wv, a.y, r[1]); r[2] = fmaf(wv, a.z, r[2]); r[3] = fmaf(wv, a.w, r[3]);
+          }
+          if (p.bias != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + o));
+            r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
+          }
+          stg_f4_hint(out + o, r, pol_stream);
+        } else {
+          float r = 0.f;
+#pragma unroll 4
+          for (int ab = 0; ab < AB; ++ab) r = fmaf(wh[ab], ad[ab * D], r);
+          if (p.bias != nullptr) r += __ldg(p.bias + o);
+          __stcs(out + o, r);
+        }
+      }
+    }
+    __syncwarp();                                              // the next row overwrites the aggregate staging area
+  };
+
+  // =========================== phase 0: chunks of long rows (strided over the grid) ===========================
+  {
+    const int warps_total = gridDim.x * kAggWarps;
+    for (int task = blockIdx.x * kAggWarps + warp; task < p.n_chunks; task += warps_total) {
+      const int row = __ldg(p.chunk_row + task);
+      const int begin = __ldg(p.chunk_begin + task);
+      const int end = min(begin + EGC_CHUNK_EDGES, __ldg(p.rowptr + row + 1));
+      AccT acc;
+      acc.init();
+      for (int e0 = begin; e0 < end; e0 += 32) {
+        const int cnt = min(32, end - e0);
+        int my_col = 0;
+        float my_vs = 0.f;
+        if (lane < cnt) {
+          my_col = __ldg(p.col + e0 + lane);
+          if constexpr (MASK & P_SYM) my_vs = __ldg(p.val_sym + e0 + lane);
+        }
+        for (int u0 = 0; u0 < cnt; u0 += STEP) {
+          float4 x[U];
+          float vs[U];
+#pragma unroll
+          for (int t = 0; t < U; ++t) {
+            const int u = min(u0 + t * NG + g, cnt - 1);
+            const uint32_t j = static_cast<uint32_t>(__shfl_sync(kFull, my_col, u));
+            vs[t] = 0.f;
+            if constexpr (MASK & P_SYM) vs[t] = __shfl_sync(kFull, my_vs, u);
+            x[t] = ldg_f4_hint(src + static_cast<size_t>(j * BD), pol_keep);
+          }
+#pragma unroll
+          for (int t = 0; t < U; ++t) {
+            const int u = u0 + t * NG + g;
+            if (u < cnt) add_edge<MASK, ARG>(acc, x[t], vs[t], e0 + u);
+          }
+        }
+      }
+      if constexpr (NG > 1) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) acc.merge_xor(off);
+      }
+      // publish the partial; the LAST chunk warp of the row to arrive merges all of them in chunk order (same result
+      // whichever warp it is) and goes on to finalize the row
+      if (writer) acc.store(p.partials + (static_cast<int64_t>(task) * p.n_slots) * BD + foff, BD);
+      __threadfence();
+      __syncwarp();
+      int lo = 0, hi = p.n_long;                               // long row of this chunk: last l with long_chunk_ptr[l] <= task
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.long_chunk_ptr + mid) <= task) lo = mid; else hi = mid;
+      }
+      const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
+      int last = 0;
+      if (lane == 0) last = atomicAdd(p.long_counter + lo, 1) == c1 - c0 - 1 ? 1 : 0;
+      last = __shfl_sync(kFull, last, 0);
+      if (!last) continue;
+      __threadfence();
+      if (lane == 0) p.long_counter[lo] = 0;                   // ready for the next launch
+      acc.init();
+      for (int c = c0; c < c1; ++c) acc.merge_from(p.partials + (static_cast<int64_t>(c) * p.n_slots) * BD + foff, BD);
+      if (stage_w) {
+        const float* wsrc = p.weightings + static_cast<int64_t>(row) * GC::HAB(p);
+        for (int t = lane; t < GC::HAB(p); t += 32) cp_async_4(s_w + t, wsrc + t);
+        cp_async_wait_all();
+      }
+      finalize(row, __ldg(p.rowptr + row), __ldg(p.rowptr + row + 1), acc, s_w);
+    }
+  }
+
+  // =========================== phase 1: blocks of consecutive rows (dynamic) ===========================
+  const int n_blocks = (p.n_rows + kRowsPerTask - 1) / kRowsPerTask;
+  int task = 0;
+  if (lane == 0) task = atomicAdd(task_counter, 1);
+  task = __shfl_sync(kFull, task, 0);
+  while (task < n_blocks) {
+    const int r0 = task * kRowsPerTask;
+    const int nrows = min(kRowsPerTask, p.n_rows - r0);
+    const int rp = __ldg(p.rowptr + r0 + min(lane, nrows));    // lanes 0..nrows hold the block's row pointers
+    int next_task = 0;
+    if (lane == 0) next_task = atomicAdd(task_counter, 1);      // consumed at the end of this task
+    const int rpn = __shfl_down_sync(kFull, rp, 1);             // lane l < nrows: row l = [rp, rpn)
+    const unsigned long_mask = __ballot_sync(kFull, lane < nrows && rpn - rp > EGC_CHUNK_EDGES);
+    int ri = 0;
+    while (ri < nrows) {
+      if ((long_mask >> ri) & 1u) { ++ri; continue; }           // long row: its chunk tasks did it
+      const unsigned later_long = long_mask >> ri;
+      const int limit = later_long != 0u ? ri + __ffs(later_long) - 1 : nrows;
+      const int wb = __shfl_sync(kFull, rp, ri);
+      const unsigned fit = __ballot_sync(kFull, lane >= ri && lane < limit && rpn - wb <= kWindow);
+      const int n_fit = __popc(fit);                            // >= 1: a normal row has at most EGC_CHUNK_EDGES nnz
+      const int we = __shfl_sync(kFull, rpn, ri + n_fit - 1);
+      // ---- stage the window: column ids, symnorm weights, the rows' combination weights
+      for (int i = lane; i < we - wb; i += 32) {
+        cp_async_4(s_col + i, p.col + wb + i);
+        if constexpr (MASK & P_SYM) cp_async_4(s_val + i, p.val_sym + wb + i);
+      }
+      if (stage_w) {
+        const float* wsrc = p.weightings + static_cast<int64_t>(r0 + ri) * GC::HAB(p);
+        const int nw = n_fit * GC::HAB(p);
+        for (int t = lane; t < nw; t += 32) cp_async_4(s_w + t, wsrc + t);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+
+      // gathers of one batch: positions b + t * NG + g clamped to the row's last nnz
+      float4 x[U];
+      auto issue = [&](int b, int e) {
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+          const int pos = min(b + t * NG + g, e - 1);
+          const uint32_t j = static_cast<uint32_t>(s_col[pos - wb]);
+          x[t] = ldg_f4_hint(src + static_cast<size_t>(j * BD), pol_keep);
+        }
+      };
+      int b = wb, e = __shfl_sync(kFull, rpn, ri);
+      if (b < e) issue(b, e);
+      for (int r = ri; r < ri + n_fit; ++r) {
+        AccT acc;
+        acc.init();
+        for (int pos = b; pos < e;) {                           // x holds the batch that starts at pos
+          if (pos + STEP <= e) {
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+              const int q = pos + t * NG + g;
+              float vs = 0.f;
+              if constexpr (MASK & P_SYM) vs = s_val[q - wb];
+              add_edge<MASK, ARG>(acc, x[t], vs, q);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+              const int q = pos + t * NG + g;
+              if (q < e) {
+                float vs = 0.f;
+                if constexpr (MASK & P_SYM) vs = s_val[q - wb];
+                add_edge<MASK, ARG>(acc, x[t], vs, q);
+              }
+            }
+          }
+          pos += STEP;
+          if (pos < e) issue(pos, e);
+        }
+        if constexpr (NG > 1) {
+#pragma unroll
+          for (int off = G; off < 32; off <<= 1) acc.merge_xor(off);
+        }
+        int nb = 0, ne = 0;
+        if (r + 1 < ri + n_fit) {                               // next row's first batch flies over this row's epilogue
+          nb = e;
+          ne = __shfl_sync(kFull, rpn, r + 1);
+          if (nb < ne) issue(nb, ne);
+        }
+        finalize(r0 + r, b, e, acc, s_w + (r - ri) * GC::HAB(p));
+        b = nb;
+        e = ne;
+      }
+      ri += n_fit;
+    }
+    task = __shfl_sync(kFull, next_task, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+inline int rows_smem_bytes(const AggParams& p) {
+  return RowsSmem(p.A * p.BD, p.HAB).per_warp * kAggWarps * static_cast<int>(sizeof(float));
+}
+
+template <class Cfg, bool ARG>
+int launch_rows_one(const AggParams& p, int* task_counter, cudaStream_t st) {
+  auto kern = k_aggregate_rows<Cfg, ARG>;
+  const int smem_bytes = rows_smem_bytes(p);
+  if (smem_bytes > 48 * 1024) {
+    EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  }
+  const int n_blocks = ceil_div(p.n_rows, kRowsPerTask);
+  const int64_t warps_wanted = std::max<int64_t>(n_blocks, p.n_chunks);
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(warps_wanted, kAggWarps), static_cast<int64_t>(sm_count()) * 3));
+  {
+    LaunchScope egc_ls_("k_aggregate_fwd", st);
+    kern<<<grid, kAggThreads, smem_bytes, st>>>(p, task_counter);
+  }
+  EGC_LAUNCH_CHECK("k_aggregate_rows");
+  return EGC_OK;
+}
+
+template <class Cfg>
+int launch_rows_arg(const AggParams& p, bool arg, int* task_counter, cudaStream_t st) {
+  if constexpr ((Cfg::MASK & (P_MAX | P_MIN)) != 0) {
+    if (arg) return launch_rows_one<Cfg, true>(p, task_counter, st);
+  }
+  return launch_rows_one<Cfg, false>(p, task_counter, st);
+}
+
+}  // namespace egc
