@@ -657,6 +657,218 @@ static int launch_scatter_mask(const ScatterParams& p, int tsmask, cudaStream_t 
   return EGC_ERR_UNSUPPORTED;
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward pass 2, column-block variant (the CSC twin of k_aggregate_rows, aggregate_rows.cuh): a task is a block of
+// kColsPerTask CONSECUTIVE source columns handed out by an atomic counter; the column pointers are one coalesced
+// load, the block's target ids / symnorm weights are one contiguous range staged into the warp's shared memory with
+// cp.async in windows of kColWindow entries.  The warp-per-column kernel paid colptr -> rowidx -> gather (three
+// dependent global latencies) for every column of ~15 entries.  Chunks of long columns run first (strided), merged by
+// the last chunk warp to arrive.  128-bit pieces, unweighted entries, one pass (BD <= 128).
+// ---------------------------------------------------------------------------------------------
+constexpr int kColsPerTask = 8;
+constexpr int kColWindow = 384;
+static_assert(kColWindow >= EGC_CHUNK_EDGES, "a normal column must fit the staging window");
+
+template <int TSMASK, int G>
+__global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 : 3) k_scatter_cols(const __grid_constant__ ScatterParams p, int* __restrict__ task_counter) {
+  __shared__ int s_idx_all[kAggWarps][kColWindow];
+  __shared__ float s_val_all[kAggWarps][(TSMASK & 1) ? kColWindow : 1];
+  constexpr int NG = 32 / G, U = kScatterUnroll, STEP = U * NG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* s_idx = s_idx_all[warp];
+  float* s_val = s_val_all[warp];
+  const int g = lane / G, piece = lane & (G - 1);
+  const bool writer = piece < p.nvec && lane < G;
+  const int foff = min(piece, p.nvec - 1) * 4;
+  const uint32_t row_stride = static_cast<uint32_t>(p.ts_row_stride);   // n_dst * row_stride < 2^32 (checked by the host)
+  const int64_t part_stride = static_cast<int64_t>(p.n_ts) * p.BD;
+  const float* __restrict__ src_sym = p.tstreams + p.off_sym + foff;
+  const float* __restrict__ src_lin = p.tstreams + p.off_lin + foff;
+  const float* __restrict__ src_sq = p.tstreams + p.off_sq + foff;
+  float a_sym[4], a_lin[4], a_sq[4];
+
+  auto stage = [&](int wb, int we) {                           // entries [wb, we) -> shared memory (we - wb <= kColWindow)
+    for (int i = lane; i < we - wb; i += 32) {
+      cp_async_4(s_idx + i, p.rowidx + wb + i);
+      if constexpr ((TSMASK & 1) != 0) cp_async_4(s_val + i, p.val_sym + wb + i);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+  };
+  // sums over the staged entries [b, e) of one column (window base wb), then the xor-merge of the lane groups
+  auto accumulate = [&](int b, int e, int wb) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
+    for (int pos = b; pos < e; pos += STEP) {
+      float m[U], vs[U];
+      float4 xs[U], xl[U], xq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = pos + u * NG + g, qc = min(q, e - 1);
+        const size_t r = static_cast<size_t>(static_cast<uint32_t>(s_idx[qc - wb]) * row_stride);
+        m[u] = q < e ? 1.f : 0.f;
+        vs[u] = 0.f;
+        if constexpr ((TSMASK & 1) != 0) { vs[u] = q < e ? s_val[qc - wb] : 0.f; xs[u] = __ldg(reinterpret_cast<const float4*>(src_sym + r)); }
+        if constexpr ((TSMASK & 2) != 0) xl[u] = __ldg(reinterpret_cast<const float4*>(src_lin + r));
+        if constexpr ((TSMASK & 4) != 0) xq[u] = __ldg(reinterpret_cast<const float4*>(src_sq + r));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if constexpr ((TSMASK & 1) != 0) {
+          a_sym[0] = __fadd_rn(a_sym[0], __fmul_rn(xs[u].x, vs[u])); a_sym[1] = __fadd_rn(a_sym[1], __fmul_rn(xs[u].y, vs[u]));
+          a_sym[2] = __fadd_rn(a_sym[2], __fmul_rn(xs[u].z, vs[u])); a_sym[3] = __fadd_rn(a_sym[3], __fmul_rn(xs[u].w, vs[u]));
+        }
+        if constexpr ((TSMASK & 2) != 0) {
+          a_lin[0] = fmaf(xl[u].x, m[u], a_lin[0]); a_lin[1] = fmaf(xl[u].y, m[u], a_lin[1]);
+          a_lin[2] = fmaf(xl[u].z, m[u], a_lin[2]); a_lin[3] = fmaf(xl[u].w, m[u], a_lin[3]);
+        }
+        if constexpr ((TSMASK & 4) != 0) {
+          a_sq[0] = fmaf(xq[u].x, m[u], a_sq[0]); a_sq[1] = fmaf(xq[u].y, m[u], a_sq[1]);
+          a_sq[2] = fmaf(xq[u].z, m[u], a_sq[2]); a_sq[3] = fmaf(xq[u].w, m[u], a_sq[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr ((TSMASK & 1) != 0) a_sym[k] += __shfl_xor_sync(kFull, a_sym[k], off);
+        if constexpr ((TSMASK & 2) != 0) a_lin[k] += __shfl_xor_sync(kFull, a_lin[k], off);
+        if constexpr ((TSMASK & 4) != 0) a_sq[k] += __shfl_xor_sync(kFull, a_sq[k], off);
+      }
+    }
+  };
+  auto write_col = [&](int colj) {
+    if (!writer) return;
+    float* dst = p.d_bases + static_cast<int64_t>(colj) * p.BD + foff;
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.routed) ld_plain<4>(r, dst);
+    if constexpr ((TSMASK & 4) != 0) {
+      float xj[4];
+      ld_row<4>(xj, p.bases + static_cast<int64_t>(colj) * p.BD + foff);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] += 2.f * xj[k] * a_sq[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if constexpr ((TSMASK & 1) != 0) r[k] += a_sym[k];
+      if constexpr ((TSMASK & 2) != 0) r[k] += a_lin[k];
+    }
+    st_row<4>(dst, r);
+  };
+
+  // =========================== phase 0: chunks of long columns (strided over the grid) ===========================
+  {
+    const int warps_total = gridDim.x * kAggWarps;
+    for (int chunk_id = blockIdx.x * kAggWarps + warp; chunk_id < p.n_chunks; chunk_id += warps_total) {
+      const int colj = __ldg(p.chunk_row + chunk_id);
+      const int begin = __ldg(p.chunk_begin + chunk_id);
+      const int end = min(begin + EGC_CHUNK_EDGES, __ldg(p.colptr + colj + 1));
+      stage(begin, end);
+      accumulate(begin, end, begin);
+      if (writer) {
+        float* q = p.partials + static_cast<int64_t>(chunk_id) * part_stride + foff;
+        if constexpr ((TSMASK & 1) != 0) st_row<4>(q + p.ts_sym * p.BD, a_sym);
+        if constexpr ((TSMASK & 2) != 0) st_row<4>(q + p.ts_lin * p.BD, a_lin);
+        if constexpr ((TSMASK & 4) != 0) st_row<4>(q + p.ts_sq * p.BD, a_sq);
+      }
+      // the last chunk warp of the column to arrive sums all partials in chunk order and writes the column
+      __threadfence();
+      __syncwarp();
+      int lo = 0, hi = p.n_long;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.long_chunk_ptr + mid) <= chunk_id) lo = mid; else hi = mid;
+      }
+      const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
+      int last = 0;
+      if (lane == 0) last = atomicAdd(p.long_counter + lo, 1) == c1 - c0 - 1 ? 1 : 0;
+      last = __shfl_sync(kFull, last, 0);
+      if (!last) continue;
+      __threadfence();
+      if (lane == 0) p.long_counter[lo] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
+      for (int c = c0; c < c1; ++c) {
+        const float* q = p.partials + static_cast<int64_t>(c) * part_stride + foff;
+        float t[4];
+        if constexpr ((TSMASK & 1) != 0) {
+          ld_cg<4>(t, q + p.ts_sym * p.BD);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a_sym[k] += t[k];
+        }
+        if constexpr ((TSMASK & 2) != 0) {
+          ld_cg<4>(t, q + p.ts_lin * p.BD);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a_lin[k] += t[k];
+        }
+        if constexpr ((TSMASK & 4) != 0) {
+          ld_cg<4>(t, q + p.ts_sq * p.BD);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a_sq[k] += t[k];
+        }
+      }
+      write_col(colj);
+    }
+  }
+
+  // =========================== phase 1: blocks of consecutive columns (dynamic) ===========================
+  const int n_blocks = (p.n_cols + kColsPerTask - 1) / kColsPerTask;
+  int task = 0;
+  if (lane == 0) task = atomicAdd(task_counter, 1);
+  task = __shfl_sync(kFull, task, 0);
+  while (task < n_blocks) {
+    const int c0 = task * kColsPerTask;
+    const int ncols = min(kColsPerTask, p.n_cols - c0);
+    const int cp = __ldg(p.colptr + c0 + min(lane, ncols));    // lanes 0..ncols hold the block's column pointers
+    int next_task = 0;
+    if (lane == 0) next_task = atomicAdd(task_counter, 1);      // consumed at the end of this task
+    const int cpn = __shfl_down_sync(kFull, cp, 1);             // lane l < ncols: column l = [cp, cpn)
+    const unsigned long_mask = __ballot_sync(kFull, lane < ncols && cpn - cp > EGC_CHUNK_EDGES);
+    int ci = 0;
+    while (ci < ncols) {
+      if ((long_mask >> ci) & 1u) { ++ci; continue; }           // long column: its chunk tasks did it
+      const unsigned later_long = long_mask >> ci;
+      const int limit = later_long != 0u ? ci + __ffs(later_long) - 1 : ncols;
+      const int wb = __shfl_sync(kFull, cp, ci);
+      const unsigned fit = __ballot_sync(kFull, lane >= ci && lane < limit && cpn - wb <= kColWindow);
+      const int n_fit = __popc(fit);                            // >= 1
+      const int we = __shfl_sync(kFull, cpn, ci + n_fit - 1);
+      __syncwarp();                                             // every lane is done with the previous window
+      stage(wb, we);
+      for (int c = ci; c < ci + n_fit; ++c) {
+        const int b = __shfl_sync(kFull, cp, c), e = __shfl_sync(kFull, cpn, c);
+        accumulate(b, e, wb);
+        write_col(c0 + c);
+      }
+      ci += n_fit;
+    }
+    task = __shfl_sync(kFull, next_task, 0);
+  }
+}
+
+template <int G>
+static int launch_scatter_cols(const ScatterParams& p, int tsmask, int* task_counter, cudaStream_t st) {
+  const int n_blocks = ceil_div(p.n_cols, kColsPerTask);
+  const int resident = (tsmask & (tsmask - 1)) == 0 ? 4 : 3;     // CTAs per SM, as the launch bounds
+  const int grid = std::max(1, std::min(ceil_div(std::max(n_blocks, p.n_chunks), kAggWarps), sm_count() * resident));
+  {
+    LaunchScope egc_ls_("k_scatter_bwd", st);
+    switch (tsmask) {
+      case 1: k_scatter_cols<1, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 2: k_scatter_cols<2, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 3: k_scatter_cols<3, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 4: k_scatter_cols<4, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 5: k_scatter_cols<5, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 6: k_scatter_cols<6, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      case 7: k_scatter_cols<7, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      default: set_error("scatter_cols: bad stream mask %d", tsmask); return EGC_ERR_UNSUPPORTED;
+    }
+  }
+  EGC_LAUNCH_CHECK("k_scatter_cols");
+  return EGC_OK;
+}
+
 static int launch_scatter(const ScatterParams& p, int tsmask, bool vec4, bool linw, cudaStream_t st) {
   if (vec4) return linw ? launch_scatter_mask<4, true>(p, tsmask, st) : launch_scatter_mask<4, false>(p, tsmask, st);
   return linw ? launch_scatter_mask<1, true>(p, tsmask, st) : launch_scatter_mask<1, false>(p, tsmask, st);
@@ -923,7 +1135,8 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
   L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256) +
-                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * kSlabMaxSlabs * sizeof(int), 256);
+                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * kSlabMaxSlabs * sizeof(int), 256) +
+                     256;   // + the task counter of k_scatter_cols
   // per-CTA column-sum partials of the fused pass-1 kernel, or the two-stage colsum scratch when it cannot fuse
   const size_t hd = static_cast<size_t>(d.heads) * d.dim, hab = static_cast<size_t>(d.heads) * d.n_aggr * d.bases;
   const size_t fused = static_cast<size_t>(combine_bwd_grid(d.n_dst)) * (hd + hab) * sizeof(float) + 256;
@@ -1069,24 +1282,17 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const bool stream_major = L.n_ts >= 2 && one_stream * L.n_ts > (size_t{72} << 20) && one_stream <= (size_t{100} << 20) &&
                             (flags & EGC_BWD_STREAM_SWEEPS) != 0;
 
-  // Feature-slab layout ([slab][N][L][W], see k_scatter_slab): chosen when the streams overflow the L2; W is the widest
-  // of 32 / 16 floats whose slab (n_dst x L x W x 4 bytes) stays well inside it.  EGC_BWD_SLAB16 / SLAB32 force a width,
-  // EGC_BWD_NO_SLABS keeps the plain interleaved layout.
+  // Feature-slab layout ([slab][N][L][W], see k_scatter_slab): an opt-in tuning layout, EGC_BWD_SLAB16 / SLAB32 pick the
+  // width; the default (and EGC_BWD_NO_SLABS) is the plain interleaved layout.
   int slab_w = 0;
   {
-    const size_t ts_total = one_stream * L.n_ts;
     const bool eligible = vec4 && val_lin == nullptr && !stream_major && L.tsmask != 0 && (flags & EGC_BWD_NO_SLABS) == 0;
     auto fits = [&](int w) { return bd % w == 0 && bd / w >= 2 && bd / w <= kSlabMaxSlabs; };
     if (eligible) {
       if ((flags & EGC_BWD_SLAB32) && fits(32)) slab_w = 32;
       else if ((flags & EGC_BWD_SLAB16) && fits(16)) slab_w = 16;
-      else if (!(flags & (EGC_BWD_SLAB16 | EGC_BWD_SLAB32)) && ts_total > (size_t{80} << 20)) {
-        // measured on B200 (profiles/r01e_bwd_layouts.txt): HBM-resident gathers of >= 512 B per entry run at ~6.5 TB/s
-        // (arxiv shape, 3 x 512 B: 0.57 ms plain vs 0.60 ms in 32-float slabs), 256 B entries only at ~4 TB/s (mag shape:
-        // 0.72 ms plain vs 0.54 ms in two 32-float slabs); 16-float slabs (64 B pieces) lose everywhere (0.89 / 0.93 ms).
-        const size_t entry_bytes = static_cast<size_t>(L.n_ts) * bd * sizeof(float);
-        if (fits(32) && entry_bytes <= 256) slab_w = 32;
-      }
+      // No automatic choice any more: measured on B200 (profiles/r01e_bwd_layouts.txt) the column-block kernel on the
+      // plain interleaved layout beats every slab layout (arxiv shape 0.49 vs 0.60 ms, mag shape 0.39 vs 0.54 ms).
     }
   }
 
@@ -1210,7 +1416,18 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.long_counter = fuse_merge ? reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
                                                         align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256))
                                 : nullptr;
-    if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
+    // column-block kernel: 128-bit pieces, unweighted entries, one pass, interleaved streams
+    // (EGC_BWD_WARP_PER_COLUMN=1 keeps the warp-per-column kernel)
+    static const bool legacy_cols = getenv("EGC_BWD_WARP_PER_COLUMN") != nullptr;
+    const bool col_blocks = vec4 && val_lin == nullptr && !stream_major && slab_w == 0 && geo.n_pass == 1 &&
+                            (geo.G == 32 || geo.G == 16) && !legacy_cols;
+    const size_t counters_bytes = align_up(static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), 256);
+    int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
+                                               align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256) + counters_bytes);
+    if (col_blocks && s.long_counter == nullptr)
+      s.long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(task_counter) - counters_bytes);
+    if (col_blocks) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, counters_bytes + sizeof(int), st));
+    else if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
@@ -1228,6 +1445,10 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       s.mode = 0;
       if (int rc = slab_w == 32 ? launch_scatter_slab<32>(s, L.tsmask, st) : launch_scatter_slab<16>(s, L.tsmask, st)) return rc;
       EGC_LAUNCH_CHECK("k_scatter_slab");
+    } else if (col_blocks) {
+      s.routed = accumulate ? 1 : 0;
+      s.mode = 0;
+      if (int rc = geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st)) return rc;
     } else
     for (int bit = 1; bit <= 4; bit <<= 1) {
       const int sweep_mask = stream_major ? (L.tsmask & bit) : (bit == 1 ? L.tsmask : 0);

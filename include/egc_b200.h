@@ -224,7 +224,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 #define EGC_BWD_NO_HUB_PRIVATISATION 8 /* tuning: route min/max gradients of hub sources (long CSC columns) with global
                                    fp32 atomics like every other source instead of per-CTA shared-memory accumulators */
 #define EGC_BWD_SLAB16 16       /* tuning: force the feature-slab layout of the target-side streams, 16 floats per slab */
-#define EGC_BWD_SLAB32 32       /* tuning: same with 32 floats per slab (default: chosen from the stream footprint)    */
+#define EGC_BWD_SLAB32 32       /* tuning: same with 32 floats per slab (default: plain interleaved streams)            */
 #define EGC_BWD_NO_SLABS 64     /* tuning: never use the feature-slab layout (one interleaved sweep)                    */
 size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags);
 int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
