@@ -395,5 +395,8 @@ int launch_aggregate_fast_g16(const AggParams& p, int mask, bool arg, int smem_b
 int launch_aggregate_fast_static(int cfg_index, const AggParams& p, bool arg, int smem_bytes, cudaStream_t st);
 // row-block kernel (aggregate_rows.cuh): whole-graph calls of the specialised layer shapes; *task_counter must be 0
 int launch_aggregate_rows_static(int cfg_index, const AggParams& p, bool arg, int* task_counter, cudaStream_t st);
+int launch_aggregate_rows_g32(const AggParams& p, int mask, bool arg, int* task_counter, cudaStream_t st);
+int launch_aggregate_rows_g16(const AggParams& p, int mask, bool arg, int* task_counter, cudaStream_t st);
+int rows_kernel_smem_bytes(const AggParams& p);
 
 }  // namespace egc

@@ -1211,13 +1211,16 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int static_idx = fast ? static_cfg_index(*desc) : -1;
   // row-block kernel: whole-graph calls of the specialised shapes (EGC_FWD_WARP_PER_ROW=1 keeps the warp-per-row kernel)
   static const bool legacy_rows = getenv("EGC_FWD_WARP_PER_ROW") != nullptr;
-  const bool row_blocks = static_idx >= 0 && row_subset == nullptr && !legacy_rows;
+  // needs the window + 8 rows of weights per warp in shared memory (3 CTAs per SM)
+  const bool row_blocks = fast && row_subset == nullptr && !legacy_rows && rows_kernel_smem_bytes(p) <= 72 * 1024;
   const size_t counter_off = align_up(static_cast<size_t>(p.n_long) * sizeof(int), 256);   // inside the trailing 256 B
   int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(p.long_counter) + counter_off);
   if (row_blocks) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, counter_off + sizeof(int), st));
   else if (fast && p.n_long > 0) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, static_cast<size_t>(p.n_long) * sizeof(int), st));
-  if (row_blocks) {
+  if (row_blocks && static_idx >= 0) {
     if (int rc = launch_aggregate_rows_static(static_idx, p, want_arg, task_counter, st)) return rc;
+  } else if (row_blocks) {
+    if (int rc = (p.G == 32 ? launch_aggregate_rows_g32 : launch_aggregate_rows_g16)(p, mask, want_arg, task_counter, st)) return rc;
   } else if (static_idx >= 0) {
     if (int rc = launch_aggregate_fast_static(static_idx, p, want_arg, smem, st)) return rc;
   } else if (fast) {

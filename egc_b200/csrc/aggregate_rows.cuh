@@ -366,4 +366,15 @@ int launch_rows_arg(const AggParams& p, bool arg, int* task_counter, cudaStream_
   return launch_rows_one<Cfg, false>(p, task_counter, st);
 }
 
+template <int G>
+int launch_rows_family(const AggParams& p, int mask, bool arg, int* task_counter, cudaStream_t st) {
+  switch (mask) {
+#define X(M) case M: return launch_rows_arg<DynCfg<M, G>>(p, arg, task_counter, st);
+    EGC_FAST_MASK_CASES(X)
+#undef X
+  }
+  set_error("aggregate: unsupported primitive mask %d", mask);
+  return EGC_ERR_UNSUPPORTED;
+}
+
 }  // namespace egc

@@ -13,4 +13,5 @@ int launch_aggregate_rows_static(int cfg_index, const AggParams& p, bool arg, in
   set_error("aggregate: unknown static configuration %d", cfg_index);
   return EGC_ERR_UNSUPPORTED;
 }
+int rows_kernel_smem_bytes(const AggParams& p) { return rows_smem_bytes(p); }
 }  // namespace egc
