@@ -59,6 +59,8 @@ struct TcParams {
   int raw_stages;
   int n_terms;                             // 3: 3xTF32, 1: TF32
   int num_tiles;
+  int ablate;                              // diagnostics (EGC_TC_ABLATE, results become wrong): 1 no lo conversion, 2 no epilogue,
+                                           // 4 no MMA, 8 no A copies, 16 no global stores  (tools/gemm_ablate.sh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -163,13 +165,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       const bool k_ok = k < K;
       mbar_wait(raw_empty(stage), phase ^ 1u);
       const uint32_t dst = raw_addr + stage * kChunkBytes + c4 * (kTileM * 16) + r0 * 16;
+      if (p.ablate & 8) {
+        mbar_arrive(raw_full(stage));
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int64_t row = row_base + r0 + 8 * i;
-        const bool ok = k_ok && row < p.M;
-        cp_async_16_zfill(dst + i * 128, ok ? base + row * ld : p.a1, ok ? 16u : 0u);
+        for (int i = 0; i < 16; ++i) {
+          const int64_t row = row_base + r0 + 8 * i;
+          const bool ok = k_ok && row < p.M;
+          cp_async_16_zfill(dst + i * 128, ok ? base + row * ld : p.a1, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(raw_full(stage));
       }
-      cp_async_mbar_arrive_noinc(raw_full(stage));
       stage += kCopyWarps;
       if (stage >= R) { stage -= R; phase ^= 1u; }
       j += kCopyWarps;
@@ -186,10 +192,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       mbar_wait(raw_full(stage), phase);
       const uint32_t src = raw_addr + stage * kChunkBytes + lane * 16;
       float4 v[16];
+      if (!(p.ablate & 1)) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = lds128(src + i * 512);
+        for (int i = 0; i < 16; ++i) v[i] = lds128(src + i * 512);
+      }
       mbar_wait(lo_empty(cw), lo_phase ^ 1u);
       const uint32_t dlo = lo_addr + cw * kChunkBytes + lane * 16;
+      if (!(p.ablate & 1))
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float4 l = make_float4(v[i].x - tf32_hi(v[i].x), v[i].y - tf32_hi(v[i].y), v[i].z - tf32_hi(v[i].z),
@@ -226,7 +235,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       for (int j = 0; j < n_chunks; ++j) {
         mbar_wait(conv_full(stage), phase);
         tc_fence_after();
-        if (leader) {
+        if (leader && (p.ablate & 4)) {
+          umma_commit(raw_empty(stage));
+          umma_commit(lo_empty(lo));
+          if (j == n_chunks - 1) umma_commit(tfull_bar(acc));
+        } else if (leader) {
           const uint64_t da_hi = da_raw0 + static_cast<uint32_t>(stage * (kChunkBytes >> 4));
           const uint64_t da_lo = da_lo0 + static_cast<uint32_t>(lo * (kChunkBytes >> 4));
           const uint64_t db_hi = db_hi0 + static_cast<uint32_t>(2 * j) * b_kstep;
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       mbar_wait(tfull_bar(acc), (static_cast<uint32_t>(t) >> 1) & 1u);
       tc_fence_after();
       const int64_t row0 = static_cast<int64_t>(first_tile + t * tile_step) * kTileM + warp * 32;
-      for (int col0 = 0; col0 < n_pad; col0 += 32) {
+      for (int col0 = 0; col0 < ((p.ablate & 2) ? 0 : n_pad); col0 += 32) {
         const int width = min(32, n_pad - col0);              // 16 or 32 columns in this block
         uint32_t r[32];
         {
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
                                __uint_as_float(r[4 * q + 3])));
         __syncwarp();
         const int col = n_begin + col0 + 4 * piece;
-        if (4 * piece < width && col < n_end) {
+        if (4 * piece < width && col < n_end && !(p.ablate & 16)) {
           const bool to_c1 = col < p.n1;
           const int c2 = col - p.n1;
           float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -361,6 +374,7 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   p.cols_per_group = plan.cols_per_group;
   p.raw_stages = plan.raw_stages;
   p.num_tiles = ceil_div(p.M, kTileM);
+  if (const char* ab = getenv("EGC_TC_ABLATE")) p.ablate = atoi(ab);
   static bool attr_set = false;
   if (!attr_set) {
     EGC_CUDA(cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));

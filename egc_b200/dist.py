@@ -383,3 +383,56 @@ class GraphedStep:
     def replay(self):
         self.graph.replay()
         return self.outputs
+
+
+class GradientAllReduce:
+    """Data-parallel mini-batch training (BASELINE configs 1 / 5): every rank runs the same
+    model on different collated batches and the parameter gradients are combined with ONE flat all-reduce per
+    bucket.  `weight` is this rank's share of the global batch (graphs on this rank / graphs on all ranks), so that
+    a loss averaged over the local graphs yields the gradient of the loss averaged over ALL graphs - the parity
+    statement of the single-process run on the concatenated batch.  Buckets are persistent flat buffers (no
+    allocation per step, CUDA-graph friendly); NCCL on GPUs, gloo in the CPU tests."""
+
+    def __init__(self, params, group=None, bucket_bytes: int = 32 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.buckets = []                                   # (flat buffer, [(param, offset, numel)])
+        cur, cur_bytes = [], 0
+        for p in self.params:
+            nbytes = p.numel() * p.element_size()
+            if cur and (cur_bytes + nbytes > bucket_bytes or cur[0].dtype != p.dtype or cur[0].device != p.device):
+                self._close(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close(cur)
+
+    def _close(self, ps):
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+        views, off = [], 0
+        for p in ps:
+            views.append((p, off, p.numel()))
+            off += p.numel()
+        self.buckets.append((flat, views))
+
+    @torch.no_grad()
+    def __call__(self, weight: float = None):
+        """Overwrites every p.grad with sum_r weight_r * grad_r (weight defaults to 1 / world_size)."""
+        world = dist.get_world_size(self.group)
+        w = (1.0 / world) if weight is None else float(weight)
+        handles = []
+        for flat, views in self.buckets:
+            for p, off, n in views:
+                if p.grad is None:
+                    flat[off:off + n].zero_()
+                else:
+                    torch.mul(p.grad.reshape(-1), w, out=flat[off:off + n])
+            handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for (flat, views), h in zip(self.buckets, handles):
+            h.wait()
+            for p, off, n in views:
+                if p.grad is None:
+                    p.grad = flat[off:off + n].view_as(p).clone()
+                else:
+                    p.grad.copy_(flat[off:off + n].view_as(p))

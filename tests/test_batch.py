@@ -150,3 +150,53 @@ def test_zinc_shaped_stack_with_pooling_matches_oracle():
     assert rel_err(rc, ro) < 1e-5
     for a, c in zip(grc, gro):
         assert rel_err(a, c) < 1e-5
+
+
+def _stack_case(graphs, f_in, hidden, aggrs, heads, layers, readout, seed):
+    """L x (EGConv -> ReLU) then a graph readout, CUDA library vs the fp64 oracle on one collated batch
+    (the model bodies of ref experiments/zinc/models.py:56-73 and experiments/cifar/models.py:56-75)."""
+    import egc_b200
+    from oracle import restatement as R
+    _, eio, bo, po = OB.collate(graphs)
+    n, g = int(po[-1]), len(graphs)
+    torch.manual_seed(seed)
+    dims = [f_in] + [hidden] * layers
+    oracles = [R.EGConvOracle(dims[i], dims[i + 1], aggrs=aggrs, num_heads=heads, num_bases=4).double() for i in range(layers)]
+    convs = []
+    for o in oracles:
+        c = egc_b200.EGConv(o.in_channels, o.out_channels, aggrs=aggrs, num_heads=heads, num_bases=4)
+        c.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+        convs.append(c.cuda())
+    x, go = torch.randn(n, f_in), torch.randn(g, hidden)
+    xo = x.double().requires_grad_(True)
+    h = xo
+    for o in oracles:
+        h = torch.relu(o(h, eio))
+    ro = OB.global_pool(h, bo, g, readout)
+    po_list = [p for o in oracles for p in o.parameters()]
+    gro = torch.autograd.grad(ro, [xo] + po_list, go.double())
+    b = egc_b200.collate(graphs, device="cuda")
+    xc = x.cuda().requires_grad_(True)
+    h = xc
+    for c in convs:
+        h = torch.relu(c(h, b.edge_index))
+    pool = {"mean": egc_b200.global_mean_pool, "sum": egc_b200.global_add_pool, "max": egc_b200.global_max_pool}[readout]
+    rc = pool(h, b)
+    pc_list = [p for c in convs for p in c.parameters()]
+    grc = torch.autograd.grad(rc, [xc] + pc_list, go.cuda())
+    # four stacked fp32 layers: the forward error compounds, the bar per layer stays 1e-5 (tests/test_gpu_parity.py)
+    assert rel_err(rc, ro) < 4e-5
+    for a, c in zip(grc, gro):
+        assert rel_err(a, c) < 4e-5
+
+
+@pytest.mark.gpu
+def test_zinc_shaped_egc_s_four_layers():
+    """BASELINE config 1: EGC-S (sum aggregator, 8 heads, 4 bases, hidden 104, 4 layers), 128 molecule-like graphs."""
+    _stack_case(OB.zinc_like_graphs(128, 5), 104, 104, ["sum"], 8, 4, "mean", 0)
+
+
+@pytest.mark.gpu
+def test_cifar_shaped_egc_m_four_layers():
+    """BASELINE config 5: EGC-M (symnorm + max + std, 4 heads, 4 bases, hidden 128, 4 layers), kNN superpixel graphs."""
+    _stack_case(OB.cifar_like_graphs(32, 5), 128, 128, ["symnorm", "max", "std"], 4, 4, "mean", 1)

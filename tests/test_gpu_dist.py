@@ -142,3 +142,53 @@ def test_partitioned_layer_matches_single_gpu_world2(transport):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel mini-batches (BASELINE config 5: CIFAR-shaped EGC-M batches, gradient all-reduce)
+# ------------------------------------------------------------------------------------------------
+def _dp_model(dev):
+    import egc_b200
+    torch.manual_seed(11)
+    return torch.nn.ModuleList([egc_b200.EGConv(5, 128, aggrs=AGGRS, num_heads=4, num_bases=4),
+                                egc_b200.EGConv(128, 128, aggrs=AGGRS, num_heads=4, num_bases=4)]).to(dev)
+
+
+def _dp_loss(model, graphs, dev):
+    import egc_b200
+    b = egc_b200.collate(graphs, device=dev)
+    h = b.x
+    for layer in model:
+        h = torch.relu(layer(h, b.edge_index))
+    return egc_b200.global_mean_pool(h, b).pow(2).sum(1).mean()
+
+
+def _dp_worker(rank, world, port, ret):
+    from egc_b200.dist import GradientAllReduce
+    from oracle import batching as OB
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        graphs = OB.cifar_like_graphs(24, seed=3)
+        ref = _dp_model(dev)
+        _dp_loss(ref, graphs, dev).backward()
+        mine = graphs[:9] if rank == 0 else graphs[9:]
+        model = _dp_model(dev)
+        _dp_loss(model, mine, dev).backward()
+        GradientAllReduce(model.parameters())(weight=len(mine) / len(graphs))
+        torch.cuda.synchronize()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert rel_err(p.grad, q.grad) < 2e-5
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_gradients_match_single_gpu_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
