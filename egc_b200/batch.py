@@ -36,9 +36,13 @@ def _require_cuda(name: str, t: Tensor) -> None:
         raise RuntimeError(f"egc_b200: `{name}` must be a CUDA tensor - this library has no CPU path")
 
 
-def collate_arrays(edge_local: Tensor, edge_ptr: Tensor, node_ptr: Tensor) -> Tuple[Tensor, Tensor]:
+def collate_arrays(edge_local: Tensor, edge_ptr: Tensor, node_ptr: Tensor, num_nodes: Optional[int] = None,
+                   validate: bool = True) -> Tuple[Tensor, Tensor]:
     """(edge_index [2, E] int64 with global ids, batch [N] int64) from the concatenated graph-local edge lists.
-    edge_local [2, E] int64; edge_ptr / node_ptr [G + 1] int32 exclusive prefix sums of per-graph edge / node counts."""
+    edge_local [2, E] int64; edge_ptr / node_ptr [G + 1] int32 exclusive prefix sums of per-graph edge / node counts.
+    `num_nodes` (= node_ptr[-1], known to a caller that built the offsets on the host) and `validate=False` (skip the
+    check that every local id lies inside its graph) each save one device-to-host read, i.e. one pipeline drain per
+    batch; PyG's collation does not validate ids either."""
     lib = _lib.load()
     for n, t in (("edge_local", edge_local), ("edge_ptr", edge_ptr), ("node_ptr", node_ptr)):
         _require_cuda(n, t)
@@ -51,10 +55,13 @@ def collate_arrays(edge_local: Tensor, edge_ptr: Tensor, node_ptr: Tensor) -> Tu
         raise ValueError("node_ptr must hold at least one element")
     edge_local = edge_local.contiguous()
     e = int(edge_local.size(1))
-    ends = torch.stack([node_ptr[-1], edge_ptr[-1]]).cpu()           # one host read: N and the edge count check
-    n = int(ends[0])
-    if int(ends[1]) != e:
-        raise ValueError(f"edge_ptr[-1] = {int(ends[1])} does not match the number of edges {e}")
+    if num_nodes is None:
+        ends = torch.stack([node_ptr[-1], edge_ptr[-1]]).cpu()       # one host read: N and the edge count check
+        n = int(ends[0])
+        if int(ends[1]) != e:
+            raise ValueError(f"edge_ptr[-1] = {int(ends[1])} does not match the number of edges {e}")
+    else:
+        n = int(num_nodes)
     dev = edge_local.device
     out = torch.empty((2, e), dtype=torch.int64, device=dev)
     batch = torch.empty(n, dtype=torch.int64, device=dev)
@@ -63,7 +70,7 @@ def collate_arrays(edge_local: Tensor, edge_ptr: Tensor, node_ptr: Tensor) -> Tu
         check(lib.egc_collate_edges(ptr(edge_local[0]), ptr(edge_local[1]), ptr(edge_ptr.contiguous()),
                                     ptr(node_ptr.contiguous()), g, e, n, ptr(out[0]), ptr(out[1]), ptr(batch), ptr(flags),
                                     _stream()), "egc_collate_edges")
-    if int(flags.item()) & 1:
+    if validate and int(flags.item()) & 1:
         raise ValueError("collate: an edge refers to a node id outside its graph")
     return out, batch
 
@@ -83,7 +90,7 @@ def collate(graphs: Sequence[Tuple[Optional[Tensor], Tensor, int]], device=None)
     x = None
     if graphs[0][0] is not None:
         x = torch.cat([xg for xg, _, _ in graphs], dim=0).to(device, non_blocking=True)
-    edge_index, batch = collate_arrays(edge_local, ptrs[1], ptrs[0])
+    edge_index, batch = collate_arrays(edge_local, ptrs[1], ptrs[0], num_nodes=int(counts[:, 0].sum()))
     return Batch(x, edge_index, batch, ptrs[0], len(graphs))
 
 

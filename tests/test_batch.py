@@ -152,7 +152,7 @@ def test_zinc_shaped_stack_with_pooling_matches_oracle():
         assert rel_err(a, c) < 1e-5
 
 
-def _stack_case(graphs, f_in, hidden, aggrs, heads, layers, readout, seed):
+def _stack_case(graphs, f_in, hidden, aggrs, heads, layers, readout, seed, gemm="fp32"):
     """L x (EGConv -> ReLU) then a graph readout, CUDA library vs the fp64 oracle on one collated batch
     (the model bodies of ref experiments/zinc/models.py:56-73 and experiments/cifar/models.py:56-75)."""
     import egc_b200
@@ -166,15 +166,22 @@ def _stack_case(graphs, f_in, hidden, aggrs, heads, layers, readout, seed):
     for o in oracles:
         c = egc_b200.EGConv(o.in_channels, o.out_channels, aggrs=aggrs, num_heads=heads, num_bases=4)
         c.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+        c.gemm_algo = egc_b200.GEMM_FP32_SIMT if gemm == "fp32" else egc_b200.GEMM_AUTO
         convs.append(c.cuda())
     x, go = torch.randn(n, f_in), torch.randn(g, hidden)
-    xo = x.double().requires_grad_(True)
-    h = xo
-    for o in oracles:
-        h = torch.relu(o(h, eio))
-    ro = OB.global_pool(h, bo, g, readout)
-    po_list = [p for o in oracles for p in o.parameters()]
-    gro = torch.autograd.grad(ro, [xo] + po_list, go.double())
+
+    def run_oracle(dtype):
+        ms = [R.EGConvOracle(o.in_channels, o.out_channels, aggrs=aggrs, num_heads=heads, num_bases=4).to(dtype) for o in oracles]
+        for m, o in zip(ms, oracles):
+            m.load_state_dict({k: v.to(dtype) for k, v in o.state_dict().items()})
+        xo = x.to(dtype).requires_grad_(True)
+        h = xo
+        for m in ms:
+            h = torch.relu(m(h, eio))
+        r = OB.global_pool(h, bo, g, readout)
+        return [r] + list(torch.autograd.grad(r, [xo] + [p for m in ms for p in m.parameters()], go.to(dtype)))
+
+    ref64, ref32 = run_oracle(torch.float64), run_oracle(torch.float32)
     b = egc_b200.collate(graphs, device="cuda")
     xc = x.cuda().requires_grad_(True)
     h = xc
@@ -184,19 +191,27 @@ def _stack_case(graphs, f_in, hidden, aggrs, heads, layers, readout, seed):
     rc = pool(h, b)
     pc_list = [p for c in convs for p in c.parameters()]
     grc = torch.autograd.grad(rc, [xc] + pc_list, go.cuda())
-    # four stacked fp32 layers: the forward error compounds, the bar per layer stays 1e-5 (tests/test_gpu_parity.py)
-    assert rel_err(rc, ro) < 4e-5
-    for a, c in zip(grc, gro):
-        assert rel_err(a, c) < 4e-5
+    # bar with exact-fp32 projections: 1e-5 per layer (four stacked fp32 layers compound it), or 4x the error the
+    # reference's own fp32 arithmetic shows on the same input where that is larger (tests/test_gpu_parity.py).
+    # Stated tolerance of the default tensor-core path (tcgen05 3xTF32, ~2e-6 per projection instead of fp32's 1e-7):
+    # 5e-4 on this stack - std's var = E[x^2] - E[x]^2 cancels on the smooth features of deeper kNN layers and
+    # amplifies the projection error ~100x (measured 1.4e-4); sum-only stacks stay at the fp32 bar.
+    for a, r64, r32 in zip([rc] + list(grc), ref64, ref32):
+        bar = max(4e-5, 4.0 * rel_err(r32, r64))
+        if gemm != "fp32" and any(k in aggrs for k in ("std", "var")):
+            bar = max(bar, 5e-4)
+        assert rel_err(a, r64) < bar
 
 
 @pytest.mark.gpu
-def test_zinc_shaped_egc_s_four_layers():
+@pytest.mark.parametrize("gemm", ["fp32", "3xtf32"])
+def test_zinc_shaped_egc_s_four_layers(gemm):
     """BASELINE config 1: EGC-S (sum aggregator, 8 heads, 4 bases, hidden 104, 4 layers), 128 molecule-like graphs."""
-    _stack_case(OB.zinc_like_graphs(128, 5), 104, 104, ["sum"], 8, 4, "mean", 0)
+    _stack_case(OB.zinc_like_graphs(128, 5), 104, 104, ["sum"], 8, 4, "mean", 0, gemm)
 
 
 @pytest.mark.gpu
-def test_cifar_shaped_egc_m_four_layers():
+@pytest.mark.parametrize("gemm", ["fp32", "3xtf32"])
+def test_cifar_shaped_egc_m_four_layers(gemm):
     """BASELINE config 5: EGC-M (symnorm + max + std, 4 heads, 4 bases, hidden 128, 4 layers), kNN superpixel graphs."""
-    _stack_case(OB.cifar_like_graphs(32, 5), 128, 128, ["symnorm", "max", "std"], 4, 4, "mean", 1)
+    _stack_case(OB.cifar_like_graphs(32, 5), 128, 128, ["symnorm", "max", "std"], 4, 4, "mean", 1, gemm)

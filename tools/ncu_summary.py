@@ -17,7 +17,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "smsp__inst_executed.sum"]
 # kernel-name fragment -> key used by bench.py's byte model
-KEYS = {"k_aggregate_fast": "k_aggregate_fwd", "k_aggregate<": "k_aggregate_fwd", "k_combine_bwd": "k_combine_bwd",
+KEYS = {"k_aggregate_rows": "k_aggregate_fwd", "k_scatter_cols": "k_scatter_bwd", "k_aggregate_fast": "k_aggregate_fwd", "k_aggregate<": "k_aggregate_fwd", "k_combine_bwd": "k_combine_bwd",
         "k_route_minmax": "k_route_minmax", "k_scatter_bwd": "k_scatter_bwd", "k_scatter_slab": "k_scatter_bwd",
         "k_project_tc": "k_project_tc", "k_wgrad_tc": "k_wgrad_tc"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
