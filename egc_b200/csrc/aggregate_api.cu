@@ -673,7 +673,8 @@ template <int TSMASK, int G>
 __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 : 3) k_scatter_cols(const __grid_constant__ ScatterParams p, int* __restrict__ task_counter) {
   __shared__ int s_idx_all[kAggWarps][kColWindow];
   __shared__ float s_val_all[kAggWarps][(TSMASK & 1) ? kColWindow : 1];
-  constexpr int NG = 32 / G, U = kScatterUnroll, STEP = U * NG;
+  // entries in flight per lane group: single-stream instances have the registers for 8
+  constexpr int NG = 32 / G, U = (TSMASK & (TSMASK - 1)) == 0 ? 2 * kScatterUnroll : kScatterUnroll, STEP = U * NG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* s_idx = s_idx_all[warp];
   float* s_val = s_val_all[warp];

@@ -18,7 +18,16 @@
 
 namespace egc {
 
-constexpr int kRowsPerTask = 8;
+#ifndef EGC_ROWS_PER_TASK
+#define EGC_ROWS_PER_TASK 8
+#endif
+#ifndef EGC_ROWS_UNROLL
+#define EGC_ROWS_UNROLL 6        // gathers in flight per lane: 6 x 3 CTAs measured best (4: 0.271 ms, 6: 0.257, 8 x 2 CTAs: 0.267; arxiv shape)
+#endif
+#ifndef EGC_ROWS_CTAS
+#define EGC_ROWS_CTAS 3
+#endif
+constexpr int kRowsPerTask = EGC_ROWS_PER_TASK;
 constexpr int kWindow = 384;              // nnz staged at a time; >= EGC_CHUNK_EDGES so that every normal row fits
 static_assert(kWindow >= EGC_CHUNK_EDGES, "a normal row must fit the staging window");
 
@@ -33,12 +42,12 @@ struct RowsSmem {                          // per-warp layout in floats, from A 
 };
 
 template <class Cfg, bool ARG>
-__global__ void __launch_bounds__(kAggThreads, 3) k_aggregate_rows(const __grid_constant__ AggParams p, int* __restrict__ task_counter) {
+__global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(const __grid_constant__ AggParams p, int* __restrict__ task_counter) {
   extern __shared__ __align__(16) float smem_all[];
   constexpr int MASK = Cfg::MASK, G = Cfg::G;
   using GC = Get<Cfg>;
   constexpr int NG = 32 / G;
-  constexpr int U = kFastUnroll;
+  constexpr int U = EGC_ROWS_UNROLL;
   constexpr int STEP = U * NG;                                  // nnz consumed by one batch of the warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RowsSmem lay(GC::A(p) * GC::BD(p), GC::HAB(p));
@@ -349,7 +358,7 @@ int launch_rows_one(const AggParams& p, int* task_counter, cudaStream_t st) {
   }
   const int n_blocks = ceil_div(p.n_rows, kRowsPerTask);
   const int64_t warps_wanted = std::max<int64_t>(n_blocks, p.n_chunks);
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(warps_wanted, kAggWarps), static_cast<int64_t>(sm_count()) * 3));
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div(warps_wanted, kAggWarps), static_cast<int64_t>(sm_count()) * EGC_ROWS_CTAS));
   {
     LaunchScope egc_ls_("k_aggregate_fwd", st);
     kern<<<grid, kAggThreads, smem_bytes, st>>>(p, task_counter);
