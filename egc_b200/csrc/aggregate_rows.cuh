@@ -159,11 +159,24 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
         const float* ad = s_agg + epi_d[it];
         if (EV == 4) {
           float r[4] = {0.f, 0.f, 0.f, 0.f};
+          if ((AB & 3) == 0) {                                 // weights of one head: whole 128-bit pieces (same order of FMAs)
+#pragma unroll 3
+            for (int ab = 0; ab < AB; ab += 4) {
+              const float4 wv4 = *reinterpret_cast<const float4*>(wh + ab);
+              const float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4*>(ad + (ab + q) * D);
+                r[0] = fmaf(wv[q], a.x, r[0]); r[1] = fmaf(wv[q], a.y, r[1]); r[2] = fmaf(wv[q], a.z, r[2]); r[3] = fmaf(wv[q], a.w, r[3]);
+              }
+            }
+          } else {
 #pragma unroll 12
-          for (int ab = 0; ab < AB; ++ab) {
-            const float wv = wh[ab];
-            const float4 a = *reinterpret_cast<const float4*>(ad + ab * D);
-            r[0] = fmaf(wv, a.x, r[0]); r[1] = fmaf(wv, a.y, r[1]); r[2] = fmaf(wv, a.z, r[2]); r[3] = fmaf(wv, a.w, r[3]);
+            for (int ab = 0; ab < AB; ++ab) {
+              const float wv = wh[ab];
+              const float4 a = *reinterpret_cast<const float4*>(ad + ab * D);
+              r[0] = fmaf(wv, a.x, r[0]); r[1] = fmaf(wv, a.y, r[1]); r[2] = fmaf(wv, a.z, r[2]); r[3] = fmaf(wv, a.w, r[3]);
+            }
           }
           if (p.bias != nullptr) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + o));

@@ -337,6 +337,49 @@ def test_layer_vs_oracle(cfg, kind):
     assert_close(res)
 
 
+def _degree_pattern_graph(n, degrees, seed, symmetric):
+    """Row i gets degrees[i % len(degrees)] distinct sources: exercises the row-/column-block kernels' window
+    splits (8 consecutive rows > 384 nnz), rows of exactly 256 / 257 nnz (chunk threshold), runs of empty rows."""
+    gen = torch.Generator().manual_seed(seed)
+    src, dst = [], []
+    for i in range(n):
+        d = degrees[i % len(degrees)]
+        if d:
+            src.append(torch.randperm(n, generator=gen)[:d])
+            dst.append(torch.full((d,), i, dtype=torch.long))
+    ei = torch.stack([torch.cat(src), torch.cat(dst)])
+    if symmetric:                                    # the CSC pass then sees the same column lengths
+        ei = torch.cat([ei, ei.flip(0)], 1)
+    return ei
+
+
+BLOCK_CONFIGS = [  # f_in, f_out, aggrs, heads, bases: a specialised shape, a dynamic G = 32 shape, a G = 16 shape
+    (128, 128, ["symnorm", "max", "std"], 4, 4),
+    (64, 128, ["sum", "mean", "min", "var"], 4, 4),
+    (128, 128, ["symnorm"], 8, 4),
+    (64, 48, ["max", "mean"], 4, 3),                 # B*D = 36
+]
+
+
+@pytest.mark.parametrize("cfg", BLOCK_CONFIGS, ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}-h{c[3]}b{c[4]}")
+@pytest.mark.parametrize("pattern", ["windows", "threshold", "empty_runs"])
+@pytest.mark.parametrize("loops", [True, False])
+def test_block_kernels_on_degree_patterns(cfg, pattern, loops):
+    f_in, f_out, aggrs, h, b = cfg
+    degrees = {"windows": [200, 1, 250, 0, 130, 256, 7, 90, 3, 255, 255, 255],
+               "threshold": [256, 257, 255, 300, 0, 256, 2, 513, 1],
+               "empty_runs": [0] * 37 + [5, 0, 0, 300, 0, 1] + [0] * 21}[pattern]
+    n = 1203                                          # not a multiple of the block size
+    ei = _degree_pattern_graph(n, degrees, seed=3, symmetric=pattern == "windows")
+    o, c = oracle_and_cuda(f_in, f_out, aggrs, h, b, loops=loops, seed=5)
+    torch.manual_seed(6)
+    x, go = torch.randn(n, f_in), torch.randn(n, f_out)
+    assert_close(run_both(o, c, x, ei, ei.to(DEV), go))
+    rowptr, col, _ = to_adj_csr(ei, n)
+    adj = egc_b200.SparseTensor(rowptr=rowptr.to(DEV), col=col.to(DEV), sparse_sizes=(n, n), is_sorted=True)
+    assert_close(run_both(o, c, x, (rowptr, col, None), adj, go))
+
+
 SLAB_CONFIGS = [  # f_in, f_out, aggrs, heads, bases  (B*D a multiple of the slab width)
     (128, 128, ["symnorm", "max", "std"], 4, 4),          # three target-side streams + routed max
     (128, 128, ["symnorm"], 8, 4),                        # one stream, B*D = 64
