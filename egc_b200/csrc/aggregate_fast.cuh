@@ -114,12 +114,15 @@ struct StaticCfg {
 
 // the specialised layer shapes (heads, bases, head dim, aggregators in constructor order).  BASELINE.json
 // configs 2 / 3 / 5 are the first, config 4 the second; the others are the reference's EGC-S / EGC-M variants
-// at hidden 128 (ref experiments/*/configs.py).  Every other layer runs the DynCfg kernels.
+// at hidden 128 (ref experiments/*/configs.py); 4 / 5 are REGConv's relation and root terms (ref rmag/models.py).
+// Every other layer runs the DynCfg kernels.
 #define EGC_STATIC_CFGS(X)                                               \
   X(0, 4, 4, 32, EGC_AGGR_SYMNORM, EGC_AGGR_MAX, EGC_AGGR_STD)           \
   X(1, 8, 4, 16, EGC_AGGR_SYMNORM)                                       \
   X(2, 4, 4, 32, EGC_AGGR_SYMNORM)                                       \
-  X(3, 4, 4, 32, EGC_AGGR_SYMNORM, EGC_AGGR_MAX, EGC_AGGR_MEAN)
+  X(3, 4, 4, 32, EGC_AGGR_SYMNORM, EGC_AGGR_MAX, EGC_AGGR_MEAN)          \
+  X(4, 8, 4, 16, EGC_AGGR_MEAN, EGC_AGGR_MAX)                            \
+  X(5, 8, 4, 16, EGC_AGGR_SUM)
 
 inline int static_cfg_index(const egc_layer_desc& d) {
 #define X(I, ...) if (StaticCfg<__VA_ARGS__>::matches(d)) return I;
