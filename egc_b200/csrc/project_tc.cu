@@ -8,7 +8,10 @@
 //
 // The op is an HBM stream (AI ~ 37 flop/B), so the kernel is organised around bytes in flight:
 // one persistent CTA per SM, 11 warps:
-//   warps 9-10  copy      cp.async (16 B, L2-only) of raw A chunks into a deep shared-memory ring, already in
+//   warps 9-10  copy      default: one lane of warp 9 issues TMA tensor copies - four [128 rows x 16 B] boxes per 8 KB
+//                         chunk, each landing as 16 stacked core matrices, completion by mbarrier transaction bytes.
+//                         Fallback (no tensor-map encoder / unaligned rows):
+//                         cp.async (16 B, L2-only) of raw A chunks into a deep shared-memory ring, already in
 //                         the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices);
 //                         completion is signalled on an mbarrier (cp.async.mbarrier.arrive.noinc), so up to
 //                         `raw_stages` x 8 KB per SM are in flight without holding registers
@@ -20,7 +23,9 @@
 // (CTA c serves group c % n_split); the groups walk the row tiles in lockstep, so the second read of an A
 // tile is an L2 hit.  The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile t
 // overlaps the main loop of tile t+1.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -59,6 +64,7 @@ struct TcParams {
   int raw_stages;
   int n_terms;                             // 3: 3xTF32, 1: TF32
   int num_tiles;
+  int use_tma;                             // A chunks arrive by TMA tensor copies (4 x [128 rows x 16 B] boxes per chunk) instead of LDGSTS
   int ablate;                              // diagnostics (EGC_TC_ABLATE, results become wrong): 1 no lo conversion, 2 no epilogue,
                                            // 4 no MMA, 8 no A copies, 16 no global stores  (tools/gemm_ablate.sh)
 };
@@ -66,7 +72,8 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tm_a1,
+                                                               const __grid_constant__ CUtensorMap tm_a2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * R + kLoStages + 2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), 32); mbar_init(raw_empty(s), 1); mbar_init(conv_full(s), 32); }
+    for (int s = 0; s < R; ++s) { mbar_init(raw_full(s), p.use_tma ? 1 : 32); mbar_init(raw_empty(s), 1); mbar_init(conv_full(s), 32); }
     for (int s = 0; s < kLoStages; ++s) mbar_init(lo_empty(s), 1);
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
     fence_barrier_init();
@@ -148,7 +155,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   const int total_chunks = my_tiles * n_chunks;
   const uint32_t raw_addr = smem_u32(raw_ring), lo_addr = smem_u32(lo_ring);
 
-  if (warp >= 9) {
+  if (warp >= 9 && p.use_tma) {
+    // ================= TMA producer: one lane, four [128 rows x 16 B] boxes per chunk =================
+    // Each box is one 16-byte K piece of the 128 rows of the tile, which lands as 16 stacked core matrices - the
+    // canonical no-swizzle K-major layout the MMA descriptors expect.  Rows past M and K pieces past the operand's
+    // width are zero-filled by the TMA unit.
+    if (warp == 9 && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0, j = 0;
+      for (int c = 0; c < total_chunks; ++c) {
+        const int row_base = (first_tile + t * tile_step) * kTileM;
+        mbar_wait(raw_empty(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(raw_full(stage), kChunkBytes);
+        const uint32_t dst = raw_addr + stage * kChunkBytes;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int k = j * kChunkK + 4 * c4;
+          const bool second = k >= p.k1 && p.k2 > 0;
+          tma_load_2d(dst + c4 * (kTileM * 16), second ? &tm_a2 : &tm_a1, second ? k - p.k1 : k, row_base, raw_full(stage));
+        }
+        if (++stage == R) { stage = 0; phase ^= 1u; }
+        if (++j == n_chunks) { j = 0; ++t; }
+      }
+    }
+  } else if (warp >= 9) {
     // ================= copy producers: each warp owns every other chunk =================
     const int pw = warp - 9;
     const int c4 = lane & 3, r0 = lane >> 2;                   // 16-byte K piece, first row (rows r0 + 8 i)
@@ -365,6 +396,32 @@ bool project_tc_supported(int n, int f_in, int bd, int hab) {
   return tc_plan(f_in, bd + hab, a) && tc_plan(bd + hab, f_in, b);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// [M rows x k floats] row-major operand, boxes of 128 rows x 4 floats
+static bool make_a_map(CUtensorMap* m, const float* base, int k, int64_t ld, int M) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr || base == nullptr || k <= 0) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(M)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {4, static_cast<cuuint32_t>(kTileM)};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_tc(TcParams& p, cudaStream_t st) {
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
   TcPlan plan;
@@ -380,11 +437,21 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
     EGC_CUDA(cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
+  // TMA feed of the A operand (default; EGC_TC_NO_TMA=1 keeps the cp.async producers): needs the driver's tensor-map
+  // encoder and 16-byte aligned rows.  Measured on B200: arxiv shape 0.106 -> 0.088 ms, mag shape 0.217 -> 0.159 ms.
+  alignas(64) CUtensorMap tm1, tm2;
+  memset(&tm1, 0, sizeof(tm1));
+  memset(&tm2, 0, sizeof(tm2));
+  static const bool want_tma = getenv("EGC_TC_NO_TMA") == nullptr;
+  p.use_tma = 0;
+  if (want_tma && p.k1 % 4 == 0 && p.lda1 % 4 == 0 && (p.k2 == 0 || (p.k2 % 4 == 0 && p.lda2 % 4 == 0)) &&
+      make_a_map(&tm1, p.a1, p.k1, p.lda1, p.M) && (p.k2 == 0 || make_a_map(&tm2, p.a2, p.k2, p.lda2, p.M)))
+    p.use_tma = 1;
   const int per_group = std::max(1, std::min(p.num_tiles, sm_count() / p.n_split));
   const int grid = per_group * p.n_split;
   {
     LaunchScope ls("k_project_tc", st);
-    k_project_tc<<<grid, kTcThreads, plan.smem, st>>>(p);
+    k_project_tc<<<grid, kTcThreads, plan.smem, st>>>(p, tm1, tm2);
   }
   EGC_LAUNCH_CHECK("k_project_tc");
   return EGC_OK;

@@ -106,6 +106,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gmem_src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
+// TMA tensor copy (2-D tiled map): box at element coordinates (c0, c1) -> this CTA's shared memory; out-of-bounds
+// elements are zero-filled; completion is reported to `bar` as transaction bytes
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tensor_map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t tx_bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
 }
