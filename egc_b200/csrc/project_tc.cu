@@ -64,6 +64,7 @@ struct TcParams {
   int raw_stages;
   int n_terms;                             // 3: 3xTF32, 1: TF32
   int num_tiles;
+  int use_tma_store;                       // epilogue writes C through TMA tensor stores (128B-swizzled 32 x 32 staging tiles)
   int use_tma;                             // A chunks arrive by TMA tensor copies (4 x [128 rows x 16 B] boxes per chunk) instead of LDGSTS
   int ablate;                              // diagnostics (EGC_TC_ABLATE, results become wrong): 1 no lo conversion, 2 no epilogue,
                                            // 4 no MMA, 8 no A copies, 16 no global stores  (tools/gemm_ablate.sh)
@@ -73,7 +74,8 @@ struct TcParams {
 // kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tm_a1,
-                                                               const __grid_constant__ CUtensorMap tm_a2) {
+                                                               const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_c1,
+                                                               const __grid_constant__ CUtensorMap tm_c2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
@@ -318,6 +320,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
           if (width > 16) tmem_ld16(taddr + 16u, rb);
           tmem_ld_wait();
         }
+        if (p.use_tma_store) {
+          // ---- TMA store: bias / sigmoid in registers, row `lane` into a 128B-swizzled [32 rows x 128 B] tile
+          // (16-byte piece q of row r sits at piece q ^ (r & 7): conflict-free quarter-warp stores), one tensor store
+          const int colg = n_begin + col0;                     // first output column of the block (multiple of 32)
+          const bool to_c1 = colg < p.n1;
+          const int cbase = to_c1 ? colg : colg - p.n1;
+          const uint32_t tile = smem_u32(epi_stage) + warp * 4096;
+          if (lane == 0) bulk_wait_read_all();                 // the previous block's tile has been read by the TMA unit
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                   __uint_as_float(r[4 * q + 3]));
+            if (4 * q >= width) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!to_c1) {
+              if (p.bias2 != nullptr && cbase + 4 * q < p.n2) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + cbase + 4 * q));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              if (p.sigmoid2) {
+                v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y));
+                v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
+              }
+            }
+            sts128(tile + lane * 128 + ((q ^ (lane & 7)) << 4), v);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && !(p.ablate & 16)) {
+            tma_store_2d(to_c1 ? &tm_c1 : &tm_c2, tile, cbase, static_cast<int>(row0));
+            bulk_commit();
+          }
+          continue;
+        }
         __syncwarp();                                          // previous block fully read back
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -355,6 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
+    if (p.use_tma_store && lane == 0) bulk_wait_all();       // every tensor store has left shared memory and completed
   }
 
   tc_fence_before();
@@ -410,6 +447,17 @@ static EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
+// [M rows x n floats] row-major output, 128B-swizzled boxes of 32 rows x 32 floats
+static bool make_c_map(CUtensorMap* m, const float* base, int n, int64_t ld, int M) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr || base == nullptr || n <= 0) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(M)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // [M rows x k floats] row-major operand, boxes of 128 rows x 4 floats
 static bool make_a_map(CUtensorMap* m, const float* base, int k, int64_t ld, int M) {
   EncodeTiledFn fn = encode_tiled();
@@ -447,11 +495,20 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   if (want_tma && p.k1 % 4 == 0 && p.lda1 % 4 == 0 && (p.k2 == 0 || (p.k2 % 4 == 0 && p.lda2 % 4 == 0)) &&
       make_a_map(&tm1, p.a1, p.k1, p.lda1, p.M) && (p.k2 == 0 || make_a_map(&tm2, p.a2, p.k2, p.lda2, p.M)))
     p.use_tma = 1;
+  // TMA tensor stores of the output (EGC_TC_TMA_STORE=1; experimental): column blocks of 32 must not straddle c1 | c2
+  alignas(64) CUtensorMap tc1, tc2;
+  memset(&tc1, 0, sizeof(tc1));
+  memset(&tc2, 0, sizeof(tc2));
+  static const bool want_tma_store = getenv("EGC_TC_TMA_STORE") != nullptr;
+  p.use_tma_store = 0;
+  if (want_tma_store && p.n1 % 32 == 0 && p.cols_per_group % 32 == 0 && p.ldc1 % 4 == 0 && (p.n2 == 0 || (p.ldc2 % 4 == 0 && p.n2 % 4 == 0)) &&
+      make_c_map(&tc1, p.c1, p.n1, p.ldc1, p.M) && (p.n2 == 0 || make_c_map(&tc2, p.c2, p.n2, p.ldc2, p.M)))
+    p.use_tma_store = 1;
   const int per_group = std::max(1, std::min(p.num_tiles, sm_count() / p.n_split));
   const int grid = per_group * p.n_split;
   {
     LaunchScope ls("k_project_tc", st);
-    k_project_tc<<<grid, kTcThreads, plan.smem, st>>>(p, tm1, tm2);
+    k_project_tc<<<grid, kTcThreads, plan.smem, st>>>(p, tm1, tm2, tc1, tc2);
   }
   EGC_LAUNCH_CHECK("k_project_tc");
   return EGC_OK;

@@ -112,6 +112,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tenso
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_dst), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// TMA tensor store (2-D tiled map): shared-memory tile -> box at element coordinates (c0, c1); elements outside the
+// tensor are dropped.  Bulk async-group completion: commit, then wait (".read": the tile may be overwritten).
+__device__ __forceinline__ void tma_store_2d(const void* tensor_map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tensor_map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t tx_bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
 }
