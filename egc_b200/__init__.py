@@ -6,6 +6,7 @@ Public surface (mirrors the reference operator API, /root/reference/experiments/
     SparseTensor      minimal `torch_sparse.SparseTensor` container accepted by EGConv.forward
     GraphStructure    prepared device graph (CSR / CSC / symnorm weights / long-row plan)
     egconv            functional form on a prepared graph
+    GraphedStep       capture a (multi-layer) forward + backward step into one CUDA graph and replay it
     REGConv           heterogeneous layer of the reference's rmag experiments on the same kernels
     collate / Batch / global_{add,mean,max}_pool   device-side mini-batch collation and graph readout
     build / load      compile / load libegc_b200.so (C ABI in include/egc_b200.h)
@@ -15,6 +16,7 @@ from ._lib import (BWD_DETERMINISTIC, GEMM_3XTF32, GEMM_AUTO, GEMM_FP32_SIMT, GE
 from .batch import Batch, collate, collate_arrays, global_add_pool, global_max_pool, global_mean_pool, segment_ptr  # noqa: F401
 from .compat import EfficientGraphConv, convert_paper_state_dict, paper_to_egconv_perm  # noqa: F401
 from .conv import EGConv  # noqa: F401
+from .dist import GradientAllReduce, GraphedStep  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
 from .hetero import REGConv  # noqa: F401
 from .graph import GraphStructure, SparseTensor  # noqa: F401

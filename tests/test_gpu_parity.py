@@ -470,3 +470,48 @@ def test_caching_reset_and_no_grad():
     nc = egc_b200.EGConv(16, 32, aggrs=["symnorm"], num_heads=4, cached=False).to(DEV)
     nc(x, ei)
     assert nc._cached_edge_index is None
+
+
+def test_three_layer_full_graph_step_replays_from_a_cuda_graph():
+    """The reference's full-graph model body (mag/models.py:61-69: conv -> ReLU per layer, log_softmax + nll_loss)
+    with cached structure: forward + backward captured once into ONE CUDA graph, replayed on new inputs."""
+    n, classes = 5000, 40
+    ei = random_graph(n, 60000, seed=12, hub=900)
+    torch.manual_seed(2)
+    convs = torch.nn.ModuleList([egc_b200.EGConv(64, 128, aggrs=["symnorm", "max", "std"], num_heads=4, num_bases=4, cached=True),
+                                 egc_b200.EGConv(128, 128, aggrs=["symnorm", "max", "std"], num_heads=4, num_bases=4, cached=True),
+                                 egc_b200.EGConv(128, classes, aggrs=["symnorm"], num_heads=8, num_bases=4, cached=True)]).to(DEV)
+    params = list(convs.parameters())
+    eid = ei.to(DEV)
+    x_static = torch.randn(n, 64, device=DEV, requires_grad=True)
+    y_static = torch.randint(0, classes, (n,), device=DEV)
+
+    def step(x=None, y=None):
+        x = x_static if x is None else x
+        y = y_static if y is None else y
+        h = x
+        for i, c in enumerate(convs):
+            h = c(h, eid)
+            if i + 1 < len(convs):
+                h = torch.relu(h)
+        loss = torch.nn.functional.nll_loss(torch.log_softmax(h, dim=-1), y)
+        return (loss,) + torch.autograd.grad(loss, [x] + params)
+
+    before = egc_b200._lib.launch_count()
+    step()
+    per_step = egc_b200._lib.launch_count() - before
+    graphed = egc_b200.GraphedStep(step, warmup=2)
+    for it in range(3):
+        gen = torch.Generator().manual_seed(70 + it)
+        xf, yf = torch.randn(n, 64, generator=gen), torch.randint(0, classes, (n,), generator=gen)
+        with torch.no_grad():
+            x_static.copy_(xf.to(DEV))
+            y_static.copy_(yf.to(DEV))
+        counted = egc_b200._lib.launch_count()
+        res = graphed.replay()
+        torch.cuda.synchronize()
+        assert egc_b200._lib.launch_count() == counted          # no eager launches: the step is one graph launch
+        ref = step(xf.to(DEV).requires_grad_(True), yf.to(DEV))
+        for a, b in zip(res, ref):
+            assert rel_err(a, b.double().cpu()) < 1e-5
+    assert per_step >= 3 * 8                                    # sanity: every layer contributes its kernels
