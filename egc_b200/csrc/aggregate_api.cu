@@ -1213,7 +1213,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   // row-block kernel: whole-graph calls of the specialised shapes (EGC_FWD_WARP_PER_ROW=1 keeps the warp-per-row kernel)
   static const bool legacy_rows = getenv("EGC_FWD_WARP_PER_ROW") != nullptr;
   // needs the window + 8 rows of weights per warp in shared memory (3 CTAs per SM)
-  const bool row_blocks = fast && row_subset == nullptr && !legacy_rows && rows_kernel_smem_bytes(p) <= 72 * 1024;
+  const bool row_blocks = fast && !legacy_rows && rows_kernel_smem_bytes(p) <= 72 * 1024;
   const size_t counter_off = align_up(static_cast<size_t>(p.n_long) * sizeof(int), 256);   // inside the trailing 256 B
   int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(p.long_counter) + counter_off);
   if (row_blocks) EGC_CUDA(cudaMemsetAsync(p.long_counter, 0, counter_off + sizeof(int), st));

@@ -1,5 +1,5 @@
-// Row-block forward aggregation + per-head combination (sm_100a): the successor of k_aggregate_fast for whole-graph
-// calls (no row subset).  Same task model for long rows (chunk tasks, last chunk warp merges), same arithmetic and
+// Row-block forward aggregation + per-head combination (sm_100a): the successor of k_aggregate_fast, for whole-graph
+// calls and for row subsets (interior / boundary rows of a partitioned graph).  Same task model for long rows (chunk tasks, last chunk warp merges), same arithmetic and
 // the same bits; what changes is how a warp finds and feeds its rows:
 //
 //   * a task is a block of kRowsPerTask CONSECUTIVE rows handed out by an atomic counter: the row pointers of the
@@ -262,53 +262,89 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
     }
   }
 
-  // =========================== phase 1: blocks of consecutive rows (dynamic) ===========================
-  const int n_blocks = (p.n_rows + kRowsPerTask - 1) / kRowsPerTask;
+  // =========================== phase 1: blocks of rows (dynamic) ===========================
+  // Whole-graph calls: a block is kRowsPerTask CONSECUTIVE rows (one contiguous nnz range).  Row-subset calls (the
+  // interior / boundary rows of a partitioned graph): kRowsPerTask consecutive entries of row_map, each row's range
+  // staged on its own.  Lane l < nrows holds row l of the block: its id, [rp, rpn) and its offset in the window.
+  const bool subset = p.row_map != nullptr;
+  const int n_blocks = (p.n_row_tasks + kRowsPerTask - 1) / kRowsPerTask;
   int task = 0;
   if (lane == 0) task = atomicAdd(task_counter, 1);
   task = __shfl_sync(kFull, task, 0);
   while (task < n_blocks) {
     const int r0 = task * kRowsPerTask;
-    const int nrows = min(kRowsPerTask, p.n_rows - r0);
-    const int rp = __ldg(p.rowptr + r0 + min(lane, nrows));    // lanes 0..nrows hold the block's row pointers
+    const int nrows = min(kRowsPerTask, p.n_row_tasks - r0);
+    int row_id, rp, rpn;
+    if (subset) {
+      row_id = __ldg(p.row_map + r0 + min(lane, nrows - 1));
+      rp = __ldg(p.rowptr + row_id);
+      rpn = __ldg(p.rowptr + row_id + 1);
+    } else {
+      row_id = r0 + lane;
+      rp = __ldg(p.rowptr + r0 + min(lane, nrows));            // lanes 0..nrows hold the block's row pointers
+      rpn = __shfl_down_sync(kFull, rp, 1);
+    }
     int next_task = 0;
     if (lane == 0) next_task = atomicAdd(task_counter, 1);      // consumed at the end of this task
-    const int rpn = __shfl_down_sync(kFull, rp, 1);             // lane l < nrows: row l = [rp, rpn)
     const unsigned long_mask = __ballot_sync(kFull, lane < nrows && rpn - rp > EGC_CHUNK_EDGES);
     int ri = 0;
     while (ri < nrows) {
       if ((long_mask >> ri) & 1u) { ++ri; continue; }           // long row: its chunk tasks did it
       const unsigned later_long = long_mask >> ri;
       const int limit = later_long != 0u ? ri + __ffs(later_long) - 1 : nrows;
-      const int wb = __shfl_sync(kFull, rp, ri);
-      const unsigned fit = __ballot_sync(kFull, lane >= ri && lane < limit && rpn - wb <= kWindow);
-      const int n_fit = __popc(fit);                            // >= 1: a normal row has at most EGC_CHUNK_EDGES nnz
-      const int we = __shfl_sync(kFull, rpn, ri + n_fit - 1);
-      // ---- stage the window: column ids, symnorm weights, the rows' combination weights
-      for (int i = lane; i < we - wb; i += 32) {
-        cp_async_4(s_col + i, p.col + wb + i);
-        if constexpr (MASK & P_SYM) cp_async_4(s_val + i, p.val_sym + wb + i);
+      // window offsets = running sum of the row lengths from row ri on; rows fit while the sum stays inside the window
+      const int len = (lane >= ri && lane < limit) ? rpn - rp : 0;
+      int incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
       }
-      if (stage_w) {
-        const float* wsrc = p.weightings + static_cast<int64_t>(r0 + ri) * GC::HAB(p);
-        const int nw = n_fit * GC::HAB(p);
-        for (int t = lane; t < nw; t += 32) cp_async_4(s_w + t, wsrc + t);
+      const int woff = incl - len;
+      const unsigned fit = __ballot_sync(kFull, lane >= ri && lane < limit && incl <= kWindow);
+      const int n_fit = __popc(fit);                            // >= 1: a normal row has at most EGC_CHUNK_EDGES nnz
+      const int total = __shfl_sync(kFull, incl, ri + n_fit - 1);
+      // ---- stage the window: column ids, symnorm weights, the rows' combination weights
+      if (!subset) {
+        const int wb = __shfl_sync(kFull, rp, ri);
+        for (int i = lane; i < total; i += 32) {
+          cp_async_4(s_col + i, p.col + wb + i);
+          if constexpr (MASK & P_SYM) cp_async_4(s_val + i, p.val_sym + wb + i);
+        }
+        if (stage_w) {
+          const float* wsrc = p.weightings + static_cast<int64_t>(r0 + ri) * GC::HAB(p);
+          const int nw = n_fit * GC::HAB(p);
+          for (int t = lane; t < nw; t += 32) cp_async_4(s_w + t, wsrc + t);
+        }
+      } else {
+        for (int r = ri; r < ri + n_fit; ++r) {
+          const int rb = __shfl_sync(kFull, rp, r), rl = __shfl_sync(kFull, len, r), ro = __shfl_sync(kFull, woff, r);
+          for (int i = lane; i < rl; i += 32) {
+            cp_async_4(s_col + ro + i, p.col + rb + i);
+            if constexpr (MASK & P_SYM) cp_async_4(s_val + ro + i, p.val_sym + rb + i);
+          }
+          if (stage_w) {
+            const float* wsrc = p.weightings + static_cast<int64_t>(__shfl_sync(kFull, row_id, r)) * GC::HAB(p);
+            for (int t = lane; t < GC::HAB(p); t += 32) cp_async_4(s_w + (r - ri) * GC::HAB(p) + t, wsrc + t);
+          }
+        }
       }
       cp_async_wait_all();
       __syncwarp();
 
-      // gathers of one batch: positions b + t * NG + g clamped to the row's last nnz
+      // gathers of one batch: positions b + t * NG + g clamped to the row's last nnz; wofs maps nnz position -> window
       float4 x[U];
-      auto issue = [&](int b, int e) {
+      auto issue = [&](int b, int e, int wofs) {
 #pragma unroll
         for (int t = 0; t < U; ++t) {
           const int pos = min(b + t * NG + g, e - 1);
-          const uint32_t j = static_cast<uint32_t>(s_col[pos - wb]);
+          const uint32_t j = static_cast<uint32_t>(s_col[pos + wofs]);
           x[t] = ldg_f4_hint(src + static_cast<size_t>(j * BD), pol_keep);
         }
       };
-      int b = wb, e = __shfl_sync(kFull, rpn, ri);
-      if (b < e) issue(b, e);
+      int b = __shfl_sync(kFull, rp, ri), e = __shfl_sync(kFull, rpn, ri);
+      int wofs = __shfl_sync(kFull, woff, ri) - b;
+      if (b < e) issue(b, e, wofs);
       for (int r = ri; r < ri + n_fit; ++r) {
         AccT acc;
         acc.init();
@@ -318,7 +354,7 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
             for (int t = 0; t < U; ++t) {
               const int q = pos + t * NG + g;
               float vs = 0.f;
-              if constexpr (MASK & P_SYM) vs = s_val[q - wb];
+              if constexpr (MASK & P_SYM) vs = s_val[q + wofs];
               add_edge<MASK, ARG>(acc, x[t], vs, q);
             }
           } else {
@@ -327,27 +363,29 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
               const int q = pos + t * NG + g;
               if (q < e) {
                 float vs = 0.f;
-                if constexpr (MASK & P_SYM) vs = s_val[q - wb];
+                if constexpr (MASK & P_SYM) vs = s_val[q + wofs];
                 add_edge<MASK, ARG>(acc, x[t], vs, q);
               }
             }
           }
           pos += STEP;
-          if (pos < e) issue(pos, e);
+          if (pos < e) issue(pos, e, wofs);
         }
         if constexpr (NG > 1) {
 #pragma unroll
           for (int off = G; off < 32; off <<= 1) acc.merge_xor(off);
         }
-        int nb = 0, ne = 0;
+        int nb = 0, ne = 0, nwofs = 0;
         if (r + 1 < ri + n_fit) {                               // next row's first batch flies over this row's epilogue
-          nb = e;
+          nb = __shfl_sync(kFull, rp, r + 1);
           ne = __shfl_sync(kFull, rpn, r + 1);
-          if (nb < ne) issue(nb, ne);
+          nwofs = __shfl_sync(kFull, woff, r + 1) - nb;
+          if (nb < ne) issue(nb, ne, nwofs);
         }
-        finalize(r0 + r, b, e, acc, s_w + (r - ri) * GC::HAB(p));
+        finalize(__shfl_sync(kFull, row_id, r), b, e, acc, s_w + (r - ri) * GC::HAB(p));
         b = nb;
         e = ne;
+        wofs = nwofs;
       }
       ri += n_fit;
     }
@@ -369,7 +407,7 @@ int launch_rows_one(const AggParams& p, int* task_counter, cudaStream_t st) {
   if (smem_bytes > 48 * 1024) {
     EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
-  const int n_blocks = ceil_div(p.n_rows, kRowsPerTask);
+  const int n_blocks = ceil_div(p.n_row_tasks, kRowsPerTask);
   const int64_t warps_wanted = std::max<int64_t>(n_blocks, p.n_chunks);
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div(warps_wanted, kAggWarps), static_cast<int64_t>(sm_count()) * EGC_ROWS_CTAS));
   {

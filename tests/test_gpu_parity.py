@@ -515,3 +515,34 @@ def test_three_layer_full_graph_step_replays_from_a_cuda_graph():
         for a, b in zip(res, ref):
             assert rel_err(a, b.double().cpu()) < 1e-5
     assert per_step >= 3 * 8                                    # sanity: every layer contributes its kernels
+
+
+@pytest.mark.parametrize("cfg", BLOCK_CONFIGS[:3], ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}-h{c[3]}b{c[4]}")
+def test_row_subset_launches_reproduce_the_whole_graph_call(cfg):
+    """What the partitioned layer does: rows computed in two launches over complementary row subsets (the second one
+    with the long-row plan) must give the bits of the single whole-graph launch - out, saved state and argmax positions."""
+    from egc_b200 import functional as F
+    f_in, f_out, aggrs, h, b = cfg
+    n = 2500
+    ei = _degree_pattern_graph(n, [3, 0, 40, 1, 300, 12, 7, 255, 256, 2, 90], seed=9, symmetric=False)
+    g = egc_b200.GraphStructure.from_edge_index(ei.to(DEV), n, "symnorm" in aggrs, True)
+    torch.manual_seed(4)
+    bd = b * (f_out // h)
+    bases = torch.randn(n, bd, device=DEV)
+    weightings = torch.randn(n, h * len(aggrs) * b, device=DEV)
+    bias = torch.randn(f_out, device=DEV)
+    desc = F.make_desc(g, h, b, f_out // h, aggrs, False)
+    whole = F.aggregate_combine(desc, g, bases, weightings, bias, want_saved=True)
+    pick = torch.rand(n, generator=torch.Generator().manual_seed(1)) < 0.6
+    first = torch.nonzero(pick).flatten().to(torch.int32).to(DEV)
+    second = torch.nonzero(~pick).flatten().to(torch.int32).to(DEV)
+    outs = F.alloc_aggregate_outputs(desc, DEV, want_out=True, want_saved=True)
+    for t in outs:
+        if t is not None:
+            t.fill_(0)
+    F.aggregate_combine(desc, g, bases, weightings, bias, row_subset=first, use_plan=False, outputs=outs)
+    F.aggregate_combine(desc, g, bases, weightings, bias, row_subset=second, use_plan=True, outputs=outs)
+    for a, ref in zip(outs, whole):
+        assert (a is None) == (ref is None)
+        if a is not None:
+            assert torch.equal(a, ref)
