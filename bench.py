@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""Headline benchmark: EGConv forward+backward edges/s on synthetic arxiv-/mag-shaped graphs.
+"""Headline benchmark: EGConv forward+backward edges/s on synthetic graphs of the shapes BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|mag|cifar|zinc] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|mag|zinc|cifar|rmag] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-One "step" = one EGConv layer forward + backward over the whole synthetic graph (BASELINE.json
-configs[1] at N=1: EGC-M symnorm+max+std, H4 B4, 128->128 on an ogbn-arxiv-shaped graph, structure
-cached as in the reference's full-graph training).  Rank 0 prints ONE JSON line.
-`value` = aggregated nnz (after symmetrisation + self-loops) per second with inputs resident in HBM,
-`e2e` = same through the public `EGConv` API with the step's features arriving from pinned host
-memory and the loss read back; `roofline` is for the dominant kernel, `cpu_baseline` is the oracle
-port of the reference path timed on this box's host cores.  `--impl reference` times that CPU path alone.
+Default (no flags, N = 1): BASELINE.json configs[1] - one EGC-M layer (symnorm+max+std, H4 B4, 128->128) forward +
+backward over an ogbn-arxiv-shaped graph, structure cached as in the reference's full-graph training.
+Other workloads: `mag` (configs[3], EGC-S on the ogbn-mag-shaped paper graph), `zinc` / `cifar` (configs[0] / [4]:
+128 collated small graphs through a 4-layer stack + readout, structure rebuilt every step), `rmag` (REGConv on an
+ogbn-mag-shaped heterogeneous graph).  N > 1 (torchrun): the arxiv / mag layer row-partitioned over N GPUs with the
+halo exchange over NVLink peer memory, strong scaling, max-over-ranks CUDA-event time.
+
+Rank 0 prints ONE JSON line.  `value` = aggregated nnz (after symmetrisation + self-loops) per second with inputs
+resident in HBM; `e2e` = the same through the public API with the step's features arriving from pinned host memory
+and the loss read back; `roofline` = the dominant kernel's algorithmic bytes / its CUDA-event time against the
+measured HBM peak (`traffic` = its DRAM bytes from the committed ncu capture); `step_roofline` = the layer's unique
+bytes / step time; `cpu_baseline` = the oracle port of the reference path timed on this box's host cores;
+`gpu_launches` = kernels of libegc_b200 launched in the timed region.  `--impl reference` times the CPU path alone.
 """
 import argparse
 import json
