@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
       const int n_fit = __popc(fit);                            // >= 1: a normal row has at most EGC_CHUNK_EDGES nnz
       const int total = __shfl_sync(kFull, incl, ri + n_fit - 1);
       // ---- stage the window: column ids, symnorm weights, the rows' combination weights
+      __syncwarp();                                             // every lane is done reading the previous window
       if (!subset) {
         const int wb = __shfl_sync(kFull, rp, ri);
         for (int i = lane; i < total; i += 32) {

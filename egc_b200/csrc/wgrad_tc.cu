@@ -47,7 +47,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int W = p.f_in + p.n1 + p.n2;                                // floats per raw node row
   const int ppn = W >> 2;                                            // 16-byte pieces per node
   const uint32_t a_half = kWgM * kWgChunk * 4;                       // 8 KB: hi (or lo) of an A chunk
