@@ -18,6 +18,15 @@
  *   - target-major CSR: row i lists the sources j of the messages node i receives
  *     (= the reference's `adj_t`, ref experiments/utils.py:107-109).
  */
+/*
+ * Environment switches read once per process (A/B and diagnostics; none changes results except EGC_TC_ABLATE):
+ *   EGC_FWD_WARP_PER_ROW=1     forward aggregation: warp-per-row kernel instead of the row-block kernel
+ *   EGC_BWD_WARP_PER_COLUMN=1  backward CSC pass: warp-per-column kernel instead of the column-block kernel
+ *   EGC_TC_NO_TMA=1            projection GEMM: cp.async producers instead of TMA tensor copies for the A operand
+ *   EGC_TC_TMA_STORE=1         projection GEMM: TMA tensor-store epilogue (measured equal to the default)
+ *   EGC_TC_MAX_RAW_STAGES=n    projection GEMM: cap the A ring depth
+ *   EGC_TC_ABLATE=bits         projection GEMM: switch pipeline stages off for timing (WRONG results; tools/gemm_ablate.sh)
+ */
 #ifndef EGC_B200_H_
 #define EGC_B200_H_
 
