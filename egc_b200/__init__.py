@@ -19,6 +19,6 @@ from .conv import EGConv  # noqa: F401
 from .dist import GradientAllReduce, GraphedStep  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
 from .hetero import REGConv  # noqa: F401
-from .graph import GraphStructure, SparseTensor  # noqa: F401
+from .graph import GraphStructure, SparseTensor, to_sparse_tensor  # noqa: F401
 
 __version__ = "0.1.0"

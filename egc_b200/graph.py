@@ -134,6 +134,20 @@ class SparseTensor:
         return f"SparseTensor(nnz={self.nnz()}, sparse_sizes={self._sizes}, has_value={self.has_value()})"
 
 
+def to_sparse_tensor(edge_index: Tensor, num_nodes: int) -> SparseTensor:
+    """`adj_t` of an edge list as the reference's `ToSparseTensor` transform builds it
+    (/root/reference/experiments/utils.py:89-115): rows = targets, entries sorted by (target, source), duplicates kept,
+    edge attributes dropped, `rowptr` pre-computed.  Runs on whatever device `edge_index` lives on."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, E]")
+    n = int(num_nodes)
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    perm = torch.argsort(dst * n + src, stable=True)                      # ref :93 `(col * N + row).argsort()`
+    adj_t = SparseTensor(row=dst[perm], col=src[perm], value=None, sparse_sizes=(n, n), is_sorted=True)   # ref :107-109
+    adj_t.rowptr()                                                        # ref :111-113 fill_cache
+    return adj_t
+
+
 class _Plan:
     """Device arrays + the ctypes view of an `egc_row_plan`."""
 

@@ -190,3 +190,34 @@ def test_paper_to_egconv_permutation():
     perm = paper_to_egconv_perm(h, b, a)
     expect = [hh * b * a + bb * a + aa for hh in range(h) for aa in range(a) for bb in range(b)]
     assert perm.tolist() == expect and sorted(perm.tolist()) == list(range(h * b * a))
+
+
+@pytest.mark.skipif(not rl.available(), reason="needs /root/reference")
+def test_to_sparse_tensor_matches_the_reference_transform_bit_exact():
+    """egc_b200.to_sparse_tensor == experiments/utils.py:82-118 ToSparseTensor (run through the shims) on an edge list
+    with duplicates and self-loops: same rowptr, same column order."""
+    import importlib
+    from types import SimpleNamespace
+
+    import egc_b200
+    rl.load()
+    try:
+        utils = importlib.import_module("experiments.utils")
+    except Exception as exc:                                   # the module pulls optional training dependencies
+        pytest.skip(f"experiments.utils not importable here: {exc}")
+    n = 300
+    ei = random_graph(n, 2500, seed=21, hub=120)
+
+    class Data(SimpleNamespace):
+        def __iter__(self):
+            return iter(list(vars(self).items()))
+
+        def __setitem__(self, k, v):
+            setattr(self, k, v)
+
+    data = utils.ToSparseTensor()(Data(edge_index=ei.clone(), num_nodes=n, num_edges=ei.size(1)))
+    rowptr_ref, col_ref, _ = data.adj_t.csr()
+    mine = egc_b200.to_sparse_tensor(ei, n)
+    rowptr, col, value = mine.csr()
+    assert value is None and mine.sparse_sizes() == (n, n)
+    assert torch.equal(rowptr, rowptr_ref) and torch.equal(col, col_ref)
