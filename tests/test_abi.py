@@ -78,3 +78,37 @@ def test_product_does_not_import_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src, f"egc_b200/{fn} mentions the oracle"
+
+
+def test_adjacency_inputs_accepted_without_torch_sparse():
+    """the layer accepts the repo's SparseTensor, a torch sparse CSR tensor, and any object with
+    .csr() / .sparse_sizes() (a real torch_sparse.SparseTensor); everything else is a TypeError."""
+    import warnings
+
+    from egc_b200.graph import adjacency_to_csr
+    rowptr, col, val = torch.tensor([0, 2, 3]), torch.tensor([0, 1, 1]), torch.tensor([1., 2., 3.])
+    own = egc_b200.SparseTensor(rowptr=rowptr, col=col, value=val, sparse_sizes=(2, 3))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        native = torch.sparse_csr_tensor(rowptr, col, val, size=(2, 3))
+
+    class Foreign:
+        def csr(self):
+            return rowptr, col, None
+
+        def sparse_sizes(self):
+            return (2, 3)
+
+    for adj, has_val in ((own, True), (native, True), (Foreign(), False)):
+        rp, c, v, n_src = adjacency_to_csr(adj)
+        assert torch.equal(rp, rowptr) and torch.equal(c, col) and n_src == 3 and (v is not None) == has_val
+    with pytest.raises(TypeError):
+        adjacency_to_csr(object())
+    # unsorted COO input is sorted by (row, col) with values carried along; .t() swaps the roles and stays sorted
+    coo = egc_b200.SparseTensor(row=torch.tensor([1, 0, 0]), col=torch.tensor([1, 1, 0]), value=torch.tensor([3., 2., 1.]),
+                                sparse_sizes=(2, 2))
+    assert coo.coo()[0].tolist() == [0, 0, 1] and coo.coo()[1].tolist() == [0, 1, 1] and coo.coo()[2].tolist() == [1., 2., 3.]
+    t = coo.t()
+    assert t.coo()[0].tolist() == [0, 1, 1] and t.coo()[1].tolist() == [0, 0, 1] and t.coo()[2].tolist() == [1., 2., 3.]
+    sym = egc_b200.SparseTensor(row=torch.tensor([0]), col=torch.tensor([1]), sparse_sizes=(2, 2)).to_symmetric()
+    assert sym.coo()[0].tolist() == [0, 1] and sym.coo()[1].tolist() == [1, 0]
