@@ -131,7 +131,7 @@ inline int static_cfg_index(const egc_layer_desc& d) {
   return -1;
 }
 
-// same idea for the parameter block of backward pass 1 (CombineBwdParams, aggregate_api.cu)
+// same idea for the parameter block of backward pass 1 (CombineBwdParams, backward_pass1.cuh)
 template <class Cfg, class P>
 struct GetB {
 #define EGC_GETB(name, sname)                                                                 \
