@@ -112,3 +112,38 @@ def test_adjacency_inputs_accepted_without_torch_sparse():
     assert t.coo()[0].tolist() == [0, 1, 1] and t.coo()[1].tolist() == [0, 0, 1] and t.coo()[2].tolist() == [1., 2., 3.]
     sym = egc_b200.SparseTensor(row=torch.tensor([0]), col=torch.tensor([1]), sparse_sizes=(2, 2)).to_symmetric()
     assert sym.coo()[0].tolist() == [0, 1] and sym.coo()[1].tolist() == [1, 0]
+
+
+def test_plain_c_program_links_against_the_abi(tmp_path):
+    """include/egc_b200.h is a C header: a C99 translation unit includes it, links libegc_b200.so and calls the
+    device-free entry points (no GPU needed)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "egc_b200.h"
+int main(void) {
+  egc_layer_desc d;
+  memset(&d, 0, sizeof d);
+  d.n_dst = d.n_src = 10; d.heads = 4; d.bases = 4; d.dim = 32; d.n_aggr = 3;
+  d.aggr[0] = EGC_AGGR_SYMNORM; d.aggr[1] = EGC_AGGR_MAX; d.aggr[2] = EGC_AGGR_STD;
+  printf("%d %d %d %s\n", egc_abi_version(), (int)egc_saved_slots(&d), (int)egc_saved_arg_slots(&d), egc_build_info());
+  /* a call that must fail cleanly without a device: null descriptor */
+  int rc = egc_aggregate_fwd(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL);
+  printf("%d %s\n", rc, egc_last_error_string());
+  return 0;
+}
+''')
+    exe = tmp_path / "abi_probe"
+    libdir = os.path.join(ROOT, "egc_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-legc_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    version, saved, saved_arg, *info = out[0].split()
+    assert int(version) == _lib.ABI_VERSION and int(saved) == 4 and int(saved_arg) == 1 and "sm_100a" in " ".join(info)
+    rc, msg = out[1].split(" ", 1)
+    assert int(rc) == -1 and "null descriptor" in msg
