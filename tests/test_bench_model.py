@@ -57,3 +57,17 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_local_roofline_of_partitioned_runs():
+    w = bench.WORKLOADS["arxiv"]
+    kernels = {"k_scatter_bwd": {"launches_per_step": 1.0, "ms_per_step": 0.25},
+               "k_aggregate_fwd": {"launches_per_step": 2.0, "ms_per_step": 0.19},
+               "k_peer_wait": {"launches_per_step": 4.0, "ms_per_step": 2.5},            # no byte model: never dominant
+               "k_project_tc": {"launches_per_step": 2.0, "ms_per_step": 0.13}}
+    r = bench.local_roofline(kernels, 84_000, 1_250_000, w, 6500.0, "test")
+    assert r["kernel"] == "k_scatter_bwd" and r["unit"] == "GB/s" and 0 < r["frac"] < 1
+    kb = bench.kernel_algorithmic_bytes(84_000, 1_250_000, w["f_in"], w["heads"], w["bases"], 32, w["aggrs"])
+    assert abs(r["achieved"] - kb["k_scatter_bwd"] / 0.25e-3 / 1e9) < 1e-6
+    assert bench.local_roofline({}, 10, 10, w, 6500.0, "test") is None
+    assert bench.local_roofline({"k_scatter_bwd": {"ms_per_step": "bad"}}, 10, 10, w, 6500.0, "test") is None
