@@ -1,0 +1,69 @@
+"""`EGC` - the layer stack the reference trains on the full-graph workloads, on the sm_100a kernels.
+
+Mirrors /root/reference/experiments/mag/models.py:16-69: `num_layers` EGConv layers (IN_FEATURES -> hidden -> ... ->
+OUT_ROUNDED), ReLU + dropout between them, the last layer's output truncated to OUT_TRUE columns, `log_softmax`.
+Same constructor arguments, `convs` ModuleList (so `state_dict` keys match: `convs.{i}.bases_weight`, ...),
+`reset_parameters()` and `forward(x, adj_t)`.
+
+Differences in execution only:
+  * every layer of the stack uses the same aggregator list, so the prepared graph (CSR, CSC, symnorm weights, plans)
+    is built ONCE and shared by the layers (the reference caches one copy per layer, `cached=True`);
+  * `forward` also accepts a `PartitionedGraph` (row-partitioned multi-GPU run, `egc_b200.dist`): `x` then holds
+    this rank's rows and the result is this rank's rows of the single-GPU result.
+"""
+from typing import Iterable
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .conv import EGConv
+from .graph import GraphStructure
+
+IN_FEATURES = 128        # ref mag/models.py:8-10
+OUT_ROUNDED = 352
+OUT_TRUE = 349
+
+
+class EGC(torch.nn.Module):
+    def __init__(self, hidden_channels: int, num_layers: int, dropout: float, num_heads: int, num_bases: int,
+                 aggrs: Iterable[str], in_features: int = IN_FEATURES, out_rounded: int = OUT_ROUNDED,
+                 out_true: int = OUT_TRUE, **conv_kwargs):
+        super().__init__()
+        if num_layers < 2:
+            raise ValueError("EGC needs at least two layers (ref mag/models.py:22-54)")
+        aggrs = list(aggrs)
+        dims = [in_features] + [hidden_channels] * (num_layers - 1) + [out_rounded]
+        self.convs = torch.nn.ModuleList(
+            EGConv(dims[i], dims[i + 1], aggrs=aggrs, num_heads=num_heads, num_bases=num_bases, cached=True, **conv_kwargs)
+            for i in range(num_layers))
+        self.dropout = dropout
+        self.out_true = out_true
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+
+    def prepare(self, x: Tensor, adj_t):
+        """The prepared graph shared by the layers: built and cached by the first layer's rules (`cached=True`,
+        ref optimized_layers.py:126-175), so - as in the reference - later calls reuse the first call's graph."""
+        from .dist import PartitionedGraph
+        if isinstance(adj_t, (GraphStructure, PartitionedGraph)):
+            return adj_t
+        return self.convs[0]._prepare(x, adj_t)
+
+    def forward(self, x: Tensor, adj_t) -> Tensor:
+        from .dist import PartitionedGraph, partitioned_egconv
+        g = self.prepare(x, adj_t)
+        if isinstance(g, PartitionedGraph):
+            def run(conv, h):
+                return partitioned_egconv(h, g, conv)
+        else:
+            def run(conv, h):
+                return conv(h, g)
+        for conv in self.convs[:-1]:                                   # ref :61-65
+            x = run(conv, x)
+            x = F.relu(x)
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        x = run(self.convs[-1], x)[:, :self.out_true]                   # ref :68
+        return x.log_softmax(dim=-1)                                   # ref :69

@@ -372,6 +372,28 @@ class EGConvOracle(torch.nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------
+# the full-graph stack  (/root/reference/experiments/mag/models.py:16-69 `EGC`)
+# ---------------------------------------------------------------------------------------------------
+class EGCOracle(torch.nn.Module):
+    """conv -> ReLU -> dropout for all but the last layer; last layer IN->OUT_ROUNDED truncated to OUT_TRUE columns;
+    log_softmax.  Same constructor arguments and `convs.{i}.*` state_dict keys as the reference class."""
+
+    def __init__(self, hidden_channels, num_layers, dropout, num_heads, num_bases, aggrs, in_features=128,
+                 out_rounded=352, out_true=349):
+        super().__init__()
+        dims = [in_features] + [hidden_channels] * (num_layers - 1) + [out_rounded]          # ref :22-54
+        self.convs = torch.nn.ModuleList(
+            EGConvOracle(dims[i], dims[i + 1], aggrs=aggrs, num_heads=num_heads, num_bases=num_bases, cached=True)
+            for i in range(num_layers))
+        self.dropout, self.out_true = dropout, out_true
+
+    def forward(self, x: Tensor, adj_t) -> Tensor:
+        for conv in self.convs[:-1]:                                                          # ref :61-65
+            x = torch.nn.functional.dropout(torch.relu(conv(x, adj_t)), p=self.dropout, training=self.training)
+        return self.convs[-1](x, adj_t)[:, :self.out_true].log_softmax(dim=-1)                # ref :68-69
+
+
+# ---------------------------------------------------------------------------------------------------
 # paper variant  (/root/reference/experiments/layers.py:11-228 `EfficientGraphConv` + `_AggLayer`)
 # ---------------------------------------------------------------------------------------------------
 PAPER_NAMES = {"symadd": "symnorm", "add": "sum", "mean": "mean", "min": "min", "max": "max", "var": "var", "std": "std"}
