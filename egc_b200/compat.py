@@ -119,7 +119,11 @@ class EfficientGraphConv(torch.nn.Module):
         other_idx = [i for i, a in enumerate(names) if a != "symnorm"]
         # one fused call per distinct graph: symadd on the normalised (self-looped) graph, the rest on the raw graph
         groups = []
-        if sym_idx and other_idx and self.add_self_loops:
+        # A valued adjacency also needs the split without self-loops: the symnorm graph carries D^-1/2 A D^-1/2 only,
+        # while add / mean / max / min multiply by the adjacency values (ref layers.py:225 `matmul(adj_t, x, reduce=)`)
+        valued = (not is_tensor) and (edge_index.has_value() if hasattr(edge_index, "has_value") else
+                                      getattr(edge_index, "layout", None) == torch.sparse_csr)
+        if sym_idx and other_idx and (self.add_self_loops or valued):
             groups = [(sym_idx, True), (other_idx, False)]
         else:
             groups = [(list(range(n_a)), bool(sym_idx))]

@@ -99,6 +99,9 @@ class EGConv(torch.nn.Module):
     def forward(self, x: Tensor, edge_index) -> Tensor:
         if not x.is_cuda:
             raise RuntimeError("egc_b200.EGConv runs on CUDA (sm_100a) only; move the module and inputs to the GPU")
+        if x.size(self.node_dim) == 0:                         # zero-node batch: empty output, zero parameter gradients
+            keep = sum(p.sum() for p in self.parameters()) * 0.0
+            return x.new_zeros((0, self.out_channels)) + keep + x.sum() * 0.0
         graph = self._prepare(x, edge_index)
         flags = (_lib.BWD_DETERMINISTIC if self.deterministic else 0) | int(getattr(self, "bwd_flags", 0))
         return egconv(x, graph, self.bases_weight, self.comb_weight.weight, self.comb_weight.bias, self.bias,

@@ -37,14 +37,14 @@ struct PushParams {
   unsigned int* counter;          // zero on entry, zero again on exit
 };
 
-__device__ __forceinline__ void raise_flags(uint32_t* const* flags, int world, int rank, uint32_t slot_mask, uint32_t e) {
-  for (int q = 0; q < world; ++q) {
-    if (q == rank) continue;
-    for (int slot = 0; slot < 8; ++slot) {
-      if (!((slot_mask >> slot) & 1u)) continue;
-      uint32_t* f = flags[q] + slot * world + rank;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
-    }
+// Thread `t` of the calling group raises the flags of peer t (q = t): the release stores are round trips over
+// NVLink, so one thread per peer keeps them in flight together instead of paying world - 1 serial round trips.
+__device__ __forceinline__ void raise_flags_of(uint32_t* const* flags, int world, int rank, uint32_t slot_mask, uint32_t e, int q) {
+  if (q >= world || q == rank) return;
+  for (int slot = 0; slot < 8; ++slot) {
+    if (!((slot_mask >> slot) & 1u)) continue;
+    uint32_t* f = flags[q] + slot * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
   }
 }
 
@@ -71,14 +71,14 @@ __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PushP
   if (p.slot_mask == 0u) return;
   __threadfence_system();                       // my posted stores are visible system-wide before the flag can be
   __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(p.counter, 1u);
-    if (prev == gridDim.x - 1) {                // every CTA has fenced its stores
-      __threadfence_system();
-      *p.counter = 0u;
-      raise_flags(p.flags, p.world, p.rank, p.slot_mask, *p.epoch);
-    }
+    s_last = prev == gridDim.x - 1 ? 1 : 0;     // every CTA has fenced its stores
+    if (s_last) { __threadfence_system(); *p.counter = 0u; }
   }
+  __syncthreads();
+  if (s_last && threadIdx.x < EGC_MAX_PEERS) raise_flags_of(p.flags, p.world, p.rank, p.slot_mask, *p.epoch, threadIdx.x);
 }
 
 // ---- epoch flags ------------------------------------------------------------------------------------
@@ -93,12 +93,11 @@ struct SignalParams {
 };
 
 __global__ void k_peer_signal(const __grid_constant__ SignalParams p) {
-  if (threadIdx.x != 0) return;
   __threadfence_system();
-  raise_flags(p.flags, p.world, p.rank, p.slot_mask, *p.epoch);
+  raise_flags_of(p.flags, p.world, p.rank, p.slot_mask, *p.epoch, threadIdx.x);
 }
 
-// spins until every peer's entry of `slot` has reached epoch - lag; gives up after `timeout_ns` and raises *err
+// spins until every peer's entry of `slot` has reached epoch - lag; after `timeout_ns` it records the slot in *err and traps
 __global__ void k_peer_wait(const uint32_t* flags, int world, int rank, int slot, uint32_t* epoch, uint32_t lag,
                             int advance, unsigned long long timeout_ns, uint32_t* err) {
   const int q = threadIdx.x;
@@ -119,8 +118,12 @@ __global__ void k_peer_wait(const uint32_t* flags, int world, int rank, int slot
       __nanosleep(64);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (now - t0 > timeout_ns) {
+        // A peer never raised its flag: whatever this stream computes next would read stale or partial peer data.
+        // Record which slot (readable through cudaMemcpy after the failure) and make the failure fatal: the trap
+        // aborts the kernel, the stream and every later CUDA call of the process report an error.
         atomicExch(err, 1u + static_cast<uint32_t>(slot));
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
   }

@@ -33,7 +33,9 @@ def balanced_row_bounds(rowptr: Tensor, world_size: int) -> List[int]:
     for p in range(1, world_size):
         target = total * p / world_size
         b = int(torch.searchsorted(work, torch.tensor(target, dtype=torch.float64)))
-        bounds.append(min(max(b, bounds[-1]), n))
+        # every rank owns at least one row whenever there are enough rows (a hub row can outweigh a whole share)
+        b = min(max(b, bounds[-1] + 1), n - (world_size - p)) if n >= world_size else min(max(b, bounds[-1]), n)
+        bounds.append(b)
     bounds.append(n)
     return bounds
 
@@ -75,6 +77,8 @@ class PartitionPlan:
         self.val_lin = val_lin.cpu() if val_lin is not None else None
         self.world_size = world_size
         self.n = self.rowptr.numel() - 1
+        if self.n < world_size:
+            raise ValueError(f"cannot partition {self.n} rows over {world_size} ranks: every rank needs at least one row")
         self.bounds = bounds or balanced_row_bounds(self.rowptr, world_size)
         self._bounds_t = torch.tensor(self.bounds, dtype=torch.long)
         self._needs = [self._needed_remote(r) for r in range(world_size)]      # [rank][owner] -> ids
@@ -257,7 +261,7 @@ class PartitionedGraph:
 class _PartitionedEGConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, pg, heads, num_bases, aggrs, sigmoid, algo, key,
-                grad_mode=True):
+                grad_mode=True, bwd_flags=0):
         from . import functional as F
         from . import peer as P
         part, g = pg.part, pg.graph
@@ -271,7 +275,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 n_flat = bases_weight.numel() + comb_weight.numel() + comb_weight.size(0) + heads * (bd // num_bases)
                 peer = pg.peer_context(key, bd, n_flat)
                 # new epoch; every peer is done with the halo rows of my previous step
-                peer.wait(P.SLOT_CONS, lag=1, advance=True)
+                ctx.step_id = peer.begin_step(needs_grad)
                 bases_ext = peer.bases_ext
             else:
                 bases_ext = torch.empty((part.n_local + part.n_halo, bd), dtype=torch.float32, device=x.device)
@@ -297,7 +301,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         out, _, _, saved, saved_arg = outs
         if needs_grad:
             ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg)
-        ctx.pg, ctx.desc, ctx.algo, ctx.peer = pg, desc, algo, peer
+        ctx.pg, ctx.desc, ctx.algo, ctx.peer, ctx.bwd_flags = pg, desc, algo, peer, int(bwd_flags)
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
@@ -314,7 +318,8 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             if peer is None:
                 d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
-                                                                      saved_arg, grad_out, want_b, want_lin_colsum=True)
+                                                                      saved_arg, grad_out, want_b, ctx.bwd_flags,
+                                                                      want_lin_colsum=True)
                 d_bases = d_bases_ext[:part.n_local]
                 pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
                 d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
@@ -324,7 +329,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
                     if t is not None:
                         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)
-                return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
+                return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
             # ---- peer transport: flat parameter-gradient vector [d_wb | d_wc | d_bc | d_bias] in the exchange context
             n_wb, n_wc, hab = bases_weight.numel(), comb_weight.numel(), comb_weight.size(0)
             hd = ctx.desc.heads * ctx.desc.dim
@@ -333,11 +338,12 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             v_wc = flat[n_wb:n_wb + n_wc].view_as(comb_weight)
             v_bc = flat[n_wb + n_wc:n_wb + n_wc + hab]
             v_b = flat[n_wb + n_wc + hab:n_wb + n_wc + hab + hd]
+            peer.begin_backward(ctx.step_id)
             if not (need_wb and need_wc and want_b):
                 flat.zero_()
             d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
-                                                          grad_out, want_b, want_lin_colsum=True, out_bias=v_b,
-                                                          out_lin_colsum=v_bc)
+                                                          grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
+                                                          out_bias=v_b, out_lin_colsum=v_bc)
             peer.push_backward(d_bases_ext)                # halo partial sums go home (posted stores), BWD + CONS flags
             peer.wait(P.SLOT_BWD)
             d_bases = d_bases_ext[:part.n_local]
@@ -349,7 +355,12 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             d_wc = total[n_wb:n_wb + n_wc].view_as(comb_weight).clone() if need_wc else None
             d_bc = total[n_wb + n_wc:n_wb + n_wc + hab].clone() if want_bc else None
             d_bias = total[n_wb + n_wc + hab:n_wb + n_wc + hab + hd].clone() if want_b else None
-        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
+        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
+
+
+def _bwd_flags_of(conv) -> int:
+    from . import _lib
+    return (_lib.BWD_DETERMINISTIC if getattr(conv, "deterministic", False) else 0) | int(getattr(conv, "bwd_flags", 0))
 
 
 def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv) -> Tensor:
@@ -358,7 +369,8 @@ def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv) -> Tensor:
     With the peer transport every layer keeps its own exchange buffers (keyed by the module), one step in flight."""
     return _PartitionedEGConvFunction.apply(x_local, conv.bases_weight, conv.comb_weight.weight, conv.comb_weight.bias,
                                             conv.bias, pg, conv.num_heads, conv.num_bases, tuple(conv.aggregators),
-                                            bool(conv.sigmoid), int(conv.gemm_algo), id(conv), torch.is_grad_enabled())
+                                            bool(conv.sigmoid), int(conv.gemm_algo), id(conv), torch.is_grad_enabled(),
+                                            (_bwd_flags_of(conv)))
 
 
 class GraphedStep:

@@ -82,6 +82,10 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
     if outputs is None:
         outputs = alloc_aggregate_outputs(desc, dev, want_out, want_agg, want_arg, want_saved)
     out, agg, arg, saved, saved_arg = outputs
+    if desc.n_dst == 0:                                   # no target rows: empty outputs (the reference returns [0, F])
+        return outputs
+    if desc.n_src == 0:
+        raise ValueError("egc_b200: aggregation over a graph with target rows but no source nodes")
     plan = graph.plan.struct if use_plan else None
     nbytes = lib.egc_aggregate_fwd_workspace_bytes(desc, plan)
     ws = _ws(nbytes, dev)
@@ -103,8 +107,17 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
     with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias)."""
     lib = _lib.load()
     dev = bases.device
-    graph.ensure_csc()
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
+    if desc.n_dst == 0:                                   # no target rows: every gradient is zero
+        d_w = torch.zeros((0, hab), dtype=torch.float32, device=dev)
+        d_bases = torch.zeros((desc.n_src, bd), dtype=torch.float32, device=dev)
+        d_bias = (out_bias.zero_() if out_bias is not None else
+                  torch.zeros(desc.heads * desc.dim, dtype=torch.float32, device=dev)) if want_bias else None
+        if want_lin_colsum:
+            return d_w, d_bases, d_bias, (out_lin_colsum.zero_() if out_lin_colsum is not None else
+                                          torch.zeros(hab, dtype=torch.float32, device=dev))
+        return d_w, d_bases, d_bias
+    graph.ensure_csc()
     d_w = torch.empty((desc.n_dst, hab), dtype=torch.float32, device=dev)
     d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev)
     d_bias = (out_bias if out_bias is not None else
@@ -136,6 +149,11 @@ def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bas
     d_wb = (out_wb if out_wb is not None else torch.empty_like(bases_weight)) if need_wb else None
     d_wc = (out_wc if out_wc is not None else torch.empty_like(comb_weight)) if need_wc else None
     d_bc = torch.empty(hab, dtype=torch.float32, device=dev) if need_bc else None
+    if n == 0:                                            # no rows: the parameter gradients are zero
+        for t in (d_wb, d_wc, d_bc):
+            if t is not None:
+                t.zero_()
+        return d_x, d_wb, d_wc, d_bc
     nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
     ws = _ws(nbytes, dev)
     check(lib.egc_project_bwd(ptr(x), ptr(bases_weight), ptr(comb_weight), ptr(d_bases), ptr(d_lin), n, f_in, bd, hab,
@@ -231,7 +249,16 @@ class _AggregateCombineFunction(torch.autograd.Function):
         bases = _require_cuda_f32("bases", bases)
         weightings = _require_cuda_f32("weightings", weightings)
         bias = _require_cuda_f32("bias", bias)
+        if bases.dim() != 2 or bases.size(0) != graph.n_src:
+            raise ValueError(f"bases must be [n_src, B * D] with n_src == {graph.n_src} (got {tuple(bases.shape)})")
+        if bases.size(1) % num_bases != 0:
+            raise ValueError(f"bases width {bases.size(1)} is not divisible by num_bases={num_bases}")
         dim = bases.size(1) // num_bases
+        hab = heads * len(aggrs) * num_bases
+        if weightings.dim() != 2 or weightings.size(0) != graph.n_dst or weightings.size(1) != hab:
+            raise ValueError(f"weightings must be [n_dst, H * A * B] = [{graph.n_dst}, {hab}] (got {tuple(weightings.shape)})")
+        if bias is not None and bias.numel() != heads * dim:
+            raise ValueError(f"bias must have H * D = {heads * dim} entries (got {bias.numel()})")
         desc = make_desc(graph, heads, num_bases, dim, aggrs, False)
         needs_grad = grad_mode and any(ctx.needs_input_grad[:3])
         with torch.cuda.device(bases.device):

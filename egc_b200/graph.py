@@ -198,6 +198,16 @@ class GraphStructure:
 
     # -- builders --------------------------------------------------------------------------
     @staticmethod
+    def _empty(n_dst: int, n_src: int, dev) -> "GraphStructure":
+        """A graph without target rows (zero-node batch, a node type without nodes): no kernel ever runs on it."""
+        g = GraphStructure()
+        g.n_dst, g.n_src = n_dst, n_src
+        g.rowptr = torch.zeros(n_dst + 1, dtype=torch.int32, device=dev)
+        g.col = torch.zeros(0, dtype=torch.int32, device=dev)
+        g.plan = _Plan(g.rowptr, n_dst, 0, 0)
+        return g
+
+    @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, symnorm: bool, add_self_loops: bool) -> "GraphStructure":
         if not edge_index.is_cuda:
             raise RuntimeError("egc_b200: edge_index must live on a CUDA device (there is no CPU path)")
@@ -206,6 +216,10 @@ class GraphStructure:
         lib = _lib.load()
         ei = edge_index.long().contiguous()
         dev, n_edges = ei.device, ei.size(1)
+        if num_nodes == 0:
+            if n_edges:
+                raise IndexError("egc_b200: node index out of range in the graph input")
+            return GraphStructure._empty(0, 0, dev)
         loops = _lib.LOOPS_NONE if not add_self_loops else (_lib.LOOPS_ALL_NODES if symnorm else _lib.LOOPS_UP_TO_MAX_ID)
         g = GraphStructure()
         g.n_dst = g.n_src = int(num_nodes)
@@ -230,6 +244,8 @@ class GraphStructure:
         rowptr64, col64 = rowptr.to(dev).long().contiguous(), col.long().contiguous()
         val_in = value.to(dev, torch.float32).contiguous() if value is not None else None
         n_dst, nnz_in = rowptr64.numel() - 1, col64.numel()
+        if n_dst == 0:
+            return GraphStructure._empty(0, int(n_src), dev)
         cap = nnz_in + (min(n_dst, n_src) if add_self_loops else 0)
         g = GraphStructure()
         g.n_dst, g.n_src = int(n_dst), int(n_src)

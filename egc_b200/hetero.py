@@ -73,13 +73,16 @@ class REGConv(torch.nn.Module):
     def _relation(self, key: EdgeType, adj_t, device) -> GraphStructure:
         if isinstance(adj_t, GraphStructure):
             return adj_t
-        g = self._graphs.get(key) if self.cached else None
-        if g is None:
-            rowptr, col, value, n_src = adjacency_to_csr(adj_t)
-            g = GraphStructure.from_csr(rowptr.to(device), col.to(device), value.to(device) if value is not None else None,
-                                        n_src, False, False)
-            if self.cached:
-                self._graphs[key] = g
+        # the reference does no caching (rmag/models.py:134); here the CSR -> device structure build is cached per edge
+        # type AND per adjacency object, so a different adjacency passed under the same key is rebuilt, never reused
+        hit = self._graphs.get(key) if self.cached else None
+        if hit is not None and hit[0] is adj_t:
+            return hit[1]
+        rowptr, col, value, n_src = adjacency_to_csr(adj_t)
+        g = GraphStructure.from_csr(rowptr.to(device), col.to(device), value.to(device) if value is not None else None,
+                                    n_src, False, False)
+        if self.cached:
+            self._graphs[key] = (adj_t, g)
         return g
 
     def forward(self, x_dict: Dict[str, Tensor], adj_t_dict: Dict[EdgeType, object]) -> Dict[str, Tensor]:
@@ -98,8 +101,13 @@ class REGConv(torch.nn.Module):
         out = {}
         for t, x in x_dict.items():
             w_root = weights[t][:, :hb].contiguous()
+            if x.size(0) == 0:                                  # a node type without nodes (ref handles empty tensors)
+                out[t] = x.new_zeros((0, self.out_channels)) + weights[t].sum() * 0.0
+                continue
             out[t] = aggregate_combine_autograd(bases[t], w_root, None, self._identity(x.size(0), x.device), h, b, ("sum",))
             for i, k in enumerate(incoming[t]):
+                if bases[k[0]].size(0) == 0:                    # relation from an empty node type: contributes nothing
+                    continue
                 g = self._relation(k, adj_t_dict[k], x.device)
                 if g.n_dst != x.size(0) or g.n_src != bases[k[0]].size(0):
                     raise ValueError(f"adjacency of {k} is {g.n_dst} x {g.n_src}, expected {x.size(0)} x {bases[k[0]].size(0)}")

@@ -136,6 +136,10 @@ class PeerLayerContext:
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.flat = torch.zeros(self.n_flat, dtype=torch.float32, device=self.device)
         self.flat_sum = torch.zeros(self.n_flat, dtype=torch.float32, device=self.device)
+        # host-side step bookkeeping: a forward that saved state for a backward is "outstanding" until that backward
+        # has pushed its halo gradients (which also raises CONS, releasing the peers' halo copies of my rows)
+        self.step_id = 0
+        self.outstanding = False
 
         # what every rank must know about the others: local row counts, halo layout, staging layout
         recv_off = [0]
@@ -191,6 +195,29 @@ class PeerLayerContext:
         self.grad_dst = _ptr_array([self.seg.peer_ptr(q, "slots", self.rank * self.n_flat * 4) for q in range(self.world)])
         self.grad_src = _ptr_array([self.flat.data_ptr()] * self.world)
         self.flag_ptrs = _ptr_array([self.seg.peer_ptr(q, "flags") for q in range(self.world)])
+
+    # -- step protocol -----------------------------------------------------------------------------------
+    def begin_step(self, needs_grad: bool) -> int:
+        """Start a new step of this layer: epoch += 1 after every peer is done with the halo rows of my previous
+        step (CONS).  If the previous forward required grad but its backward never ran (validation outside
+        `torch.no_grad()`, an exception between forward and backward), nobody raised CONS for it: raise it here -
+        the program is SPMD, every rank is in the same situation - instead of stalling all ranks until the timeout."""
+        if self.outstanding:
+            self.signal(SLOT_CONS)
+        self.wait(SLOT_CONS, lag=1, advance=True)
+        self.step_id += 1
+        self.outstanding = bool(needs_grad)
+        return self.step_id
+
+    def begin_backward(self, step_id: int) -> None:
+        """The backward of step `step_id` is about to use the exchange buffers: they must still hold that step."""
+        if step_id != self.step_id or not self.outstanding:
+            raise RuntimeError(
+                "egc_b200 partitioned layer: backward of a stale step - the layer ran another forward (or this backward "
+                "already ran, e.g. retain_graph=True) since the forward being differentiated, and the exchange buffers "
+                "(halo rows, staging) hold one step per layer.  Use a separate module per application, or run the "
+                "forward again.")
+        self.outstanding = False
 
     # -- stream-ordered primitives ---------------------------------------------------------------------
     @staticmethod
@@ -254,8 +281,7 @@ class PeerLayerContext:
             raise RuntimeError(
                 f"egc_b200 peer exchange: rank {self.rank} timed out waiting for its peers' {names.get(code, code)} flag "
                 f"[epoch {int(self.epoch.item())}, flags {self.flags.view(N_SLOTS, self.world).tolist()}] "
-                "(a rank skipped a step, or a forward that required grad was never followed by its backward - run "
-                "inference under torch.no_grad())")
+                "(a rank skipped a step or died; the waiting kernel trapped, this CUDA context is unusable)")
 
     def close(self):
         self.seg.close()

@@ -285,8 +285,8 @@ int egc_peer_epoch_advance(uint32_t* epoch, void* stream);
 int egc_peer_signal(uint32_t* const* flags, int32_t world, int32_t rank, uint32_t slot_mask, const uint32_t* epoch,
                     void* stream);
 /* (advance != 0: *epoch += 1 first - a new step starts.)  Block the stream until my_flags[slot * world + q] >=
- * *epoch - lag for every q != rank; after timeout_ns the kernel gives up and sets *err = 1 + slot (device word,
- * checked by the host when it next synchronises) */
+ * *epoch - lag for every q != rank; after timeout_ns the kernel records *err = 1 + slot (device word) and TRAPS:
+ * nothing downstream may run on stale peer data, so the stream and every later CUDA call of the process fail */
 int egc_peer_wait(const uint32_t* my_flags, int32_t world, int32_t rank, int32_t slot, uint32_t* epoch,
                   uint32_t lag, int32_t advance, uint64_t timeout_ns, uint32_t* err, void* stream);
 

@@ -167,3 +167,17 @@ def test_data_parallel_gradients_match_single_process_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_dp_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_every_rank_owns_a_row_even_with_a_dominant_hub():
+    """A hub row heavier than a whole share must not leave a rank without rows (empty ranks block the step)."""
+    from egc_b200.dist import PartitionPlan, balanced_row_bounds
+    n = 12
+    counts = torch.ones(n, dtype=torch.long)
+    counts[0] = 10_000                                        # one hub row outweighs everything else
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    for world in (2, 4, 8):
+        b = balanced_row_bounds(rowptr, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i + 1] > b[i] for i in range(world)), b
+    with pytest.raises(ValueError):
+        PartitionPlan(torch.tensor([0, 1, 2]), torch.tensor([0, 1]), 4)

@@ -49,3 +49,16 @@ def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     denom = b.abs().max().clamp(min=1e-30)
     return ((a - b).abs().max() / denom).item()
+
+
+def restrict_rows(g, keep_rows):
+    """Oracle graph with the entries of the target rows in `keep_rows` (bool [n_dst]) only; every other row becomes
+    empty.  Weights (symnorm / linear) keep their GLOBAL values, so the kept rows aggregate exactly as in `g`."""
+    from oracle.restatement import OracleGraph
+    row = g.row
+    sel = keep_rows[row]
+    cnt = torch.where(keep_rows, g.rowptr[1:] - g.rowptr[:-1], torch.zeros_like(g.rowptr[1:]))
+    rowptr = torch.cat([cnt.new_zeros(1), cnt.cumsum(0)])
+    pick = lambda t: t[sel] if t is not None else None  # noqa: E731
+    return OracleGraph(rowptr, g.col[sel], g.n_dst, g.n_src, val_sym=pick(g.val_sym), val_lin=pick(g.val_lin),
+                       deg=g.deg, dis=g.dis)
