@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """Headline benchmark: EGConv forward+backward edges/s on synthetic graphs of the shapes BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|mag|zinc|cifar|rmag] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload arxiv|mag|zinc|cifar|rmag] [--layers L] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
 Default (no flags, N = 1): BASELINE.json configs[1] - one EGC-M layer (symnorm+max+std, H4 B4, 128->128) forward +
-backward over an ogbn-arxiv-shaped graph, structure cached as in the reference's full-graph training.
-Other workloads: `mag` (configs[3], EGC-S on the ogbn-mag-shaped paper graph), `zinc` / `cifar` (configs[0] / [4]:
-128 collated small graphs through a 4-layer stack + readout, structure rebuilt every step), `rmag` (REGConv on an
-ogbn-mag-shaped heterogeneous graph).  N > 1 (torchrun): the arxiv / mag layer row-partitioned over N GPUs with the
-halo exchange over NVLink peer memory, strong scaling, max-over-ranks CUDA-event time.
+backward over an ogbn-arxiv-shaped graph, structure cached as in the reference's full-graph training.  `--layers 3`
+runs the reference's `EGC` stack (configs[2]); `--workload mag` configs[3].  N > 1 (torchrun): the same layer / stack
+row-partitioned over N GPUs with the halo exchange over NVLink peer memory - strong scaling on the SAME graph (one
+generator setting, p_intra = 0.8 over 8 id blocks, for every N) in the same launch mode (the whole step replayed from
+one CUDA graph), max-over-ranks CUDA-event time, and a `parity_check` of the partitioned step against the single-GPU
+layer before anything is timed (non-zero exit above the bar).  The default run also times the other full-graph
+configurations of BASELINE.json and puts them under `other_configs` of the same line (3-layer arxiv stack, mag, and at
+N = 1 the generator's uniform graph, the round-1 headline graph).  Other workloads: `zinc` / `cifar` (configs[0] / [4]:
+128 collated small graphs through a 4-layer stack + readout, structure rebuilt every step), `rmag` (REGConv).
 
-Rank 0 prints ONE JSON line.  `value` = aggregated nnz (after symmetrisation + self-loops) per second with inputs
-resident in HBM; `e2e` = the same through the public API with the step's features arriving from pinned host memory
-and the loss read back; `roofline` = the dominant kernel's algorithmic bytes / its CUDA-event time against the
-measured HBM peak (`traffic` = its DRAM bytes from the committed ncu capture); `step_roofline` = the layer's unique
-bytes / step time; `cpu_baseline` = the oracle port of the reference path timed on this box's host cores;
-`gpu_launches` = kernels of libegc_b200 launched in the timed region.  `--impl reference` times the CPU path alone.
+Rank 0 prints ONE JSON line.  `value` = aggregated nnz (after symmetrisation + self-loops) x layers per second with
+inputs resident in HBM; `e2e` = the same through the public API with the step's features arriving from pinned host
+memory and the loss read back; `roofline` = the dominant kernel's algorithmic bytes / its CUDA-event time against the
+measured HBM peak (`traffic` = its DRAM bytes from the committed ncu capture of that workload, else null);
+`step_roofline` = the step's unique bytes / step time; `cpu_baseline` = the oracle port of the reference path timed on
+this box's host cores, whose results are also the checker of `parity_check` at N = 1 (GPU vs fp64 oracle, full graph);
+`gpu_launches` = kernels of libegc_b200 launched in the timed region.  `--impl reference` times the CPU path alone on
+the same workload.
 """
 import argparse
 import json
@@ -37,10 +43,10 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: nodes, raw directed edges, F_in, F_out, heads, bases, aggregators, input kind, zipf exponent
-    "arxiv": dict(n=169_343, e0=1_166_243, f_in=128, f_out=128, heads=4, bases=4,
+    "arxiv": dict(n=169_343, e0=1_166_243, f_in=128, f_out=128, heads=4, bases=4, classes=(40, 40),
                   aggrs=["symnorm", "max", "std"], kind="edge_index", zipf=0.75,
                   desc="EGC-M (symnorm+max+std, H4 B4) 128->128, ogbn-arxiv-shaped, 1 layer fwd+bwd"),
-    "mag": dict(n=736_389, e0=5_416_271, f_in=128, f_out=128, heads=8, bases=4,
+    "mag": dict(n=736_389, e0=5_416_271, f_in=128, f_out=128, heads=8, bases=4, classes=(352, 349),
                 aggrs=["symnorm"], kind="adj_t", zipf=0.70,
                 desc="EGC-S (symnorm, H8 B4) 128->128, ogbn-mag-shaped paper graph, 1 layer fwd+bwd"),
 }
@@ -133,11 +139,13 @@ def kernel_algorithmic_bytes(n, e, f_in, heads, bases, dim, aggrs):
     }
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read + dram__bytes_write) of `kernel` on `workload` from the committed
+    `ncu --set full` capture of this round (profiles/r02_dram_traffic.json, written by tools/ncu_summary.py), or None
+    when that workload / kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
     try:
-        return json.load(open(path)).get(kernel)
+        return json.load(open(path)).get(workload, {}).get(kernel)
     except Exception:
         return None
 
@@ -191,33 +199,104 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU path of the reference (oracle port), used by --impl reference and by the cpu_baseline leg
+# models: ONE layer (configs[1] / [3]) or the reference's `EGC` stack (configs[2]: experiments/mag/models.py:16-69)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_factory(w, n, edge_index, frac, seed=0):
-    """Builds a closure running one fwd+bwd of the reference path on the host for the targets < frac*n.
-    Returns (step_fn, nnz_aggregated, description)."""
+def layer_dims(w, layers):
+    """[(f_in, f_out)] of the conv layers: a single 128 -> 128 layer, or IN -> hidden ... -> OUT_ROUNDED of the stack."""
+    if layers == 1:
+        return [(w["f_in"], w["f_out"])]
+    return list(zip([w["f_in"]] + [w["f_out"]] * (layers - 1), [w["f_out"]] * (layers - 1) + [w["classes"][0]]))
+
+
+def make_oracle_model(w, layers, seed=0, dtype=torch.float32, dropout=0.5):
+    """CPU restatement with the parameters every arm of the benchmark shares (seeded)."""
     from oracle import restatement as R
     torch.manual_seed(seed)
+    if layers == 1:
+        m = R.EGConvOracle(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"], cached=True)
+    else:
+        m = R.EGCOracle(w["f_out"], layers, dropout, w["heads"], w["bases"], w["aggrs"], in_features=w["f_in"],
+                        out_rounded=w["classes"][0], out_true=w["classes"][1])
+    return m.to(dtype)
+
+
+def make_gpu_model(w, layers, dev, state_dict=None, seed=0, dropout=0.5):
+    import egc_b200
+    torch.manual_seed(seed)
+    if layers == 1:
+        m = egc_b200.EGConv(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"], cached=True)
+    else:
+        m = egc_b200.EGC(w["f_out"], layers, dropout, w["heads"], w["bases"], w["aggrs"], in_features=w["f_in"],
+                         out_rounded=w["classes"][0], out_true=w["classes"][1])
+    if state_dict is not None:
+        m.load_state_dict({k: v.float() for k, v in state_dict.items()})
+    return m.to(dev)
+
+
+def out_width(w, layers):
+    return w["f_out"] if layers == 1 else w["classes"][1]
+
+
+def stack_bytes(w, n, nnz, layers):
+    """Unique bytes of one fwd+bwd step: the per-layer model summed over the conv layers (elementwise glue ignored)."""
+    total = 0
+    for f_in, f_out in layer_dims(w, layers):
+        bf, bb = algorithmic_bytes(n, nnz, f_in, w["heads"], w["bases"], f_out // w["heads"], w["aggrs"])
+        total += bf + bb
+    return total
+
+
+def workload_config(name, w, n, nnz, layers, p_intra, world):
+    """The `config` object BOTH arms print (ours and --impl reference): only what defines the workload."""
+    desc = w["desc"] if layers == 1 else w["desc"].replace("1 layer fwd+bwd", f"{layers}-layer EGC stack "
+                                                           f"(conv-ReLU-dropout, log_softmax; ref mag/models.py) fwd+bwd")
+    return {"workload": desc, "name": name, "layers": layers, "nodes": n, "raw_directed_edges": w["e0"], "nnz": nnz,
+            "edges_counted": "aggregated nnz (symmetrised + self-loops) x layers", "input": w["kind"],
+            "structure": "cached (graph prepared once, as the reference's cached=True)",
+            "generator": {"seed": 0, "p_intra": p_intra, "blocks": 8}, "n_gpus": world,
+            "l2": f"no flush: per-step working set {stack_bytes(w, n, nnz, layers) / 1e9:.2f} GB >> {L2_BYTES / 1e6:.0f} MB L2",
+            "algorithmic_bytes_per_step": stack_bytes(w, n, nnz, layers)}
+
+
+def default_locality(args):
+    """p_intra of the generator: ONE graph for every GPU count (the scaling curve compares like with like)."""
+    return args.locality if args.locality >= 0 else 0.8
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path of the reference (oracle port), used by --impl reference and by the cpu_baseline leg
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_job(w, n, edge_index, layers=1, frac=1.0, seed=0, dtype=torch.float32, train=True):
+    """One fwd+bwd of the reference path on the host (targets < frac*n when frac < 1).  Returns a dict with the step
+    closure (-> out, {name: grad}), the model, the inputs and the aggregated nnz."""
     ei = edge_index
     if frac < 1.0:
-        keep = ei[1] < int(frac * n)
-        ei = ei[:, keep]
-    layer = R.EGConvOracle(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"],
-                           cached=True)
-    x = torch.randn(n, w["f_in"], requires_grad=True)
-    go = torch.randn(n, w["f_out"])
-    graph_in = ei if w["kind"] == "edge_index" else to_adj_t(ei, n) + (None,)
-    g = layer.prepare(x, graph_in)      # cached structure, like the reference's full-graph runs
+        ei = ei[:, ei[1] < int(frac * n)]
+    model = make_oracle_model(w, layers, seed, dtype)
+    model.train(train)
+    gen = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, w["f_in"], generator=gen).to(dtype).requires_grad_(True)
+    go = torch.randn(n, out_width(w, layers), generator=gen).to(dtype)
+    if w["kind"] == "edge_index":
+        graph_in = ei
+    else:
+        rowptr, col = to_adj_t(ei, n)
+        graph_in = (rowptr, col, None)
+    first = model if layers == 1 else model.convs[0]
+    g = first.prepare(x, graph_in)                       # cached structure, like the reference's full-graph runs
+    if layers > 1:
+        for conv in model.convs[1:]:
+            conv._graph = g
+    names = [k for k, _ in model.named_parameters()]
 
     def step():
-        for p_ in layer.parameters():
-            p_.grad = None
-        x.grad = None
-        out = layer(x, graph_in)
-        out.backward(go)
-        return out
+        out = model(x, graph_in)
+        grads = torch.autograd.grad(out, [x] + list(model.parameters()), go)
+        return out.detach(), dict(zip(["x"] + names, grads))
 
-    return step, g.nnz, f"targets < {frac:.3f}*N of the {w['kind']} graph ({g.nnz} nnz incl. self-loops), full x"
+    sample = (f"targets < {frac:.3f}*N of the {w['kind']} graph ({g.nnz} nnz incl. self-loops), full x"
+              if frac < 1.0 else f"the whole {w['kind']} graph ({g.nnz} nnz incl. self-loops)")
+    return {"step": step, "model": model, "x": x, "go": go, "nnz": g.nnz, "sample": sample, "graph_in": graph_in}
 
 
 def time_cpu(step, steps, warmup):
@@ -229,27 +308,30 @@ def time_cpu(step, steps, warmup):
     return (time.perf_counter() - t0) / max(steps, 1)
 
 
-def run_reference_arm(args, w, n, edge_index):
+def run_reference_arm(args, name, w):
+    """The reference's CPU path alone, on OUR arm's workload (same generator, same graph, same layer count)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # calibrate on a 1/16 sample, then size the sample so the whole run stays within ~150 s
-    step_small, nnz_small, _ = cpu_reference_step_factory(w, n, edge_index, 1 / 16)
-    t_small = time_cpu(step_small, 1, 1)
-    t_full_est = t_small * 16
-    budget = 150.0
-    frac = min(1.0, budget / max(t_full_est * (args.steps + args.warmup), 1e-9))
-    frac = max(frac, 1 / 64)
-    step, nnz, sample = cpu_reference_step_factory(w, n, edge_index, frac)
-    t = time_cpu(step, args.steps, args.warmup)
-    value = nnz / t
+    p_intra = default_locality(args)
+    n, ei = synth_graph(name, args.seed, p_intra=p_intra, blocks=8)
+    job = cpu_reference_job(w, n, ei, args.layers)
+    nnz_full = job["nnz"]
+    t_full = time_cpu(job["step"], 1, 0)                 # calibration = the first warm-up step
+    budget = 300.0
+    frac = 1.0
+    if t_full * (args.steps + args.warmup) > budget:     # only then: a bounded sample of the same graph
+        frac = max(budget / (t_full * (args.steps + args.warmup)), 1 / 64)
+        job = cpu_reference_job(w, n, ei, args.layers, frac)
+    t = time_cpu(job["step"], args.steps, max(args.warmup - (1 if frac == 1.0 else 0), 0))
+    value = job["nnz"] * args.layers / t
     line = {
         "impl": "reference", "metric": "EGConv fwd+bwd edges/s", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "nodes": n, "nnz": nnz, "sample": sample,
-                   "path": "oracle port of the reference's PyG path (pure-torch leaf ops), host CPU"},
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(name, w, n, nnz_full, args.layers, p_intra, args.gpus),
+        "path": "oracle port of the reference's PyG path (pure-torch leaf ops), host CPU, all host threads",
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": job["sample"]},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -269,29 +351,126 @@ def load_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def run_single_gpu(args, w, n, edge_index):
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def device_graph_input(w, n, edge_index, dev):
     import egc_b200
+    if w["kind"] == "edge_index":
+        return edge_index.to(dev)
+    rowptr, col = to_adj_t(edge_index, n)
+    return egc_b200.SparseTensor(rowptr=rowptr.to(dev), col=col.to(dev), sparse_sizes=(n, n), is_sorted=True)
+
+
+def cuda_timed(fn, steps, warmup, barrier=None):
+    """CUDA-event time per call of `fn` after `warmup` untimed calls; (ms, kernels launched by libegc_b200)."""
+    from egc_b200 import _lib
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return ev0.elapsed_time(ev1) / steps, _lib.launch_count() - l0
+
+
+def traced_kernels(fn, steps):
+    """Per-kernel CUDA-event times of libegc_b200's launches over `steps` eager calls (separate pass)."""
+    from egc_b200 import _lib
+    _lib.profile_enable(True)
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    return prof, {k: {"launches_per_step": c / steps, "ms_per_step": t / steps} for k, (c, t) in prof.items()}
+
+
+def dominant_roofline(name, prof, kernels, kbytes, peak, peak_src):
+    cand = [k for k in kernels if kbytes.get(k)]
+    if not cand:
+        return None
+    dom = max(cand, key=lambda k: kernels[k]["ms_per_step"])
+    per_launch_ms = prof[dom][1] / prof[dom][0]
+    achieved = kbytes[dom] / (per_launch_ms * 1e-3) / 1e9
+    return {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": measured_traffic(name, dom), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": kbytes[dom], "ms_per_launch": per_launch_ms}
+
+
+class SingleGpuJob:
+    """One workload on one GPU: model, resident inputs, the eager step (public API) and its CUDA-graph replay."""
+
+    def __init__(self, name, w, layers, dev, p_intra, seed=0, state_dict=None, x=None, go=None):
+        from egc_b200.dist import GraphedStep
+        self.name, self.w, self.layers, self.dev = name, w, layers, dev
+        self.n, self.ei = synth_graph(name, seed, p_intra=p_intra, blocks=8)
+        self.model = make_gpu_model(w, layers, dev, state_dict)
+        gen = torch.Generator().manual_seed(seed + 1)
+        self.x_host = (x if x is not None else torch.randn(self.n, w["f_in"], generator=gen)).float().pin_memory()
+        go = go if go is not None else torch.randn(self.n, out_width(w, layers), generator=gen)
+        self.go = go.float().to(dev)
+        self.graph_in = device_graph_input(w, self.n, self.ei, dev)
+        self.x = self.x_host.to(dev).requires_grad_(True)
+        self.params = list(self.model.parameters())
+        self.step()                                      # builds + caches the graph structure (CSR, CSC, plans)
+        first = self.model if layers == 1 else self.model.convs[0]
+        self.graph = first._cached_edge_index if w["kind"] == "edge_index" else first._cached_adj_t
+        self.nnz = self.graph.nnz
+        self._graphed = None
+        self._GraphedStep = GraphedStep
+
+    def step(self):
+        out = self.model(self.x, self.graph_in)
+        return (out,) + torch.autograd.grad(out, [self.x] + self.params, self.go)
+
+    def replay(self):
+        if self._graphed is None:
+            self._graphed = self._GraphedStep(self.step, warmup=2)
+        return self._graphed.replay()
+
+    def grads_named(self, res):
+        names = ["x"] + [k for k, _ in self.model.named_parameters()]
+        return res[0], dict(zip(names, res[1:]))
+
+
+def parity_vs_cpu(job, cpu32, cpu64):
+    """GPU step (eval mode: dropout off) against the fp64 CPU oracle on the same inputs and parameters.  Bar: 1e-5, or
+    4x the error the reference's own fp32 arithmetic shows against fp64 on this input where that is larger (std)."""
+    was = job.model.training
+    job.model.eval()
+    out, grads = job.grads_named(job.step())
+    job.model.train(was)
+    out32, g32 = cpu32
+    out64, g64 = cpu64
+    errs, tols = {"out": rel_err(out, out64)}, {"out": max(1e-5, 4 * rel_err(out32, out64))}
+    for k in grads:
+        errs[k], tols[k] = rel_err(grads[k], g64[k]), max(1e-5, 4 * rel_err(g32[k], g64[k]))
+    ok = all(errs[k] < tols[k] for k in errs)
+    return {"against": "CPU oracle in fp64, same inputs and parameters, full graph", "max_rel_err": max(errs.values()),
+            "rel_err": errs, "tol": tols, "tol_rule": "max(1e-5, 4 x |oracle fp32 - oracle fp64|)", "ok": ok}
+
+
+def run_single_gpu(args, name, w):
     from egc_b200 import _lib
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
-    torch.manual_seed(0)
-    conv = egc_b200.EGConv(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"],
-                           cached=True).to(dev)
-    conv.bwd_flags = args.bwd_flags
-    x_host = torch.randn(n, w["f_in"]).pin_memory()
-    go = torch.randn(n, w["f_out"], device=dev)
-    if w["kind"] == "edge_index":
-        graph_in = edge_index.to(dev)
-    else:
-        rowptr, col = to_adj_t(edge_index, n)
-        graph_in = egc_b200.SparseTensor(rowptr=rowptr.to(dev), col=col.to(dev), sparse_sizes=(n, n), is_sorted=True)
-    x = x_host.to(dev).requires_grad_(True)
-    params = list(conv.parameters())
-
-    def step():
-        out = conv(x, graph_in)
-        torch.autograd.grad(out, [x] + params, go)
-        return out
+    p_intra = default_locality(args)
+    layers = args.layers
+    oracle = make_oracle_model(w, layers, args.seed)
+    job = SingleGpuJob(name, w, layers, dev, p_intra, args.seed, oracle.state_dict())
+    job.model.bwd_flags = args.bwd_flags
+    n, nnz, x_host, go, model, params, graph_in = job.n, job.nnz, job.x_host, job.go, job.model, job.params, job.graph_in
 
     # end-to-end step: the step's features come from pinned host memory, the loss is read back.  The copy of
     # step k+1 is issued on a side stream while step k computes (double-buffered input prefetch, what a
@@ -319,86 +498,99 @@ def run_single_gpu(args, w, n, edge_index):
         issue_copy(slot ^ 1)                                 # prefetch the next step's features
         torch.cuda.current_stream().wait_event(ev_ready[slot])
         xs = x_bufs[slot].detach().requires_grad_(True)
-        out = conv(xs, graph_in)
+        out = model(xs, graph_in)
         loss = (out * go).sum()
         torch.autograd.grad(loss, [xs] + params)
         ev_free[slot].record()
         e2e_state["k"] = k + 1
         return float(loss.item())
 
-    step()                                              # builds + caches the graph structure (CSR, CSC, plans)
-    graph = conv._cached_edge_index if w["kind"] == "edge_index" else conv._cached_adj_t
-    nnz = graph.nnz
-    dim = w["f_out"] // w["heads"]
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _lib.launch_count()
-        ev0.record()
-        for _ in range(steps):
-            fn()
-        ev1.record()
-        torch.cuda.synchronize()
-        return ev0.elapsed_time(ev1) / steps, _lib.launch_count() - launches0
-
+    l0 = _lib.launch_count()
+    job.step()
+    launches_per_step = _lib.launch_count() - l0
     with ClockSampler(dev.index or 0) as clocks:
-        ms, launches = timed(step, args.steps, args.warmup)
-        ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
-    # per-kernel times (CUDA events around every launch of the library, same steps, separate pass)
-    _lib.profile_enable(True)
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    prof = _lib.profile_collect()
-    _lib.profile_enable(False)
+        if args.no_graph:
+            ms, _ = cuda_timed(job.step, args.steps, args.warmup)
+            ms_eager = ms
+        else:
+            ms, _ = cuda_timed(job.replay, args.steps, args.warmup)
+            ms_eager, _ = cuda_timed(job.step, args.steps, args.warmup)
+        ms_e2e, _ = cuda_timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    prof, kernels = traced_kernels(job.step, args.steps)
 
     peak, peak_src = load_peaks()
-    bf, bb = algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], dim, w["aggrs"])
-    kbytes = kernel_algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], dim, w["aggrs"])
-    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t / args.steps} for k, (c, t) in prof.items()}
-    cand = [k for k in kernels if kbytes.get(k)]
-    dom = max(cand, key=lambda k: kernels[k]["ms_per_step"]) if cand else None
+    total_bytes = stack_bytes(w, n, nnz, layers)
     roofline = None
-    if dom:
-        per_launch_ms = prof[dom][1] / prof[dom][0]
-        achieved = kbytes[dom] / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": measured_traffic(dom), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": kbytes[dom], "ms_per_launch": per_launch_ms}
-    step_gbs = (bf + bb) / (ms * 1e-3) / 1e9
+    if layers == 1:
+        kbytes = kernel_algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], w["f_out"] // w["heads"], w["aggrs"])
+        roofline = dominant_roofline(name, prof, kernels, kbytes, peak, peak_src)
+    step_gbs = total_bytes / (ms * 1e-3) / 1e9
+    edges = nnz * layers
 
-    cpu = None
+    cpu = parity = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        frac = 1.0 if args.workload == "arxiv" else 0.25
-        cstep, cnnz, sample = cpu_reference_step_factory(w, n, edge_index, frac)
-        t_cpu = time_cpu(cstep, 2, 1)
-        cpu = {"value": cnnz / t_cpu, "unit": "edges/s", "cores": cores, "kind": "port",
-               "sample": f"{sample}; 1 warm-up + 2 timed fwd+bwd steps, {t_cpu:.2f} s/step"}
+        frac = 1.0 if (name == "arxiv" and layers == 1) else (0.5 if name == "arxiv" else 0.25)
+        cjob = cpu_reference_job(w, n, job.ei, layers, frac, args.seed)
+        t_cpu = time_cpu(cjob["step"], 2, 1)
+        cpu = {"value": cjob["nnz"] * layers / t_cpu, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": f"{cjob['sample']}; 1 warm-up + 2 timed fwd+bwd steps, {t_cpu:.2f} s/step"}
+        if frac == 1.0:
+            # the CPU leg's results are the checker: same parameters (the GPU model loaded the oracle's state_dict),
+            # same x / grad_out (same generator seed), fp32 run = the timed one, one extra fp64 run = the truth
+            cjob["model"].eval()
+            cpu32 = cjob["step"]()
+            c64 = cpu_reference_job(w, n, job.ei, layers, 1.0, args.seed, torch.float64, train=False)
+            parity = parity_vs_cpu(job, cpu32, c64["step"]())
 
     line = {
-        "metric": "EGConv fwd+bwd edges/s", "value": nnz / (ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "metric": "EGConv fwd+bwd edges/s", "value": edges / (ms * 1e-3), "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "nodes": n, "raw_directed_edges": w["e0"], "nnz": nnz,
-                   "input": w["kind"], "structure": "cached (graph prepared once, as the reference's cached=True)",
-                   "l2": f"no flush: per-step working set {(bf + bb) / 1e9:.2f} GB >> {L2_BYTES / 1e6:.0f} MB L2",
-                   "algorithmic_bytes_per_step": bf + bb, "bytes_per_edge": (bf + bb) / nnz},
+        "config": workload_config(name, w, n, nnz, layers, p_intra, 1),
+        "launch_mode": "eager launches" if args.no_graph else "whole step replayed from one CUDA graph (as the N > 1 runs)",
+        "eager_ms_per_step": ms_eager,
         "clocks": clocks.summary(),
-        "e2e": {"value": nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+        "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
-                "input_pipeline": "double-buffered: the H2D copy of step k+1 overlaps the compute of step k"},
-        "gpu_launches": launches,
+                "input_pipeline": "public API, eager; double-buffered: the H2D copy of step k+1 overlaps the compute of step k"},
+        "gpu_launches": launches_per_step * args.steps,
         "step_roofline": {"achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak},
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity_check": parity,
         "kernels": kernels,
     }
+    if not args.no_extras and name == "arxiv" and layers == 1:
+        del job
+        torch.cuda.empty_cache()
+        line["other_configs"] = single_gpu_extras(args, dev, p_intra, peak)
     print(json.dumps(line))
+    if parity is not None and not parity["ok"]:
+        sys.exit("bench.py: GPU results differ from the CPU oracle beyond the bar - see parity_check")
+
+
+def single_gpu_extras(args, dev, p_intra, peak):
+    """The other full-graph configurations BASELINE.json names, timed the same way (graph replay, resident inputs), so
+    that the 1-GPU record holds the base of every scaling curve: configs[2] (3-layer arxiv stack), configs[3] (mag),
+    plus the default layer on the generator's uniform graph (p_intra = 0, the round-1 headline graph)."""
+    out = {}
+    for key, name, layers, pi in (("arxiv_3layer", "arxiv", 3, p_intra), ("mag", "mag", 1, p_intra),
+                                  ("arxiv_uniform_graph", "arxiv", 1, 0.0)):
+        try:
+            w = WORKLOADS[name]
+            job = SingleGpuJob(name, w, layers, dev, pi, args.seed)
+            ms, _ = cuda_timed(job.replay, max(args.steps // 2, 5), 3)
+            total = stack_bytes(w, job.n, job.nnz, layers)
+            out[key] = {"config": workload_config(name, w, job.n, job.nnz, layers, pi, 1), "ms_per_step": ms,
+                        "value": job.nnz * layers / (ms * 1e-3), "unit": "edges/s",
+                        "step_roofline_frac": total / (ms * 1e-3) / 1e9 / peak}
+            del job
+            torch.cuda.empty_cache()
+        except Exception as exc:                          # an extra must never cost the headline line
+            out[key] = {"error": repr(exc)[:300]}
+    return out
 
 
 def local_roofline(kernels, n_rows, nnz, w, peak, peak_src):
@@ -421,127 +613,202 @@ def local_roofline(kernels, n_rows, nnz, w, peak, peak_src):
         return None
 
 
-def run_multi_gpu(args, w):
-    """Row-partitioned layer over N ranks (one per GPU, NCCL): strong scaling on the same graph."""
-    import torch.distributed as dist
+class PartitionedJob:
+    """One workload row-partitioned over the ranks of the process group, next to the single-GPU model on the same
+    (full) graph - every rank builds the full graph anyway - which is the parity reference and the same-graph base of
+    the speed-up."""
 
-    import egc_b200
+    def __init__(self, args, name, w, layers, dev, p_intra):
+        import egc_b200
+        from egc_b200.dist import PartitionedGraph
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.name, self.w, self.layers, self.dev = name, w, layers, dev
+        self.n, ei = synth_graph(name, args.seed, p_intra=p_intra, blocks=8)
+        n = self.n
+        self.model = make_gpu_model(w, layers, dev, seed=args.seed)       # identical replicated parameters on every rank
+        sym = "symnorm" in w["aggrs"]
+        if w["kind"] == "edge_index":
+            self.g = egc_b200.GraphStructure.from_edge_index(ei.to(dev), n, sym, True)
+        else:
+            rowptr, col = to_adj_t(ei, n)
+            self.g = egc_b200.GraphStructure.from_csr(rowptr.to(dev), col.to(dev), None, n, sym, True)
+        self.nnz = self.g.nnz
+        self.pg = PartitionedGraph.from_global(self.g, self.rank, self.world, dev, transport=args.transport)
+        b, e = self.pg.part.row_begin, self.pg.part.row_end
+        gen = torch.Generator().manual_seed(args.seed + 1)
+        self.x_full = torch.randn(n, w["f_in"], generator=gen)
+        self.go_full = torch.randn(n, out_width(w, layers), generator=gen)
+        self.x_loc = self.x_full[b:e].to(dev).requires_grad_(True)
+        self.go_loc = self.go_full[b:e].to(dev)
+        self.x_host = self.x_loc.detach().cpu().pin_memory()
+        self.params = list(self.model.parameters())
+        self.b, self.e = b, e
+
+    def run(self, x, graph):
+        from egc_b200.dist import PartitionedGraph, partitioned_egconv
+        if self.layers == 1 and isinstance(graph, PartitionedGraph):
+            return partitioned_egconv(x, graph, self.model)
+        return self.model(x, graph)                      # EGConv on a prepared graph, or the EGC stack on either kind
+
+    def step(self):
+        out = self.run(self.x_loc, self.pg)
+        return (out,) + torch.autograd.grad(out, [self.x_loc] + self.params, self.go_loc)
+
+    def single_gpu_step(self, xs, gos):
+        out = self.run(xs, self.g)
+        return (out,) + torch.autograd.grad(out, [xs] + self.params, gos)
+
+    def parity_check(self):
+        """Rank-local out / d_x rows and the (already summed) parameter gradients of the partitioned step against the
+        single-GPU layer on the same graph, dropout off.  Max over ranks."""
+        import torch.distributed as dist
+        was = self.model.training
+        self.model.eval()
+        xs = self.x_full.to(self.dev).requires_grad_(True)
+        ref = self.single_gpu_step(xs, self.go_full.to(self.dev))
+        got = self.step()
+        self.model.train(was)
+        b, e = self.b, self.e
+        errs = [rel_err(got[0], ref[0][b:e]), rel_err(got[1], ref[1][b:e])] + [rel_err(a, r) for a, r in zip(got[2:], ref[2:])]
+        t = torch.tensor([errs[0], errs[1], max(errs[2:])], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tol_out, tol_grad = 1e-6 * self.layers, 1e-5 * self.layers
+        o, dx, dp = (float(v) for v in t)
+        return {"against": "the single-GPU layer on the same graph, parameters and inputs (max over ranks)",
+                "out": o, "d_x": dx, "param_grads": dp, "max_rel_err": max(o, dx, dp), "tol": {"out": tol_out, "grads": tol_grad},
+                "ok": bool(o < tol_out and dx < tol_grad and dp < tol_grad)}
+
+    def close(self):
+        self.pg.close()
+
+
+def time_partitioned(args, job, steps, warmup, with_e2e=True):
+    """(ms per step max over ranks, e2e ms, launches per step of this rank, single-GPU same-graph ms)."""
+    import torch.distributed as dist
     from egc_b200 import _lib
-    from egc_b200.dist import GraphedStep, PartitionedGraph, partitioned_egconv
+    from egc_b200.dist import GraphedStep
+    dev = job.dev
+    use_graph = args.transport == "peer" and not args.no_graph
+    l0 = _lib.launch_count()
+    job.step()
+    launches_per_step = _lib.launch_count() - l0
+    step = GraphedStep(job.step, warmup=2).replay if use_graph else job.step
+
+    def step_e2e():
+        with torch.no_grad():
+            job.x_loc.copy_(job.x_host, non_blocking=True)
+        res = step()
+        return float((res[0].detach() * job.go_loc).sum().item())
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = reduce_max(cuda_timed(step, steps, warmup, dist.barrier)[0])
+    ms_e2e = reduce_max(cuda_timed(step_e2e, max(3, min(steps, 10)), 2, dist.barrier)[0]) if with_e2e else None
+    job.pg.check()
+    # the single-GPU layer on the SAME graph, same launch mode, timed on every rank's own GPU at the same time
+    xs, gos = job.x_full.to(dev).requires_grad_(True), job.go_full.to(dev)
+    single = GraphedStep(lambda: job.single_gpu_step(xs, gos), warmup=2).replay if not args.no_graph else (lambda: job.single_gpu_step(xs, gos))
+    ms_single = reduce_max(cuda_timed(single, max(steps // 2, 5), 3, dist.barrier)[0])
+    return ms, ms_e2e, launches_per_step, ms_single, use_graph
+
+
+def run_multi_gpu(args, name, w):
+    """Row-partitioned layer / stack over N ranks (one per GPU, NCCL bootstrap): strong scaling on the same graph."""
+    import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    p_intra = args.locality if args.locality >= 0 else 0.8
-    n, ei = synth_graph(args.workload, args.seed, p_intra=p_intra, blocks=8)
-    torch.manual_seed(0)                                   # identical replicated parameters on every rank
-    conv = egc_b200.EGConv(w["f_in"], w["f_out"], aggrs=w["aggrs"], num_heads=w["heads"], num_bases=w["bases"]).to(dev)
-    sym = "symnorm" in w["aggrs"]
-    if w["kind"] == "edge_index":
-        g = egc_b200.GraphStructure.from_edge_index(ei.to(dev), n, sym, True)
-    else:
-        rowptr, col = to_adj_t(ei, n)
-        g = egc_b200.GraphStructure.from_csr(rowptr.to(dev), col.to(dev), None, n, sym, True)
-    nnz = g.nnz
-    pg = PartitionedGraph.from_global(g, rank, world, dev, transport=args.transport)
-    del g
-    b, e = pg.part.row_begin, pg.part.row_end
-    gen = torch.Generator().manual_seed(1)
-    x_loc = torch.randn(n, w["f_in"], generator=gen)[b:e].to(dev).requires_grad_(True)
-    go_loc = torch.randn(n, w["f_out"], generator=gen)[b:e].to(dev)
-    x_host = x_loc.detach().cpu().pin_memory()
-    params = list(conv.parameters())
-
-    def step_eager():
-        out = partitioned_egconv(x_loc, pg, conv)
-        return (out,) + torch.autograd.grad(out, [x_loc] + params, go_loc)
-
-    # One step = ONE CUDA-graph launch: projections, aggregation passes, NVLink pushes, flag signals / waits and the
-    # one-shot parameter-gradient all-reduce are all nodes of the captured graph (peer transport only).
-    use_graph = args.transport == "peer" and not args.no_graph
-    launches_per_step = None
-    if use_graph:
-        l0 = _lib.launch_count()
-        step_eager()
-        launches_per_step = _lib.launch_count() - l0
-        graphed = GraphedStep(step_eager, warmup=2)
-        step = graphed.replay
-    else:
-        step = step_eager
-
-    def step_e2e():
-        with torch.no_grad():
-            x_loc.copy_(x_host, non_blocking=True)
-        res = step()
-        return float((res[0].detach() * go_loc).sum().item())
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _lib.launch_count()
-        ev0.record()
-        for _ in range(steps):
-            fn()
-        ev1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks
-        n_launch = launches_per_step * steps if launches_per_step is not None else _lib.launch_count() - l0
-        return float(t.item()), n_launch
-
+    p_intra = default_locality(args)
+    layers = args.layers
+    job = PartitionedJob(args, name, w, layers, dev, p_intra)
+    n, nnz = job.n, job.nnz
+    parity = job.parity_check()
     with ClockSampler(dev.index or 0) as clocks:
-        ms, launches = timed(step, args.steps, args.warmup)
-        ms_e2e, _ = timed(step_e2e, max(3, min(args.steps, 10)), 2)
-    pg.check()
+        ms, ms_e2e, launches_per_step, ms_single, use_graph = time_partitioned(args, job, args.steps, args.warmup)
     # per-kernel CUDA-event times of rank 0 (eager launches, separate pass; waits include the time spent on peers)
-    _lib.profile_enable(True)
-    for _ in range(args.steps):
-        step_eager()
-    torch.cuda.synchronize()
-    prof = _lib.profile_collect()
-    _lib.profile_enable(False)
-    kernels = {k: {"launches_per_step": c / args.steps, "ms_per_step": t / args.steps} for k, (c, t) in prof.items()}
-    local_rows = int(pg.part.n_local)
-    local_nnz = int(getattr(pg.graph, "nnz", 0)) if hasattr(pg, "graph") else 0
-    stats = torch.tensor([pg.part.n_halo, pg.part.n_local, pg.part.interior_rows.numel(), launches], device=dev,
-                         dtype=torch.float64)
+    prof, kernels = traced_kernels(job.step, args.steps)
+    pg = job.pg
+    stats = torch.tensor([pg.part.n_halo, pg.part.n_local, pg.part.interior_rows.numel(), launches_per_step * args.steps],
+                         device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(stats) for _ in range(world)]
     dist.all_gather(gathered, stats)
+    local_rows, local_nnz = int(pg.part.n_local), int(pg.graph.nnz)
+    job.close()
+    del job
+    torch.cuda.empty_cache()
+    others = None
+    if not args.no_extras and name == "arxiv" and layers == 1:
+        others = multi_gpu_extras(args, dev, p_intra)
     if rank == 0:
-        dim = w["f_out"] // w["heads"]
-        bf, bb = algorithmic_bytes(n, nnz, w["f_in"], w["heads"], w["bases"], dim, w["aggrs"])
+        total_bytes = stack_bytes(w, n, nnz, layers)
         peak, peak_src = load_peaks()
         halo_rows = sum(int(t[0]) for t in gathered)
-        bd = w["bases"] * dim
+        bd = w["bases"] * (w["f_out"] // w["heads"])
+        edges = nnz * layers
         line = {
-            "metric": "EGConv fwd+bwd edges/s", "value": nnz / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "metric": "EGConv fwd+bwd edges/s", "value": edges / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"] + f", row-partitioned over {world} GPUs (nnz-balanced, halo exchange)",
-                       "nodes": n, "nnz": nnz, "locality_p_intra": p_intra, "blocks": 8,
-                       "halo_rows_total": halo_rows, "interior_rows_total": sum(int(t[2]) for t in gathered),
-                       "nvlink_bytes_per_step": 2 * halo_rows * bd * 4,
-                       "transport": ("NVLink peer-memory kernels (posted stores + epoch flags), whole step replayed "
-                                     "from one CUDA graph" if use_graph else
-                                     ("NVLink peer-memory kernels, eager launches" if args.transport == "peer" else
-                                      "NCCL batch_isend_irecv + all_reduce, eager launches")),
-                       "l2": "no flush: working set >> L2", "algorithmic_bytes_per_step": bf + bb},
+            "config": workload_config(name, w, n, nnz, layers, p_intra, world),
+            "partition": {"scheme": f"contiguous target-row ranges over {world} GPUs (nnz-balanced), halo exchange of basis rows",
+                          "halo_rows_total": halo_rows, "interior_rows_total": sum(int(t[2]) for t in gathered),
+                          "nvlink_bytes_per_step": 2 * halo_rows * bd * 4 * layers,
+                          "transport": ("NVLink peer-memory kernels (posted stores + epoch flags), whole step replayed "
+                                        "from one CUDA graph" if use_graph else
+                                        ("NVLink peer-memory kernels, eager launches" if args.transport == "peer" else
+                                         "NCCL batch_isend_irecv + all_reduce, eager launches"))},
+            "parity_check": parity,
+            "single_gpu_same_graph": {"ms_per_step": ms_single, "speedup": ms_single / ms,
+                                      "note": "the single-GPU layer on the same graph, same launch mode, same box"},
             "clocks": clocks.summary(),
-            "e2e": {"value": nnz / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+            "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": n * w["f_in"] * 4, "d2h_bytes_per_step": 4 * world},
             "gpu_launches": sum(int(t[3]) for t in gathered),
-            "step_roofline": {"achieved": (bf + bb) / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
-                              "frac": (bf + bb) / (ms * 1e-3) / 1e9 / (peak * world), "peak_source": peak_src + f" x {world}"},
-            "roofline": local_roofline(kernels, local_rows, local_nnz, w, peak, peak_src), "cpu_baseline": None,
-            "kernels_rank0": kernels,
+            "step_roofline": {"achieved": total_bytes / (ms * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                              "frac": total_bytes / (ms * 1e-3) / 1e9 / (peak * world), "peak_source": peak_src + f" x {world}"},
+            "roofline": local_roofline(kernels, local_rows, local_nnz, w, peak, peak_src) if layers == 1 else None,
+            "cpu_baseline": None, "kernels_rank0": kernels,
         }
+        if others is not None:
+            line["other_configs"] = others
         print(json.dumps(line))
-    pg.close()
     dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.exit(f"bench.py: the partitioned step differs from the single-GPU layer beyond the bar: {parity}")
+
+
+def multi_gpu_extras(args, dev, p_intra):
+    """configs[2] (3-layer arxiv stack) and configs[3] (mag) partitioned over the same ranks: time, same-graph
+    single-GPU time and parity, so the scaling record covers the configurations BASELINE.json names."""
+    import torch.distributed as dist
+    out = {}
+    for key, name, layers in (("arxiv_3layer", "arxiv", 3), ("mag", "mag", 1)):
+        job = None
+        try:
+            w = WORKLOADS[name]
+            job = PartitionedJob(args, name, w, layers, dev, p_intra)
+            parity = job.parity_check()
+            ms, _, _, ms_single, _ = time_partitioned(args, job, max(args.steps // 2, 5), 3, with_e2e=False)
+            out[key] = {"config": workload_config(name, w, job.n, job.nnz, layers, p_intra, dist.get_world_size()),
+                        "ms_per_step": ms, "value": job.nnz * layers / (ms * 1e-3), "unit": "edges/s",
+                        "single_gpu_same_graph": {"ms_per_step": ms_single, "speedup": ms_single / ms},
+                        "parity_check": parity}
+        except Exception as exc:
+            out[key] = {"error": repr(exc)[:300]}
+        finally:
+            if job is not None:
+                try:
+                    job.close()
+                except Exception:
+                    pass
+            del job
+            torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -934,15 +1201,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="arxiv", choices=sorted(WORKLOADS) + sorted(MINIBATCH) + ["rmag"])
+    ap.add_argument("--layers", type=int, default=1,
+                    help="full-graph workloads: 1 = one EGConv layer (configs[1] / [3]); >= 2 = the reference's EGC stack (configs[2] uses 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the `other_configs` object (3-layer arxiv stack, mag, uniform graph) of the default run")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo exchange: our NVLink peer-memory kernels (default) or the NCCL baseline")
-    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--bwd-flags", type=int, default=0, help="EGC_BWD_* tuning bits passed to egc_aggregate_bwd (A/B runs)")
     ap.add_argument("--locality", type=float, default=-1.0,
-                    help="p_intra of the synthetic generator (default: 0 on one GPU, 0.8 when row-partitioned)")
+                    help="p_intra of the synthetic generator (default 0.8 with 8 id blocks, for every GPU count)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -963,21 +1234,21 @@ def main():
             run_minibatch(args, MINIBATCH[args.workload])
         return
     w = WORKLOADS[args.workload]
+    if args.layers < 1:
+        sys.exit("--layers must be >= 1")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        n, ei = synth_graph(args.workload, args.seed)
-        run_reference_arm(args, w, n, ei)
+        run_reference_arm(args, args.workload, w)
         return
 
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", 1)) > 1:
         if "RANK" not in os.environ:
             sys.exit("multi-GPU runs are launched with torch.distributed.run (see the module docstring)")
-        run_multi_gpu(args, w)
+        run_multi_gpu(args, args.workload, w)
         return
-    n, ei = synth_graph(args.workload, args.seed, p_intra=max(args.locality, 0.0), blocks=8)
-    run_single_gpu(args, w, n, ei)
+    run_single_gpu(args, args.workload, w)
 
 
 if __name__ == "__main__":

@@ -170,6 +170,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   p.bases = bases; p.weightings = weightings; p.bias = bias;
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
+  L2Window l2win(st, bases, static_cast<size_t>(desc->n_src) * bd * sizeof(float), (l2_persist_mask() & 1) != 0);
+  p.l2_window = l2win.on_ ? 1 : 0;
   const bool want_arg = (arg_out != nullptr || saved_arg != nullptr) && n_arg > 0;
   if (arg_out != nullptr && !want_arg && row_subset == nullptr)   // no min/max slot: every arg is "none"
     EGC_CUDA(cudaMemsetAsync(arg_out, 0xff, static_cast<size_t>(desc->n_dst) * desc->n_aggr * bd * sizeof(int32_t), st));
@@ -245,7 +247,9 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int hab = desc->heads * desc->n_aggr * desc->bases;
   const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(d_bases) && aligned16(workspace);
 
-  if (L.has_route || L.tsmask == 0)
+  // Pass 2 writes every row of d_bases (empty columns included), so the routed min/max gradients are ADDED afterwards:
+  // no memset and no read-modify-write of d_bases in pass 2.  Without linear streams there is no pass 2: zero first.
+  if (L.tsmask == 0)
     EGC_CUDA(cudaMemsetAsync(d_bases, 0, static_cast<size_t>(desc->n_src) * bd * sizeof(float), st));
 
   // Target-side stream layout.  When the streams together overflow the L2 but one of them fits, they are stored
@@ -353,25 +357,6 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     }
   }
 
-  // ---- min/max routing (feature-slab-major atomics)
-  if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
-    RouteParams r{};
-    r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
-    r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);
-    // hubs = the long columns of the CSC plan (more than EGC_CHUNK_EDGES entries), privatised per CTA
-    r.n_hubs = (csc_plan != nullptr && !(flags & EGC_BWD_NO_HUB_PRIVATISATION)) ? std::min(csc_plan->n_long, kRouteMaxHubs) : 0;
-    r.hubs = r.n_hubs > 0 ? csc_plan->long_rows : nullptr;
-    const int row_groups = ceil_div(desc->n_dst, kRouteRows);
-    const int grid = std::max(1, std::min(ceil_div(row_groups, kRouteThreads / 32), sm_count()));
-    const int smem = r.n_hubs > 0 ? 2 * kRouteHashSize * static_cast<int>(sizeof(int)) + r.n_hubs * 32 * static_cast<int>(sizeof(float)) : 0;
-    if (smem > 48 * 1024) EGC_CUDA(cudaFuncSetAttribute(k_route_minmax, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    {
-      LaunchScope egc_ls_("k_route_minmax", st);
-      k_route_minmax<<<grid, kRouteThreads, smem, st>>>(r);
-    }
-    EGC_LAUNCH_CHECK("k_route_minmax");
-  }
-
   // ---- pass 2: per source column (CSC), atomic-free
   if (L.tsmask != 0) {
     AggParams geo{};
@@ -401,6 +386,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       s.long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(task_counter) - counters_bytes);
     if (col_blocks) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, counters_bytes + sizeof(int), st));
     else if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
+    L2Window l2win(st, tstreams, L.ts_bytes, (l2_persist_mask() & 2) != 0);
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
@@ -409,7 +395,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     s.off_sym = L.ts_sym < 0 ? 0 : (stream_major ? L.ts_sym * table : static_cast<int64_t>(L.ts_sym) * bd);
     s.off_lin = L.ts_lin < 0 ? 0 : (stream_major ? L.ts_lin * table : static_cast<int64_t>(L.ts_lin) * bd);
     s.off_sq = L.ts_sq < 0 ? 0 : (stream_major ? L.ts_sq * table : static_cast<int64_t>(L.ts_sq) * bd);
-    bool accumulate = L.has_route;
+    bool accumulate = false;                           // the routed gradients are added after this pass
     if (slab_w > 0) {
       s.slab_w = slab_w;
       s.n_slabs = bd / slab_w;
@@ -435,6 +421,25 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       }
       accumulate = true;
     }
+  }
+
+  // ---- min/max routing (feature-slab-major atomics), added on top of pass 2's result
+  if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
+    RouteParams r{};
+    r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
+    r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);
+    // hubs = the long columns of the CSC plan (more than EGC_CHUNK_EDGES entries), privatised per CTA
+    r.n_hubs = (csc_plan != nullptr && !(flags & EGC_BWD_NO_HUB_PRIVATISATION)) ? std::min(csc_plan->n_long, kRouteMaxHubs) : 0;
+    r.hubs = r.n_hubs > 0 ? csc_plan->long_rows : nullptr;
+    const int row_groups = ceil_div(desc->n_dst, kRouteRows);
+    const int grid = std::max(1, std::min(ceil_div(row_groups, kRouteThreads / 32), sm_count()));
+    const int smem = r.n_hubs > 0 ? 2 * kRouteHashSize * static_cast<int>(sizeof(int)) + r.n_hubs * 32 * static_cast<int>(sizeof(float)) : 0;
+    if (smem > 48 * 1024) EGC_CUDA(cudaFuncSetAttribute(k_route_minmax, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    {
+      LaunchScope egc_ls_("k_route_minmax", st);
+      k_route_minmax<<<grid, kRouteThreads, smem, st>>>(r);
+    }
+    EGC_LAUNCH_CHECK("k_route_minmax");
   }
 
   if (!fuse_colsum) {

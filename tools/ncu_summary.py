@@ -2,7 +2,10 @@
 """Summarise an `ncu --set full` report: one CSV row per captured launch + the per-kernel DRAM traffic
 JSON that bench.py reports as `roofline.traffic`.
 
-    python tools/ncu_summary.py gpurun_out/r01c_full.ncu-rep profiles/r01c_ncu_full_summary.csv [profiles/r01_dram_traffic.json]
+    python tools/ncu_summary.py gpurun_out/r02a_full.ncu-rep profiles/r02a_ncu_full_summary.csv [profiles/r02_dram_traffic.json arxiv]
+
+The traffic JSON is keyed by workload ({"arxiv": {kernel: bytes}, "mag": {...}}): the capture of one workload only
+updates its own entry.
 """
 import csv
 import io
@@ -26,6 +29,7 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 def main():
     rep, out_csv = sys.argv[1], sys.argv[2]
     out_json = sys.argv[3] if len(sys.argv) > 3 else None
+    workload = sys.argv[4] if len(sys.argv) > 4 else "arxiv"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -43,7 +47,12 @@ def main():
                 if frag in r[ki]:
                     traffic.setdefault(key, []).append(b)
     if out_json:
-        json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open(out_json, "w"), indent=1)
+        try:
+            table = json.load(open(out_json))
+        except Exception:
+            table = {}
+        table[workload] = {k: sum(v) / len(v) for k, v in traffic.items()}
+        json.dump(table, open(out_json, "w"), indent=1)
     print(open(out_csv).read())
 
 
