@@ -10,7 +10,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libegc_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 EGC_MAX_AGGR = 8
 EGC_CHUNK_EDGES = 256
 META_SLOTS = 8
@@ -65,7 +65,7 @@ SIGNATURES = {
     "egc_aggregate_fwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, _P, c_int32,
                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
-    "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
+    "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
                                     _P, _P, _P, _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "egc_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), _P]),

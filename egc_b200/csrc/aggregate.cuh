@@ -65,7 +65,6 @@ struct AggParams {
   // per-warp shared memory layout (float offsets)
   int sm_agg, sm_w, sm_per_warp;
   int mode;      // 0: chunk tasks then row tasks, 1: merge tasks (one per long row)
-  int l2_window; // a persisting-L2 access-policy window covers `bases` (EGC_L2_PERSIST): gathers carry no eviction hint
 };
 
 // ---------------------------------------------------------------------------------------------

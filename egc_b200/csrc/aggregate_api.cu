@@ -68,6 +68,7 @@ static int validate_plan(const egc_row_plan* plan, const char* who) {
 
 #include "backward_pass1.cuh"
 #include "backward_pass2.cuh"
+#include "backward_route.cuh"
 
 namespace egc {
 
@@ -170,8 +171,6 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   p.bases = bases; p.weightings = weightings; p.bias = bias;
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
-  L2Window l2win(st, bases, static_cast<size_t>(desc->n_src) * bd * sizeof(float), (l2_persist_mask() & 1) != 0);
-  p.l2_window = l2win.on_ ? 1 : 0;
   const bool want_arg = (arg_out != nullptr || saved_arg != nullptr) && n_arg > 0;
   if (arg_out != nullptr && !want_arg && row_subset == nullptr)   // no min/max slot: every arg is "none"
     EGC_CUDA(cudaMemsetAsync(arg_out, 0xff, static_cast<size_t>(desc->n_dst) * desc->n_aggr * bd * sizeof(int32_t), st));
@@ -214,7 +213,7 @@ size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
 }
 
 int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
-                      const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
+                      const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
                       float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum, int32_t flags,
@@ -224,10 +223,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
               "egc_aggregate_bwd: null pointer");
   const BwdLayout L = bwd_layout(*desc, csc_plan);
-  if ((flags & EGC_BWD_DETERMINISTIC) && L.has_route) {
-    set_error("egc_aggregate_bwd: EGC_BWD_DETERMINISTIC routing of min/max gradients is not built yet");
-    return EGC_ERR_UNSUPPORTED;
-  }
+  const bool det_route = (flags & EGC_BWD_DETERMINISTIC) != 0 && L.has_route;
+  EGC_REQUIRE(!det_route || csr2csc != nullptr, "egc_aggregate_bwd: EGC_BWD_DETERMINISTIC needs csr2csc");
   const int mask = prim_mask_of(*desc);
   const int n_arg = n_arg_slots(*desc);
   EGC_REQUIRE(n_arg == 0 || saved_arg != nullptr, "egc_aggregate_bwd: saved_arg required for min/max");
@@ -386,7 +383,6 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       s.long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(task_counter) - counters_bytes);
     if (col_blocks) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, counters_bytes + sizeof(int), st));
     else if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
-    L2Window l2win(st, tstreams, L.ts_bytes, (l2_persist_mask() & 2) != 0);
     s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
     s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
     s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
@@ -424,7 +420,23 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   }
 
   // ---- min/max routing (feature-slab-major atomics), added on top of pass 2's result
-  if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
+  if (det_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
+    const bool route_vec4 = vec4 && aligned16(saved_arg) && aligned16(t_route);
+    AggParams geo{};
+    fill_agg_params(geo, *desc, route_vec4);
+    RouteCscParams r{};
+    r.colptr = colptr; r.rowidx = rowidx; r.csr2csc = csr2csc; r.csc_val_lin = csc_val_lin; r.n_cols = desc->n_src;
+    r.n_long = csc_plan ? csc_plan->n_long : 0;
+    r.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
+    r.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
+    r.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
+    r.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
+    r.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
+    r.partials = csc_part;                     // pass 2 is done with its chunk partials
+    r.saved_arg = saved_arg; r.t_route = t_route; r.d_bases = d_bases;
+    r.n_arg = n_arg; r.BD = bd; r.nvec = geo.nvec; r.G = geo.G; r.n_pass = geo.n_pass;
+    if (int rc = launch_route_csc(r, route_vec4, st)) return rc;
+  } else if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
     RouteParams r{};
     r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
     r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
   const int foff = min(li, GC::nvec(p) - 1) * 4;                     // idle lanes shadow the last piece, never write
   const float* __restrict__ src = p.bases + foff;
   const uint32_t BD = static_cast<uint32_t>(GC::BD(p));
-  const uint64_t pol_keep = p.l2_window ? l2_policy_normal() : l2_policy_keep(), pol_stream = l2_policy_stream();
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   using AccT = Acc<MASK, 4, false, ARG>;
   const bool stage_w = p.out != nullptr;
 

@@ -51,50 +51,6 @@ LaunchScope::~LaunchScope() {
   if (slot_ < static_cast<int>(g_prof_records.size())) cudaEventRecord(g_prof_records[slot_].stop, st_);
 }
 
-int l2_persist_mask() {
-  static const int mask = [] { const char* e = getenv("EGC_L2_PERSIST"); return e ? atoi(e) : 0; }();
-  return mask;
-}
-
-static size_t l2_set_aside() {
-  static size_t cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-  if (cached[dev] == 0) {
-    int max_persist = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    size_t want = static_cast<size_t>(max_persist > 0 ? max_persist : 0);
-    if (const char* cap = getenv("EGC_L2_PERSIST_MB")) want = std::min(want, static_cast<size_t>(atoi(cap)) << 20);
-    if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); want = 1; }
-    cached[dev] = want;
-  }
-  return cached[dev] > 1 ? cached[dev] : 0;
-}
-
-L2Window::L2Window(cudaStream_t st, const void* base, size_t bytes, bool enable) : st_(st), on_(false) {
-  if (!enable || base == nullptr || bytes == 0) return;
-  const size_t aside = l2_set_aside();
-  if (aside == 0) return;
-  int max_window = 0, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-  cudaStreamAttrValue v{};
-  v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-  v.accessPolicyWindow.num_bytes = std::min(bytes, static_cast<size_t>(max_window > 0 ? max_window : 0));
-  v.accessPolicyWindow.hitRatio = std::min(1.0f, static_cast<float>(aside) / static_cast<float>(bytes));
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) on_ = true;
-  else cudaGetLastError();
-}
-
-L2Window::~L2Window() {
-  if (!on_) return;
-  cudaStreamAttrValue v{};
-  v.accessPolicyWindow.num_bytes = 0;
-  if (cudaStreamSetAttribute(st_, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-}
-
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

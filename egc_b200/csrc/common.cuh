@@ -77,16 +77,4 @@ struct LaunchScope {
   int slot_;
 };
 
-// Persisting-L2 access-policy window over [base, base + bytes) for the launches issued on `st` while the object
-// lives (experiment switch, env EGC_L2_PERSIST: bit 0 forward gather table, bit 1 backward t-streams).  The device's
-// persisting set-aside is raised to its maximum on first use; hitRatio = set-aside / bytes (capped at 1), so the
-// part of the table that fits is pinned and the rest streams.  A no-op when disabled or when the runtime refuses.
-struct L2Window {
-  L2Window(cudaStream_t st, const void* base, size_t bytes, bool enable);
-  ~L2Window();
-  cudaStream_t st_;
-  bool on_;
-};
-int l2_persist_mask();     // env EGC_L2_PERSIST (cached)
-
 }  // namespace egc

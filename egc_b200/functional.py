@@ -127,7 +127,7 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
     nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
     ws = _ws(nbytes, dev)
     check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
-                                ptr(graph.rowidx), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
+                                ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
                                 graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
                                 ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags, ptr(ws), nbytes,
                                 _stream()),

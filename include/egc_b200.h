@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EGC_ABI_VERSION 3
+#define EGC_ABI_VERSION 4
 #define EGC_MAX_AGGR 8          /* len(aggrs) accepted by one layer */
 #define EGC_CHUNK_EDGES 256     /* rows longer than this are split into chunks of this many nnz */
 
@@ -223,10 +223,14 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
  *   d_bases[j] = sum_e val_sym[e] t_sym[i_e] + val_lin[e] (t_lin[i_e] + 2 bases[j] t_sq[i_e]) + routed.
  * rowptr / col / val_lin are the CSR of the forward (row nnz counts, arg -> source id); colptr / rowidx /
  * csc_val_sym / csc_val_lin its CSC view from egc_csr_transpose + egc_permute_f32 (values NULL like
- * their CSR twins).  d_bias (may be NULL) = column sums of grad_out; d_lin_colsum (may be NULL) = column sums of
+ * their CSR twins); csr2csc (egc_csr_transpose; may be NULL unless EGC_BWD_DETERMINISTIC is set and the layer has a
+ * min/max aggregator) = CSR position of every CSC entry.  The routed min/max gradients are added AFTER pass 2, which
+ * writes every row of d_bases.  d_bias (may be NULL) = column sums of grad_out; d_lin_colsum (may be NULL) = column sums of
  * d_weightings = gradient of the comb-weight bias (ref :108, :182), produced here because pass 1 has the rows in
  * registers - egc_project_bwd then takes d_b_comb = NULL.  flags: EGC_BWD_* bits. */
-#define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients through the CSC pass (no fp32 atomics) */
+#define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients with a compare-and-add gather over the CSC instead of fp32
+                                   atomics: bit-reproducible from run to run (needs csr2csc; two more gathered rows per
+                                   entry and min/max slot) */
 #define EGC_BWD_STREAM_SWEEPS 2 /* tuning: store the target-side streams stream-major and gather them in one CSC sweep each
                                    (measured slower on B200 at the arxiv shape: 0.85 vs 0.60 ms) */
 #define EGC_BWD_SKIP_ROUTING 4  /* diagnostics only: drop the min/max gradient routing (results are then incomplete) */
@@ -237,7 +241,7 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 #define EGC_BWD_NO_SLABS 64     /* tuning: never use the feature-slab layout (one interleaved sweep)                    */
 size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags);
 int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
-                      const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
+                      const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan,
                       const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
                       const float* grad_out, float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum,

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_build_info():
     lib = egc_b200.load()
-    assert lib.egc_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.egc_abi_version() == _lib.ABI_VERSION == 4
     info = lib.egc_build_info().decode()
     assert "sm_100a" in info and "chunk_edges=256" in info
 

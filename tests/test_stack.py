@@ -58,14 +58,20 @@ def test_stack_state_dict_keys_and_param_count():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", STACKS)
 @pytest.mark.parametrize("kind", ["adj_t", "edge_index"])
-def test_stack_cuda_matches_reference_golden(name, kind):
+@pytest.mark.parametrize("gemm", ["fp32_simt", "auto"])
+def test_stack_cuda_matches_reference_golden(name, kind, gemm):
     """egc_b200.EGC (CUDA kernels) against the unmodified reference stack: log-probabilities, loss, all gradients.
-    Bar: 1e-5 on the output, 4x the reference's own fp32-vs-fp64 error (at least 2e-5) on the gradients of the
-    3-layer stack - written here, and the bar actually used is part of the assertion message."""
+    Bars (the one used is part of the assertion message):
+      * exact-fp32 projections (GEMM_FP32_SIMT): 1e-5 on the output; on the gradients 1e-5 or 4x the reference's own
+        fp32-vs-fp64 error where that is larger (std's cancellation) - the single-layer bar holds through 3 layers;
+      * default tensor-core projections (3xTF32, ~2e-6 per projection): 1e-5 x layers."""
     import egc_b200
+    from egc_b200 import _lib
     rec = load_golden(name)
     dev = "cuda:0"
-    m = egc_b200.EGC(rec["hidden"], rec["layers"], 0.0, rec["heads"], rec["bases"], rec["aggrs"]).to(dev).train()
+    algo = _lib.GEMM_FP32_SIMT if gemm == "fp32_simt" else _lib.GEMM_AUTO
+    base = 1e-5 if gemm == "fp32_simt" else 1e-5 * rec["layers"]
+    m = egc_b200.EGC(rec["hidden"], rec["layers"], 0.0, rec["heads"], rec["bases"], rec["aggrs"], gemm_algo=algo).to(dev).train()
     m.load_state_dict(rec["state_dict"])
     x = rec["x"].to(dev).requires_grad_(True)
     if kind == "adj_t":
@@ -78,17 +84,18 @@ def test_stack_cuda_matches_reference_golden(name, kind):
     loss = F.nll_loss(out[idx], rec["y"].to(dev)[idx])
     params = list(m.named_parameters())
     grads = torch.autograd.grad(loss, [x] + [p for _, p in params])
-    assert rel_err(out, rec["out_f64"]) < 1e-5
-    assert abs(float(loss.detach()) - float(rec["loss_f64"])) < 1e-5 * abs(float(rec["loss_f64"]))
+    e = rel_err(out, rec["out_f64"])
+    assert e < base, f"out: {e:.3e} >= bar {base:.1e}"
+    assert abs(float(loss.detach()) - float(rec["loss_f64"])) < base * abs(float(rec["loss_f64"]))
     for (pn, g) in zip(["x"] + [n for n, _ in params], grads):
         ref64, ref32 = rec[f"grad_{pn}_f64"], rec[f"grad_{pn}_f32"]
-        bar = max(2e-5, 4.0 * rel_err(ref32, ref64))
+        bar = max(base, 4.0 * rel_err(ref32, ref64))
         e = rel_err(g, ref64)
         assert e < bar, f"grad {pn}: {e:.3e} >= bar {bar:.3e}"
-    m2 = egc_b200.EGC(rec["hidden"], rec["layers"], 0.5, rec["heads"], rec["bases"], rec["aggrs"]).to(dev).eval()
+    m2 = egc_b200.EGC(rec["hidden"], rec["layers"], 0.5, rec["heads"], rec["bases"], rec["aggrs"], gemm_algo=algo).to(dev).eval()
     m2.load_state_dict(rec["state_dict"])
     with torch.no_grad():
-        assert rel_err(m2(rec["x"].to(dev), gin), rec["out_eval_dropout_f32"]) < 1e-5
+        assert rel_err(m2(rec["x"].to(dev), gin), rec["out_eval_dropout_f32"]) < base
 
 
 @pytest.mark.gpu
