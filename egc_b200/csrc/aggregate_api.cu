@@ -106,7 +106,7 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   const size_t bd = static_cast<size_t>(d.bases) * d.dim;
   L.ts_bytes = align_up(static_cast<size_t>(d.n_dst) * std::max(L.n_ts, 1) * bd * 4, 256);
   L.csc_part_bytes = align_up(static_cast<size_t>(csc_plan ? csc_plan->n_chunks : 0) * std::max(L.n_ts, 1) * bd * 4, 256) +
-                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * kSlabMaxSlabs * sizeof(int), 256) +
+                     align_up(static_cast<size_t>(csc_plan ? csc_plan->n_long : 0) * sizeof(int), 256) +
                      256;   // + the task counter of k_scatter_cols
   // per-CTA column-sum partials of the fused pass-1 kernel, or the two-stage colsum scratch when it cannot fuse
   const size_t hd = static_cast<size_t>(d.heads) * d.dim, hab = static_cast<size_t>(d.heads) * d.n_aggr * d.bases;
@@ -217,7 +217,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
                       float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum, int32_t flags,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      int32_t col_split, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
   EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
@@ -233,6 +233,12 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_bwd: val_lin cannot be combined with symnorm");
   EGC_REQUIRE(workspace_bytes >= L.total, "egc_aggregate_bwd: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   EGC_REQUIRE(L.ts_bytes / 4 < (size_t{1} << 32), "egc_aggregate_bwd: target-side streams exceed 2^32 floats");
+  // Column phases (row-partitioned callers): HEAD = pass 1, routing and pass 2 of the source columns >= col_split (the
+  // halo columns, whose partial sums travel to their owners while ...) TAIL = pass 2 of the columns < col_split runs.
+  const bool head = (flags & EGC_BWD_COLS_HEAD) != 0, tail = (flags & EGC_BWD_COLS_TAIL) != 0;
+  EGC_REQUIRE(!(head && tail), "egc_aggregate_bwd: EGC_BWD_COLS_HEAD and EGC_BWD_COLS_TAIL are separate calls");
+  const bool split = head || tail;
+  EGC_REQUIRE(!split || (col_split >= 0 && col_split <= desc->n_src), "egc_aggregate_bwd: col_split=%d outside [0, %d]", col_split, desc->n_src);
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   float* tstreams = reinterpret_cast<float*>(ws);
@@ -243,36 +249,20 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int bd = desc->bases * desc->dim, hd = desc->heads * desc->dim;
   const int hab = desc->heads * desc->n_aggr * desc->bases;
   const bool vec4 = (bd % 4 == 0) && aligned16(bases) && aligned16(d_bases) && aligned16(workspace);
+  const bool skip_route = (flags & EGC_BWD_SKIP_ROUTING) != 0;
 
-  // Pass 2 writes every row of d_bases (empty columns included), so the routed min/max gradients are ADDED afterwards:
-  // no memset and no read-modify-write of d_bases in pass 2.  Without linear streams there is no pass 2: zero first.
-  if (L.tsmask == 0)
+  // Order of the routed min/max gradients and pass 2.  One call: pass 2 WRITES every row of d_bases (empty columns
+  // included) and the routed gradients are added afterwards - no memset, no read-modify-write in pass 2.  Column phases:
+  // the routing must be complete for the HEAD columns before the TAIL columns exist, so d_bases is zeroed, routed into,
+  // and both pass-2 launches accumulate.  No linear stream at all (min / max only): zero + route, there is no pass 2.
+  const bool route_first = split || L.tsmask == 0;
+  if (!tail && route_first && (L.has_route || L.tsmask == 0))
     EGC_CUDA(cudaMemsetAsync(d_bases, 0, static_cast<size_t>(desc->n_src) * bd * sizeof(float), st));
-
-  // Target-side stream layout.  When the streams together overflow the L2 but one of them fits, they are stored
-  // stream-major ([L][N][BD]) and pass 2 sweeps them one at a time, so every sweep gathers from an L2-resident
-  // table (the partial d_bases is re-read by the later sweeps); otherwise interleaved ([N][L][BD]), one sweep.
-  const size_t one_stream = static_cast<size_t>(desc->n_dst) * bd * sizeof(float);
-  const bool stream_major = L.n_ts >= 2 && one_stream * L.n_ts > (size_t{72} << 20) && one_stream <= (size_t{100} << 20) &&
-                            (flags & EGC_BWD_STREAM_SWEEPS) != 0;
-
-  // Feature-slab layout ([slab][N][L][W], see k_scatter_slab): an opt-in tuning layout, EGC_BWD_SLAB16 / SLAB32 pick the
-  // width; the default (and EGC_BWD_NO_SLABS) is the plain interleaved layout.
-  int slab_w = 0;
-  {
-    const bool eligible = vec4 && val_lin == nullptr && !stream_major && L.tsmask != 0 && (flags & EGC_BWD_NO_SLABS) == 0;
-    auto fits = [&](int w) { return bd % w == 0 && bd / w >= 2 && bd / w <= kSlabMaxSlabs; };
-    if (eligible) {
-      if ((flags & EGC_BWD_SLAB32) && fits(32)) slab_w = 32;
-      else if ((flags & EGC_BWD_SLAB16) && fits(16)) slab_w = 16;
-      // No automatic choice any more: measured on B200 (profiles/r01e_bwd_layouts.txt) the column-block kernel on the
-      // plain interleaved layout beats every slab layout (arxiv shape 0.49 vs 0.60 ms, mag shape 0.39 vs 0.54 ms).
-    }
-  }
+  const bool pass2_accumulates = route_first && L.has_route;
 
   // ---- pass 1: streaming over target nodes
   bool fuse_colsum = false;
-  {
+  if (!tail) {
     CombineBwdParams c{};
     c.rowptr = rowptr; c.col = col; c.val_lin = val_lin; c.n_rows = desc->n_dst;
     c.weightings = weightings; c.grad_out = grad_out; c.saved = saved; c.saved_arg = saved_arg;
@@ -296,16 +286,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     c.sm_per_warp = off;
     const int smem = (off * kAggWarps + 3 * hab) * static_cast<int>(sizeof(float));    // staging areas + index tables
     EGC_REQUIRE(smem <= 200 * 1024, "egc_aggregate_bwd: layer too wide for the shared-memory staging (%d bytes)", smem);
-    c.ts_row_stride = stream_major ? bd : static_cast<int64_t>(L.n_ts) * bd;
-    c.ts_stream_stride = stream_major ? static_cast<int64_t>(desc->n_dst) * bd : bd;
-    c.ts_slab_w = bd;
-    c.ts_slab_stride = 0;
-    if (slab_w > 0) {
-      c.ts_row_stride = static_cast<int64_t>(L.n_ts) * slab_w;
-      c.ts_stream_stride = slab_w;
-      c.ts_slab_w = slab_w;
-      c.ts_slab_stride = static_cast<int64_t>(desc->n_dst) * L.n_ts * slab_w;
-    }
+    c.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;       // interleaved: [n_dst][n_ts][BD]
+    c.ts_stream_stride = bd;
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
                aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
@@ -315,7 +297,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     fuse_colsum = (d_bias != nullptr || d_lin_colsum != nullptr) && hab <= 32 * kCbColIt &&
                   hd <= 32 * kCbColIt * (ev4 ? 4 : 1);
     c.colsum_part = fuse_colsum ? static_cast<float*>(colsum_ws) : nullptr;
-    c.skip_route = (flags & EGC_BWD_SKIP_ROUTING) ? 1 : 0;
+    c.skip_route = skip_route ? 1 : 0;
     c.t_route = t_route;
 #define EGC_LAUNCH_COMBINE_CFG(CFG, EV, LW)                                                                    \
     {                                                                                                          \
@@ -354,89 +336,26 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     }
   }
 
-  // ---- pass 2: per source column (CSC), atomic-free
-  if (L.tsmask != 0) {
-    AggParams geo{};
-    fill_agg_params(geo, *desc, vec4);
-    ScatterParams s{};
-    s.colptr = colptr; s.rowidx = rowidx; s.val_sym = csc_val_sym; s.val_lin = csc_val_lin; s.n_cols = desc->n_src;
-    s.n_long = csc_plan ? csc_plan->n_long : 0;
-    s.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
-    s.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
-    s.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
-    s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
-    s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
-    s.partials = csc_part;
-    const bool fuse_merge = (geo.n_pass == 1 || slab_w > 0) && s.n_long > 0;
-    s.long_counter = fuse_merge ? reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
-                                                        align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256))
-                                : nullptr;
-    // column-block kernel: 128-bit pieces, unweighted entries, one pass, interleaved streams
-    // (EGC_BWD_WARP_PER_COLUMN=1 keeps the warp-per-column kernel)
-    static const bool legacy_cols = getenv("EGC_BWD_WARP_PER_COLUMN") != nullptr;
-    const bool col_blocks = vec4 && val_lin == nullptr && !stream_major && slab_w == 0 && geo.n_pass == 1 &&
-                            (geo.G == 32 || geo.G == 16) && !legacy_cols;
-    const size_t counters_bytes = align_up(static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), 256);
-    int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) +
-                                               align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256) + counters_bytes);
-    if (col_blocks && s.long_counter == nullptr)
-      s.long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(task_counter) - counters_bytes);
-    if (col_blocks) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, counters_bytes + sizeof(int), st));
-    else if (fuse_merge) EGC_CUDA(cudaMemsetAsync(s.long_counter, 0, static_cast<size_t>(s.n_long) * kSlabMaxSlabs * sizeof(int), st));
-    s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
-    s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
-    s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
-    const int64_t table = static_cast<int64_t>(desc->n_dst) * bd;
-    s.ts_row_stride = stream_major ? bd : static_cast<int64_t>(L.n_ts) * bd;
-    s.off_sym = L.ts_sym < 0 ? 0 : (stream_major ? L.ts_sym * table : static_cast<int64_t>(L.ts_sym) * bd);
-    s.off_lin = L.ts_lin < 0 ? 0 : (stream_major ? L.ts_lin * table : static_cast<int64_t>(L.ts_lin) * bd);
-    s.off_sq = L.ts_sq < 0 ? 0 : (stream_major ? L.ts_sq * table : static_cast<int64_t>(L.ts_sq) * bd);
-    bool accumulate = false;                           // the routed gradients are added after this pass
-    if (slab_w > 0) {
-      s.slab_w = slab_w;
-      s.n_slabs = bd / slab_w;
-      s.slab_stride = static_cast<int64_t>(desc->n_dst) * L.n_ts * slab_w;
-      s.routed = accumulate ? 1 : 0;
-      s.mode = 0;
-      if (int rc = slab_w == 32 ? launch_scatter_slab<32>(s, L.tsmask, st) : launch_scatter_slab<16>(s, L.tsmask, st)) return rc;
-      EGC_LAUNCH_CHECK("k_scatter_slab");
-    } else if (col_blocks) {
-      s.routed = accumulate ? 1 : 0;
-      s.mode = 0;
-      if (int rc = geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st)) return rc;
-    } else
-    for (int bit = 1; bit <= 4; bit <<= 1) {
-      const int sweep_mask = stream_major ? (L.tsmask & bit) : (bit == 1 ? L.tsmask : 0);
-      if (sweep_mask == 0) continue;
-      s.routed = accumulate ? 1 : 0;
-      s.mode = 0;
-      if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
-      if (s.n_long > 0 && !fuse_merge) {
-        s.mode = 1;
-        if (int rc = launch_scatter(s, sweep_mask, vec4, val_lin != nullptr, st)) return rc;
-      }
-      accumulate = true;
+  // ---- min/max routing: fp32 atomics in feature-slab order (default) or the CSC compare-and-add gather (deterministic)
+  auto route = [&]() -> int {
+    if (!L.has_route || skip_route) return EGC_OK;
+    if (det_route) {
+      const bool route_vec4 = vec4 && aligned16(saved_arg) && aligned16(t_route);
+      AggParams geo{};
+      fill_agg_params(geo, *desc, route_vec4);
+      RouteCscParams r{};
+      r.colptr = colptr; r.rowidx = rowidx; r.csr2csc = csr2csc; r.csc_val_lin = csc_val_lin; r.n_cols = desc->n_src;
+      r.n_long = csc_plan ? csc_plan->n_long : 0;
+      r.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
+      r.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
+      r.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
+      r.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
+      r.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
+      r.partials = csc_part;                     // not in use by pass 2 while the routing runs (stream order)
+      r.saved_arg = saved_arg; r.t_route = t_route; r.d_bases = d_bases;
+      r.n_arg = n_arg; r.BD = bd; r.nvec = geo.nvec; r.G = geo.G; r.n_pass = geo.n_pass;
+      return launch_route_csc(r, route_vec4, st);
     }
-  }
-
-  // ---- min/max routing (feature-slab-major atomics), added on top of pass 2's result
-  if (det_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
-    const bool route_vec4 = vec4 && aligned16(saved_arg) && aligned16(t_route);
-    AggParams geo{};
-    fill_agg_params(geo, *desc, route_vec4);
-    RouteCscParams r{};
-    r.colptr = colptr; r.rowidx = rowidx; r.csr2csc = csr2csc; r.csc_val_lin = csc_val_lin; r.n_cols = desc->n_src;
-    r.n_long = csc_plan ? csc_plan->n_long : 0;
-    r.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
-    r.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
-    r.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
-    r.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
-    r.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
-    r.partials = csc_part;                     // pass 2 is done with its chunk partials
-    r.saved_arg = saved_arg; r.t_route = t_route; r.d_bases = d_bases;
-    r.n_arg = n_arg; r.BD = bd; r.nvec = geo.nvec; r.G = geo.G; r.n_pass = geo.n_pass;
-    if (int rc = launch_route_csc(r, route_vec4, st)) return rc;
-  } else if (L.has_route && !(flags & EGC_BWD_SKIP_ROUTING)) {
     RouteParams r{};
     r.saved_arg = saved_arg; r.t_route = t_route; r.col = col; r.val_lin = val_lin; r.d_bases = d_bases;
     r.n_rows = desc->n_dst; r.n_arg = n_arg; r.BD = bd; r.n_slabs = ceil_div(bd, 32);
@@ -452,9 +371,66 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
       k_route_minmax<<<grid, kRouteThreads, smem, st>>>(r);
     }
     EGC_LAUNCH_CHECK("k_route_minmax");
+    return EGC_OK;
+  };
+  if (!tail && route_first) {
+    if (int rc = route()) return rc;
   }
 
-  if (!fuse_colsum) {
+  // ---- pass 2: per source column (CSC), atomic-free
+  if (L.tsmask != 0) {
+    AggParams geo{};
+    fill_agg_params(geo, *desc, vec4);
+    ScatterParams s{};
+    s.colptr = colptr; s.rowidx = rowidx; s.val_sym = csc_val_sym; s.val_lin = csc_val_lin; s.n_cols = desc->n_src;
+    s.col_begin = head ? col_split : 0;
+    s.col_end = tail ? col_split : desc->n_src;
+    s.n_long = csc_plan ? csc_plan->n_long : 0;
+    s.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
+    s.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
+    s.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
+    s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
+    s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
+    s.partials = csc_part;
+    const size_t part_bytes = align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256);
+    const size_t counters_bytes = align_up(static_cast<size_t>(s.n_long) * sizeof(int), 256);
+    int* long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) + part_bytes);
+    int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(long_counter) + counters_bytes);
+    // column-block kernel: 128-bit pieces, unweighted entries, one pass, interleaved streams
+    // (EGC_BWD_WARP_PER_COLUMN=1 keeps the warp-per-column kernel)
+    static const bool legacy_cols = getenv("EGC_BWD_WARP_PER_COLUMN") != nullptr;
+    const bool col_blocks = vec4 && val_lin == nullptr && geo.n_pass == 1 && (geo.G == 32 || geo.G == 16) && !legacy_cols;
+    const bool fuse_merge = geo.n_pass == 1 && s.n_long > 0;     // the last chunk warp of a long column merges its partials
+    s.long_counter = (col_blocks || fuse_merge) ? long_counter : nullptr;
+    s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
+    s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
+    s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
+    s.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;
+    s.off_sym = L.ts_sym < 0 ? 0 : static_cast<int64_t>(L.ts_sym) * bd;
+    s.off_lin = L.ts_lin < 0 ? 0 : static_cast<int64_t>(L.ts_lin) * bd;
+    s.off_sq = L.ts_sq < 0 ? 0 : static_cast<int64_t>(L.ts_sq) * bd;
+    s.routed = pass2_accumulates ? 1 : 0;
+    s.mode = 0;
+    if (s.col_end > s.col_begin) {
+      if (col_blocks) {
+        EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes + sizeof(int), st));
+        if (int rc = geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st)) return rc;
+      } else {
+        if (fuse_merge) EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes, st));
+        if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
+        if (s.n_long > 0 && !fuse_merge) {
+          s.mode = 1;
+          if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
+        }
+      }
+    }
+  }
+
+  if (!tail && !route_first) {
+    if (int rc = route()) return rc;
+  }
+
+  if (!tail && !fuse_colsum) {
     if (d_bias != nullptr) {
       if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
     }

@@ -36,8 +36,6 @@ struct CombineBwdParams {
   int sm_w, sm_g, sm_saved, sm_arg, sm_per_warp;
   int vec16;
   int64_t ts_row_stride, ts_stream_stride;   // floats between the streams of consecutive rows / between streams of a row
-  int ts_slab_w;                             // features per slab (== BD: one slab, the plain interleaved / stream-major layouts)
-  int64_t ts_slab_stride;                    // floats between consecutive feature slabs ([slab][row][stream][ts_slab_w])
   float* colsum_part;                        // [grid][HD + HAB] or null
   int skip_route;                            // diagnostics: drop the min/max routing
   float* t_route;                            // [n_rows][n_arg][BD] gradients of the min/max slots, routed by k_route_minmax
@@ -212,10 +210,8 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
           }
         }
       }
-      // plain (L2 write-back) stores: pass 2 gathers these rows next, whatever part of them survives in the L2 is a hit.
-      // Slab layout: feature p0 lives in slab p0 / W at offset p0 % W (an EV-wide piece never straddles slabs).
-      const int slab = p0 / p.ts_slab_w;
-      float* tsp = ts + static_cast<int64_t>(slab) * p.ts_slab_stride + (p0 - slab * p.ts_slab_w);
+      // plain (L2 write-back) stores: pass 2 gathers these rows next, whatever part of them survives in the L2 is a hit
+      float* tsp = ts + p0;
       if (GB::ts_sym(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_sym(p)) * p.ts_stream_stride, t_sym);
       if (GB::ts_lin(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_lin(p)) * p.ts_stream_stride, t_lin);
       if (GB::ts_sq(p) >= 0) st_row<EV>(tsp + static_cast<int64_t>(GB::ts_sq(p)) * p.ts_stream_stride, t_sq);

@@ -1,5 +1,5 @@
 // Backward pass 2 of the fused aggregation: per source column (CSC) gathers of the target-side streams, atomic-free.
-// Column-block kernel (default), warp-per-column kernel, feature-slab variant.  Included by aggregate_api.cu only.
+// Column-block kernel (default) and the general warp-per-column kernel.  Included by aggregate_api.cu only.
 #pragma once
 
 #include "aggregate_fast.cuh"
@@ -15,6 +15,7 @@ struct ScatterParams {
   const float* val_sym;     // CSC order
   const float* val_lin;     // CSC order
   int n_cols;
+  int col_begin, col_end;   // this launch covers source columns [col_begin, col_end) (and the long columns among them)
   int n_long, n_chunks;
   const int32_t* long_rows;
   const int32_t* long_chunk_ptr;
@@ -26,14 +27,11 @@ struct ScatterParams {
   float* d_bases;           // [n_cols, BD]
   int n_ts, ts_sym, ts_lin, ts_sq;
   int64_t ts_row_stride;    // floats between the t-streams of consecutive target rows
-  int64_t off_sym, off_lin, off_sq;   // float offset of each stream inside a row (interleaved) or of its table (stream-major)
+  int64_t off_sym, off_lin, off_sq;   // float offset of each stream inside a target's row of interleaved streams
   int BD, nvec, G, n_pass;
   int routed;               // d_bases already holds a partial result (routed min/max gradients, earlier sweeps): accumulate
   int mode;
   int* long_counter;        // [n_long] zero on entry, or null: long columns are merged by a second launch (mode 1)
-  // feature-slab layout (k_scatter_slab): tstreams = [n_slabs][n_dst][n_ts][slab_w]; long_counter = [n_slabs][n_long]
-  int slab_w, n_slabs;
-  int64_t slab_stride;
 };
 
 constexpr int kScatterUnroll = 4;
@@ -48,11 +46,12 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
     if (gw < p.n_chunks) {
       chunk_id = gw;
       colj = p.chunk_row[gw];
+      if (colj < p.col_begin || colj >= p.col_end) return;
       begin = p.chunk_begin[gw];
       end = min(begin + EGC_CHUNK_EDGES, p.colptr[colj + 1]);
     } else {
-      colj = gw - p.n_chunks;
-      if (colj >= p.n_cols) return;
+      colj = p.col_begin + (gw - p.n_chunks);
+      if (colj >= p.col_end) return;
       begin = p.colptr[colj];
       end = p.colptr[colj + 1];
       if (end - begin > EGC_CHUNK_EDGES) return;
@@ -61,6 +60,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
     long_idx = gw;
     if (long_idx >= p.n_long) return;
     colj = p.long_rows[long_idx];
+    if (colj < p.col_begin || colj >= p.col_end) return;
     begin = p.colptr[colj];
     end = p.colptr[colj + 1];
   }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
 
 template <int TSMASK, int VEC, bool LINW>
 static int launch_scatter_one(const ScatterParams& p, cudaStream_t st) {
-  const int64_t tasks = p.mode == 0 ? static_cast<int64_t>(p.n_chunks) + p.n_cols : p.n_long;
+  const int64_t tasks = p.mode == 0 ? static_cast<int64_t>(p.n_chunks) + (p.col_end - p.col_begin) : p.n_long;
   if (tasks <= 0) return EGC_OK;
   {
     LaunchScope egc_ls_(p.mode ? "k_scatter_bwd_merge" : "k_scatter_bwd", st);
@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
     const int warps_total = gridDim.x * kAggWarps;
     for (int chunk_id = blockIdx.x * kAggWarps + warp; chunk_id < p.n_chunks; chunk_id += warps_total) {
       const int colj = __ldg(p.chunk_row + chunk_id);
+      if (colj < p.col_begin || colj >= p.col_end) continue;    // a long column outside this launch's range (warp-uniform)
       const int begin = __ldg(p.chunk_begin + chunk_id);
       const int end = min(begin + EGC_CHUNK_EDGES, __ldg(p.colptr + colj + 1));
       stage(begin, end);
@@ -395,13 +396,13 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
   }
 
   // =========================== phase 1: blocks of consecutive columns (dynamic) ===========================
-  const int n_blocks = (p.n_cols + kColsPerTask - 1) / kColsPerTask;
+  const int n_blocks = (p.col_end - p.col_begin + kColsPerTask - 1) / kColsPerTask;
   int task = 0;
   if (lane == 0) task = atomicAdd(task_counter, 1);
   task = __shfl_sync(kFull, task, 0);
   while (task < n_blocks) {
-    const int c0 = task * kColsPerTask;
-    const int ncols = min(kColsPerTask, p.n_cols - c0);
+    const int c0 = p.col_begin + task * kColsPerTask;
+    const int ncols = min(kColsPerTask, p.col_end - c0);
     const int cp = __ldg(p.colptr + c0 + min(lane, ncols));    // lanes 0..ncols hold the block's column pointers
     int next_task = 0;
     if (lane == 0) next_task = atomicAdd(task_counter, 1);      // consumed at the end of this task
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
 
 template <int G>
 static int launch_scatter_cols(const ScatterParams& p, int tsmask, int* task_counter, cudaStream_t st) {
-  const int n_blocks = ceil_div(p.n_cols, kColsPerTask);
+  const int n_blocks = ceil_div(p.col_end - p.col_begin, kColsPerTask);
   const int resident = (tsmask & (tsmask - 1)) == 0 ? 4 : 3;     // CTAs per SM, as the launch bounds
   const int grid = std::max(1, std::min(ceil_div(std::max(n_blocks, p.n_chunks), kAggWarps), sm_count() * resident));
   {
@@ -456,232 +457,6 @@ static int launch_scatter(const ScatterParams& p, int tsmask, bool vec4, bool li
   return linw ? launch_scatter_mask<1, true>(p, tsmask, st) : launch_scatter_mask<1, false>(p, tsmask, st);
 }
 
-
-// =============================================================================================
-// backward pass 2, feature-slab variant.  When the target-side streams overflow the L2 (cfg2: 3 x 87 MB),
-// pass 1 stores them slab-major - [slab][target][stream][W floats], W = 16 or 32 - and this kernel sweeps
-// the CSC once per slab, so every sweep gathers from a table of n_dst x n_ts x W x 4 bytes that stays
-// L2-resident (cfg2, W = 16: 32.5 MB) instead of missing to HBM on nearly every entry.
-//   * persistent warps; each owns a CONTIGUOUS range of columns (and of the long columns' 256-entry chunks)
-//     of equal key mass, key = first entry + column id, found by two 32-ary searches of colptr.  Every warp
-//     does the same amount of work per slab, so the grid moves from slab to slab together, and a warp's
-//     index reads (colptr, rowidx, val_sym) are sequential;
-//   * G = W / 4 lanes cover one entry (all streams: n_ts consecutive 16-byte pieces W floats apart), the
-//     32 / G lane groups walk different entries and are merged with xor-shuffles per column;
-//   * row ids / symnorm weights of 32 consecutive entries sit in one register per lane (one coalesced load)
-//     and are broadcast with shuffles, whatever column boundaries fall inside.
-// Requires a plan whose chunks are ordered by first entry (egc_plan_build's order).
-// =============================================================================================
-constexpr int kSlabMaxSlabs = 16;
-
-// first i in [0, n] with key(i) >= target (key non-decreasing, key(n) = +inf): 32 probes per round
-template <class KeyF>
-__device__ __forceinline__ int warp_lower_bound(KeyF key, int n, int64_t target, int lane) {
-  int lo = 0, hi = n;                                   // the answer lies in [lo, hi]
-  while (lo < hi) {
-    const int step = (hi - lo + 31) >> 5;
-    const int probe = lo + lane * step;
-    const bool ge = probe >= hi || key(probe) >= target;
-    const unsigned m = __ballot_sync(kFull, ge);
-    const int f = m != 0u ? __ffs(m) - 1 : 32;          // first probe at or past the target
-    if (f == 0) {
-      hi = lo;
-    } else {
-      const int nlo = lo + (f - 1) * step + 1, nhi = min(lo + f * step, hi);
-      lo = nlo;
-      hi = nhi;
-    }
-  }
-  return lo;
-}
-
-template <int TSMASK, int W>
-__global__ void __launch_bounds__(kAggThreads, 4) k_scatter_slab(const __grid_constant__ ScatterParams p) {
-  constexpr int G = W / 4, NG = 32 / G;
-  constexpr int NS = ((TSMASK & 1) ? 1 : 0) + ((TSMASK & 2) ? 1 : 0) + ((TSMASK & 4) ? 1 : 0);
-  constexpr int U = NS >= 2 ? 2 : 4;
-  constexpr int BATCH = U * NG;
-  static_assert(BATCH <= 32, "one batch must fit the 32-entry index buffer");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kAggWarps + warp, warps_total = gridDim.x * kAggWarps;
-  const int g = lane / G, foff = (lane & (G - 1)) * 4;
-  const int nnz = __ldg(p.colptr + p.n_cols);
-
-  // ---- this warp's share: keys [k_begin, k_end) of the (first entry + column id) axis
-  const int64_t total_key = static_cast<int64_t>(nnz) + p.n_cols;
-  const int64_t q = (total_key + warps_total - 1) / warps_total;
-  const int64_t k_begin = q * gw, k_end = k_begin + q;
-  auto col_key = [&](int c) { return static_cast<int64_t>(__ldg(p.colptr + c)) + c; };
-  const int c_lo = warp_lower_bound(col_key, p.n_cols, k_begin, lane);
-  const int c_hi = warp_lower_bound(col_key, p.n_cols, k_end, lane);
-  int k_lo = 0, k_hi = 0;
-  if (p.n_chunks > 0) {
-    auto chunk_key = [&](int k) { return static_cast<int64_t>(__ldg(p.chunk_begin + k)) + __ldg(p.chunk_row + k); };
-    k_lo = warp_lower_bound(chunk_key, p.n_chunks, k_begin, lane);
-    k_hi = warp_lower_bound(chunk_key, p.n_chunks, k_end, lane);
-  }
-  const int n_my_chunks = k_hi - k_lo, n_my = n_my_chunks + (c_hi - c_lo);
-  if (n_my == 0) return;
-
-  const uint64_t pol_keep = l2_policy_keep();
-  const uint32_t row_stride = static_cast<uint32_t>(p.n_ts) * W;
-  const int64_t part_stride = static_cast<int64_t>(p.n_ts) * p.BD;
-  int buf_base = -(1 << 30), my_i = 0;                   // entries [buf_base, buf_base + 32): row ids / symnorm weights
-  float my_vs = 0.f;
-  int cp_base = -(1 << 30), cp0 = 0, cp1 = 0;            // colptr of columns [cp_base, cp_base + 32] (begin / end)
-
-  for (int slab = 0; slab < p.n_slabs; ++slab) {
-    const float* __restrict__ ts = p.tstreams + static_cast<int64_t>(slab) * p.slab_stride + foff;
-    const float* __restrict__ src_sym = ts + max(p.ts_sym, 0) * W;
-    const float* __restrict__ src_lin = ts + max(p.ts_lin, 0) * W;
-    const float* __restrict__ src_sq = ts + max(p.ts_sq, 0) * W;
-    const int fcol = slab * W + foff;                    // this lane's first feature inside a [BD] row
-
-    for (int t = 0; t < n_my; ++t) {
-      int colj, begin, end, chunk_id = -1;
-      if (t < n_my_chunks) {
-        chunk_id = k_lo + t;
-        colj = __ldg(p.chunk_row + chunk_id);
-        begin = __ldg(p.chunk_begin + chunk_id);
-        end = min(begin + EGC_CHUNK_EDGES, __ldg(p.colptr + colj + 1));
-      } else {
-        colj = c_lo + (t - n_my_chunks);
-        if (colj < cp_base || colj >= cp_base + 32) {
-          cp_base = colj;
-          cp0 = __ldg(p.colptr + min(colj + lane, p.n_cols));
-          cp1 = __ldg(p.colptr + min(colj + lane + 1, p.n_cols));
-        }
-        begin = __shfl_sync(kFull, cp0, colj - cp_base);
-        end = __shfl_sync(kFull, cp1, colj - cp_base);
-        if (end - begin > EGC_CHUNK_EDGES) continue;       // long column: its chunk tasks do it
-      }
-
-      float a_sym[4] = {0.f, 0.f, 0.f, 0.f}, a_lin[4] = {0.f, 0.f, 0.f, 0.f}, a_sq[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int e0 = begin; e0 < end; e0 += BATCH) {
-        if (e0 < buf_base || e0 + BATCH > buf_base + 32) {
-          buf_base = e0;
-          const int ec = min(e0 + lane, nnz - 1);
-          my_i = __ldg(p.rowidx + ec);
-          if constexpr ((TSMASK & 1) != 0) my_vs = __ldg(p.val_sym + ec);
-        }
-        uint32_t iu[U];
-        float vsu[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int e = e0 + u * NG + g;
-          ok[u] = e < end;
-          const int sl = min(e, end - 1) - buf_base;
-          iu[u] = static_cast<uint32_t>(__shfl_sync(kFull, my_i, sl));
-          vsu[u] = 0.f;
-          if constexpr ((TSMASK & 1) != 0) vsu[u] = __shfl_sync(kFull, my_vs, sl);
-        }
-        float4 xs[U], xl[U], xq[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          xs[u] = xl[u] = xq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e0 + u * NG < end) {                         // warp-uniform: some group has a real entry in this slot
-            const size_t r = static_cast<size_t>(iu[u] * row_stride);
-            if constexpr ((TSMASK & 1) != 0) xs[u] = ldg_f4_hint(src_sym + r, pol_keep);
-            if constexpr ((TSMASK & 2) != 0) xl[u] = ldg_f4_hint(src_lin + r, pol_keep);
-            if constexpr ((TSMASK & 4) != 0) xq[u] = ldg_f4_hint(src_sq + r, pol_keep);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (ok[u]) {
-            if constexpr ((TSMASK & 1) != 0) {
-              a_sym[0] = __fadd_rn(a_sym[0], __fmul_rn(xs[u].x, vsu[u])); a_sym[1] = __fadd_rn(a_sym[1], __fmul_rn(xs[u].y, vsu[u]));
-              a_sym[2] = __fadd_rn(a_sym[2], __fmul_rn(xs[u].z, vsu[u])); a_sym[3] = __fadd_rn(a_sym[3], __fmul_rn(xs[u].w, vsu[u]));
-            }
-            if constexpr ((TSMASK & 2) != 0) { a_lin[0] += xl[u].x; a_lin[1] += xl[u].y; a_lin[2] += xl[u].z; a_lin[3] += xl[u].w; }
-            if constexpr ((TSMASK & 4) != 0) { a_sq[0] += xq[u].x; a_sq[1] += xq[u].y; a_sq[2] += xq[u].z; a_sq[3] += xq[u].w; }
-          }
-        }
-      }
-#pragma unroll
-      for (int off = G; off < 32; off <<= 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if constexpr ((TSMASK & 1) != 0) a_sym[k] += __shfl_xor_sync(kFull, a_sym[k], off);
-          if constexpr ((TSMASK & 2) != 0) a_lin[k] += __shfl_xor_sync(kFull, a_lin[k], off);
-          if constexpr ((TSMASK & 4) != 0) a_sq[k] += __shfl_xor_sync(kFull, a_sq[k], off);
-        }
-      }
-
-      const bool writer = lane < G;
-      if (chunk_id >= 0) {
-        // a chunk of a long column: publish the partial; the LAST chunk warp of (slab, column) to arrive sums all of
-        // them in chunk order and writes the column
-        if (writer) {
-          float* qd = p.partials + static_cast<int64_t>(chunk_id) * part_stride + fcol;
-          if constexpr ((TSMASK & 1) != 0) st_row<4>(qd + p.ts_sym * p.BD, a_sym);
-          if constexpr ((TSMASK & 2) != 0) st_row<4>(qd + p.ts_lin * p.BD, a_lin);
-          if constexpr ((TSMASK & 4) != 0) st_row<4>(qd + p.ts_sq * p.BD, a_sq);
-        }
-        __threadfence();
-        __syncwarp();
-        int lo = 0, hi = p.n_long;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(p.long_chunk_ptr + mid) <= chunk_id) lo = mid; else hi = mid;
-        }
-        const int c0 = __ldg(p.long_chunk_ptr + lo), c1 = __ldg(p.long_chunk_ptr + lo + 1);
-        int* counter = p.long_counter + static_cast<int64_t>(slab) * p.n_long + lo;
-        int last = 0;
-        if (lane == 0) last = atomicAdd(counter, 1) == c1 - c0 - 1 ? 1 : 0;
-        last = __shfl_sync(kFull, last, 0);
-        if (!last) continue;
-        __threadfence();
-        if (lane == 0) *counter = 0;                         // ready for the next launch
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
-        if (writer) {
-          for (int c = c0; c < c1; ++c) {
-            const float* qs = p.partials + static_cast<int64_t>(c) * part_stride + fcol;
-            float tv[4];
-            if constexpr ((TSMASK & 1) != 0) { ld_cg<4>(tv, qs + p.ts_sym * p.BD); for (int k = 0; k < 4; ++k) a_sym[k] += tv[k]; }
-            if constexpr ((TSMASK & 2) != 0) { ld_cg<4>(tv, qs + p.ts_lin * p.BD); for (int k = 0; k < 4; ++k) a_lin[k] += tv[k]; }
-            if constexpr ((TSMASK & 4) != 0) { ld_cg<4>(tv, qs + p.ts_sq * p.BD); for (int k = 0; k < 4; ++k) a_sq[k] += tv[k]; }
-          }
-        }
-      }
-      if (!writer) continue;
-      float* dst = p.d_bases + static_cast<int64_t>(colj) * p.BD + fcol;
-      float r[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.routed) ld_plain<4>(r, dst);
-      if constexpr ((TSMASK & 4) != 0) {
-        float xj[4];
-        ld_row<4>(xj, p.bases + static_cast<int64_t>(colj) * p.BD + fcol);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] += 2.f * xj[k] * a_sq[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if constexpr ((TSMASK & 1) != 0) r[k] += a_sym[k];
-        if constexpr ((TSMASK & 2) != 0) r[k] += a_lin[k];
-      }
-      st_row<4>(dst, r);
-    }
-  }
-}
-
-template <int W>
-static int launch_scatter_slab(const ScatterParams& p, int tsmask, cudaStream_t st) {
-  const int grid = sm_count() * 4;
-  LaunchScope egc_ls_("k_scatter_bwd", st);
-  switch (tsmask) {
-    case 1: k_scatter_slab<1, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 2: k_scatter_slab<2, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 3: k_scatter_slab<3, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 4: k_scatter_slab<4, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 5: k_scatter_slab<5, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 6: k_scatter_slab<6, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    case 7: k_scatter_slab<7, W><<<grid, kAggThreads, 0, st>>>(p); break;
-    default: set_error("scatter_bwd: bad stream mask %d", tsmask); return EGC_ERR_UNSUPPORTED;
-  }
-  return EGC_OK;
-}
 
 
 }  // namespace egc

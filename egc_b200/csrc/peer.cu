@@ -69,12 +69,14 @@ __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PushP
     }
   }
   if (p.slot_mask == 0u) return;
-  __threadfence_system();                       // my posted stores are visible system-wide before the flag can be
-  __syncthreads();
+  // Fused signal: the CTA barrier orders every thread's posted stores before thread 0, whose system-scope fence is
+  // cumulative over them (one fence per CTA instead of one per thread); the last CTA to count in raises the flags.
   __shared__ int s_last;
+  __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int prev = atomicAdd(p.counter, 1u);
-    s_last = prev == gridDim.x - 1 ? 1 : 0;     // every CTA has fenced its stores
+    s_last = prev == gridDim.x - 1 ? 1 : 0;
     if (s_last) { __threadfence_system(); *p.counter = 0u; }
   }
   __syncthreads();
@@ -157,6 +159,72 @@ __global__ void k_peer_sum_slots(const float* __restrict__ slots, int world, int
   float acc = 0.f;
   for (int q = 0; q < world; ++q) acc += __ldcs(slots + static_cast<int64_t>(q) * n + i);
   out[i] = acc;
+}
+
+// ---- one-shot all-reduce of a small replicated vector in ONE kernel ---------------------------------------
+// (push my vector into slot [rank] of every rank -> flags -> wait for every peer's flag -> sum the slots in rank order).
+// CTA c owns the float4 pieces c, c + gridDim.x, ...: it pushes them to every rank, and after the flags sums exactly
+// those pieces, so its own slot needs no grid-wide ordering.  All CTAs must be co-resident (grid <= number of SMs).
+struct AllReduceParams {
+  const float* src;                  // [n] my contribution
+  float* slot_of_me[EGC_MAX_PEERS];  // rank q's slot [rank] (mapped; q == rank: my own slots region)
+  const float* my_slots;             // [world][n] what the peers pushed to me
+  uint32_t* flags[EGC_MAX_PEERS];    // every rank's flag array (mapped)
+  const uint32_t* my_flags;
+  int world, rank, slot;
+  const uint32_t* epoch;
+  unsigned int* counter;             // zero on entry, zero again on exit
+  int n;                             // multiple of 4
+  float* out;                        // [n]
+  unsigned long long timeout_ns;
+  uint32_t* err;
+};
+
+__global__ void __launch_bounds__(256) k_peer_allreduce(const __grid_constant__ AllReduceParams p) {
+  const int n4 = p.n >> 2;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int i = first; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.src) + i);
+    for (int q = 0; q < p.world; ++q) reinterpret_cast<float4*>(p.slot_of_me[q])[i] = v;
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int prev = atomicAdd(p.counter, 1u);
+    s_last = prev == gridDim.x - 1 ? 1 : 0;
+    if (s_last) { __threadfence_system(); *p.counter = 0u; }
+  }
+  __syncthreads();
+  const uint32_t e = *p.epoch;
+  if (s_last && threadIdx.x < EGC_MAX_PEERS) raise_flags_of(p.flags, p.world, p.rank, 1u << p.slot, e, threadIdx.x);
+  const int q = threadIdx.x;
+  if (q < p.world && q != p.rank) {
+    const uint32_t* f = p.my_flags + p.slot * p.world + q;
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (static_cast<int32_t>(v - e) >= 0) break;
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > p.timeout_ns) {
+        atomicExch(p.err, 1u + static_cast<uint32_t>(p.slot));
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = first; i < n4; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.world; ++r) {                         // rank order: identical bits on every rank
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(p.my_slots + static_cast<int64_t>(r) * p.n) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(p.out)[i] = acc;
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -297,6 +365,32 @@ int egc_peer_reduce_rows(const float* staging, const int32_t* rows, const int32_
     k_peer_reduce_rows<<<grid, 256, 0, st>>>(staging, rows, ptr, entry, n_rows, width, into);
   }
   EGC_LAUNCH_CHECK("k_peer_reduce_rows");
+  return EGC_OK;
+}
+
+int egc_peer_allreduce(const float* src, float* const* slot_of_me, const float* my_slots, uint32_t* const* flags,
+                       const uint32_t* my_flags, int32_t world, int32_t rank, int32_t slot, const uint32_t* epoch,
+                       uint32_t* counter, int32_t n, float* out, uint64_t timeout_ns, uint32_t* err, void* stream) {
+  EGC_REQUIRE(src && slot_of_me && my_slots && flags && my_flags && epoch && counter && out && err, "egc_peer_allreduce: null pointer");
+  EGC_REQUIRE(world >= 1 && world <= EGC_MAX_PEERS && rank >= 0 && rank < world && slot >= 0 && slot < 8 && n >= 0 && n % 4 == 0,
+              "egc_peer_allreduce: world=%d rank=%d slot=%d n=%d", world, rank, slot, n);
+  if (n == 0) return EGC_OK;
+  AllReduceParams p{};
+  p.src = src; p.my_slots = my_slots; p.my_flags = my_flags; p.world = world; p.rank = rank; p.slot = slot;
+  p.epoch = epoch; p.counter = counter; p.n = n; p.out = out; p.timeout_ns = timeout_ns; p.err = err;
+  for (int q = 0; q < world; ++q) {
+    EGC_REQUIRE(slot_of_me[q] && flags[q] && aligned16(slot_of_me[q]), "egc_peer_allreduce: bad mapped pointer of rank %d", q);
+    p.slot_of_me[q] = slot_of_me[q];
+    p.flags[q] = flags[q];
+  }
+  EGC_REQUIRE(aligned16(src) && aligned16(my_slots) && aligned16(out), "egc_peer_allreduce: buffers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int grid = std::max(1, std::min(ceil_div(n / 4, 256), std::min(sm_count(), 32)));   // co-resident by construction
+  {
+    LaunchScope ls("k_peer_allreduce", st);
+    k_peer_allreduce<<<grid, 256, 0, st>>>(p);
+  }
+  EGC_LAUNCH_CHECK("k_peer_allreduce");
   return EGC_OK;
 }
 

@@ -226,6 +226,10 @@ class PartitionedGraph:
         self.exchange = CudaHaloExchange(part, self.device, group)
         self.interior = part.interior_rows.to(self.device, torch.int32)
         self.boundary = part.boundary_rows.to(self.device, torch.int32)
+        # Aggregating the interior rows while the halo rows are in flight only pays when there are enough of them:
+        # a row subset runs slower than the contiguous whole-graph launch (per-row staging), and with ~15 nnz per
+        # row and 20 % remote sources only a few rows are interior.  Below one half: wait, then ONE contiguous launch.
+        self.overlap_interior = part.interior_rows.numel() * 2 >= max(part.n_local, 1)
         self.group = group
         self._peer_ctx = {}
 
@@ -282,20 +286,26 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             _, weightings = F.project(x, bases_weight.contiguous(), comb_weight.contiguous(), comb_bias, sigmoid, algo,
                                       bases_out=bases_ext[:part.n_local])
             outs = F.alloc_aggregate_outputs(desc, x.device, want_out=True, want_saved=needs_grad)
+            def interior():
+                if pg.overlap_interior:
+                    F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
+                                        outputs=outs)
+
             if peer is not None:
                 peer.push_forward()                        # posted stores into the peers' halo regions, then FWD flag
-                F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
-                                    outputs=outs)
+                interior()
                 peer.wait(P.SLOT_FWD)
             else:
                 # halo exchange runs on the communication stream while interior rows are aggregated here
                 halo, handle = pg.exchange.start_forward(bases_ext[:part.n_local])
-                F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
-                                    outputs=outs)
+                interior()
                 pg.exchange.finish(handle)
                 bases_ext[part.n_local:].copy_(halo)
-            F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.boundary, use_plan=True,
-                                outputs=outs)
+            if pg.overlap_interior:
+                F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.boundary, use_plan=True,
+                                    outputs=outs)
+            else:                                          # one contiguous launch over every local row
+                F.aggregate_combine(desc, g, bases_ext, weightings, bias, outputs=outs)
             if peer is not None and not needs_grad:
                 peer.signal(P.SLOT_CONS)
         out, _, _, saved, saved_arg = outs
@@ -341,10 +351,18 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             peer.begin_backward(ctx.step_id)
             if not (need_wb and need_wc and want_b):
                 flat.zero_()
+            main = torch.cuda.current_stream()
+
+            def push_halo(d_ext):                          # halo partial sums go home (posted stores), BWD + CONS flags,
+                peer.side_stream.wait_stream(main)         # on a side stream while the own columns of pass 2 run
+                with torch.cuda.stream(peer.side_stream):
+                    peer.push_backward(d_ext)
+
             d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                           grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
-                                                          out_bias=v_b, out_lin_colsum=v_bc)
-            peer.push_backward(d_bases_ext)                # halo partial sums go home (posted stores), BWD + CONS flags
+                                                          out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
+                                                          between_phases=push_halo)
+            main.wait_stream(peer.side_stream)
             peer.wait(P.SLOT_BWD)
             d_bases = d_bases_ext[:part.n_local]
             peer.reduce_into(d_bases)                      # fixed peer order: deterministic

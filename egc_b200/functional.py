@@ -102,9 +102,11 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
 def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Tensor, saved: Tensor,
                        saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
                        want_lin_colsum: bool = False, out_bias: Optional[Tensor] = None,
-                       out_lin_colsum: Optional[Tensor] = None):
+                       out_lin_colsum: Optional[Tensor] = None, col_split: Optional[int] = None, between_phases=None):
     """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
-    with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias)."""
+    with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias).
+    `col_split` (row-partitioned callers): run the source columns >= col_split first (EGC_BWD_COLS_HEAD), call
+    `between_phases(d_bases)` - typically the NVLink push of those rows on a side stream - then the rest (COLS_TAIL)."""
     lib = _lib.load()
     dev = bases.device
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
@@ -126,12 +128,21 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
                  torch.empty(hab, dtype=torch.float32, device=dev)) if want_lin_colsum else None
     nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
     ws = _ws(nbytes, dev)
-    check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
-                                ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
-                                graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
-                                ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags, ptr(ws), nbytes,
-                                _stream()),
-          "egc_aggregate_bwd")
+    def call(phase_flags):
+        check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
+                                    ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
+                                    graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
+                                    ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags | phase_flags,
+                                    int(col_split or 0), ptr(ws), nbytes, _stream()),
+              "egc_aggregate_bwd")
+
+    if col_split is None:
+        call(0)
+    else:
+        call(_lib.BWD_COLS_HEAD)
+        if between_phases is not None:
+            between_phases(d_bases)
+        call(_lib.BWD_COLS_TAIL)
     if want_lin_colsum:
         return d_w, d_bases, d_bias, d_lin_sum
     return d_w, d_bases, d_bias

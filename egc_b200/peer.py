@@ -7,8 +7,9 @@ own regions.  `PeerLayerContext` binds a `LocalPartition` to the exchange kernel
   forward : epoch++ and wait CONS(epoch-1) (one kernel) -> [projection writes own basis rows into the segment]
             -> push the rows each peer needs straight into that peer's halo region (its last CTA raises FWD)
             -> [interior rows aggregate] -> wait FWD -> [boundary rows aggregate]
-  backward: [local passes produce d_bases for own + halo sources] -> push halo partial sums into their owners'
-            staging (raises BWD + CONS) -> wait BWD -> deterministic reduce into own rows -> [projection
+  backward: [pass 1, routing, pass 2 of the HALO columns] -> on a side stream: push halo partial sums into their owners'
+            staging (raises BWD + CONS), overlapped with [pass 2 of the own columns] -> wait BWD -> deterministic
+            reduce into own rows -> [projection
             gradients] -> push flat parameter gradients into every rank's slot (raises GRAD) -> wait GRAD
             -> sum the slots in rank order (bit-identical on every rank)
 
@@ -140,6 +141,7 @@ class PeerLayerContext:
         # has pushed its halo gradients (which also raises CONS, releasing the peers' halo copies of my rows)
         self.step_id = 0
         self.outstanding = False
+        self.side_stream = torch.cuda.Stream(device=self.device)      # carries the backward push next to pass 2
 
         # what every rank must know about the others: local row counts, halo layout, staging layout
         recv_off = [0]
@@ -235,9 +237,9 @@ class PeerLayerContext:
         check(_lib.load().egc_peer_wait(self.flags.data_ptr(), self.world, self.rank, slot, self.epoch.data_ptr(), lag,
                                         int(advance), self.timeout_ns, self.err.data_ptr(), self._stream()), "egc_peer_wait")
 
-    def _push(self, n_seg, src, dst, seg_ptr, index, width, slots, fused=False):
-        # the flags can be raised by the push kernel's last CTA (fused=True); measured slower than a separate
-        # one-thread signal kernel (every thread pays a system-scope fence), so the default is two launches
+    def _push(self, n_seg, src, dst, seg_ptr, index, width, slots, fused=True):
+        # the flags are raised by the push kernel's last CTA (one system-scope fence per CTA after a CTA barrier);
+        # fused=False keeps the separate one-warp signal kernel
         mask = sum(1 << s for s in slots)
         check(_lib.load().egc_peer_push_rows(n_seg, src, dst, seg_ptr, index, width, self.flag_ptrs, self.world, self.rank,
                                              mask if fused else 0, self.epoch.data_ptr(), self.counter.data_ptr(),
@@ -265,12 +267,11 @@ class PeerLayerContext:
                                                d_bases_local.data_ptr(), self._stream()), "egc_peer_reduce_rows")
 
     def allreduce_flat(self) -> torch.Tensor:
-        """Sum `self.flat` over the ranks (one-shot: push to every slot, flag, sum in rank order)."""
-        lib = _lib.load()
-        self._push(self.world, self.grad_src, self.grad_dst, self.grad_seg_ptr, None, 128, (SLOT_GRAD,))
-        self.wait(SLOT_GRAD)
-        check(lib.egc_peer_sum_slots(self.slots.data_ptr(), self.world, self.n_flat, self.flat_sum.data_ptr(), self._stream()),
-              "egc_peer_sum_slots")
+        """Sum `self.flat` over the ranks in ONE kernel (push to every rank's slot, flag, wait, sum in rank order)."""
+        check(_lib.load().egc_peer_allreduce(self.flat.data_ptr(), self.grad_dst, self.slots.data_ptr(), self.flag_ptrs,
+                                             self.flags.data_ptr(), self.world, self.rank, SLOT_GRAD, self.epoch.data_ptr(),
+                                             self.counter.data_ptr(), self.n_flat, self.flat_sum.data_ptr(), self.timeout_ns,
+                                             self.err.data_ptr(), self._stream()), "egc_peer_allreduce")
         return self.flat_sum
 
     def check(self):

@@ -231,21 +231,21 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
 #define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients with a compare-and-add gather over the CSC instead of fp32
                                    atomics: bit-reproducible from run to run (needs csr2csc; two more gathered rows per
                                    entry and min/max slot) */
-#define EGC_BWD_STREAM_SWEEPS 2 /* tuning: store the target-side streams stream-major and gather them in one CSC sweep each
-                                   (measured slower on B200 at the arxiv shape: 0.85 vs 0.60 ms) */
 #define EGC_BWD_SKIP_ROUTING 4  /* diagnostics only: drop the min/max gradient routing (results are then incomplete) */
 #define EGC_BWD_NO_HUB_PRIVATISATION 8 /* tuning: route min/max gradients of hub sources (long CSC columns) with global
                                    fp32 atomics like every other source instead of per-CTA shared-memory accumulators */
-#define EGC_BWD_SLAB16 16       /* tuning: force the feature-slab layout of the target-side streams, 16 floats per slab */
-#define EGC_BWD_SLAB32 32       /* tuning: same with 32 floats per slab (default: plain interleaved streams)            */
-#define EGC_BWD_NO_SLABS 64     /* tuning: never use the feature-slab layout (one interleaved sweep)                    */
+#define EGC_BWD_COLS_HEAD 128   /* column phases of a row-partitioned caller (source columns = [own | halo], col_split = number
+                                   of own columns): HEAD = pass 1, the min/max routing and pass 2 of the columns >= col_split,
+                                   so the halo partial sums can travel to their owners while ...                           */
+#define EGC_BWD_COLS_TAIL 256   /* ... TAIL = pass 2 of the columns < col_split runs (same arguments and workspace, after the
+                                   HEAD call on the same stream).  Neither bit: the whole backward in one call.             */
 size_t egc_aggregate_bwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan, int32_t flags);
 int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_lin,
                       const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan,
                       const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
                       const float* grad_out, float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum,
-                      int32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+                      int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row exchange for row-partitioned graphs (no reference counterpart; see DESIGN.md "multi-GPU")
@@ -297,6 +297,15 @@ int egc_peer_wait(const uint32_t* my_flags, int32_t world, int32_t rank, int32_t
 /* into[rows[r], :] += sum_{t in [ptr[r], ptr[r+1])} staging[entry[t], :]   (fixed order: deterministic) */
 int egc_peer_reduce_rows(const float* staging, const int32_t* rows, const int32_t* ptr, const int32_t* entry,
                          int32_t n_rows, int32_t width, float* into, void* stream);
+/* One-shot all-reduce (sum) of a small replicated vector in ONE kernel: src[n] is stored into slot [rank] of every
+ * rank (slot_of_me[q] = mapped address of rank q's slot [rank], own rank included), flag `slot` is raised at *epoch,
+ * the kernel waits for the same flag of every peer (traps after timeout_ns, *err = 1 + slot) and writes
+ * out[i] = sum_r my_slots[r * n + i] in rank order - identical bits on every rank.  n % 4 == 0, 16-byte aligned buffers,
+ * *counter == 0 on entry (and again on exit). */
+int egc_peer_allreduce(const float* src, float* const* slot_of_me, const float* my_slots, uint32_t* const* flags,
+                       const uint32_t* my_flags, int32_t world, int32_t rank, int32_t slot, const uint32_t* epoch,
+                       uint32_t* counter, int32_t n, float* out, uint64_t timeout_ns, uint32_t* err, void* stream);
+
 /* out[i] = sum_q slots[q * n + i] in rank order (the one-shot all-reduce of the replicated parameter gradients) */
 int egc_peer_sum_slots(const float* slots, int32_t world, int32_t n, float* out, void* stream);
 

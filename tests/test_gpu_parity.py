@@ -380,45 +380,6 @@ def test_block_kernels_on_degree_patterns(cfg, pattern, loops):
     assert_close(run_both(o, c, x, (rowptr, col, None), adj, go))
 
 
-SLAB_CONFIGS = [  # f_in, f_out, aggrs, heads, bases  (B*D a multiple of the slab width)
-    (128, 128, ["symnorm", "max", "std"], 4, 4),          # three target-side streams + routed max
-    (128, 128, ["symnorm"], 8, 4),                        # one stream, B*D = 64
-    (64, 128, ["sum", "mean", "min", "var"], 4, 4),       # lin + sq streams
-    (64, 64, ["mean"], 2, 2),                             # B*D = 64, lin only
-]
-
-
-@pytest.mark.parametrize("cfg", SLAB_CONFIGS, ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}-h{c[3]}b{c[4]}")
-@pytest.mark.parametrize("flag", ["SLAB16", "SLAB32", "NO_SLABS"])
-def test_backward_feature_slab_layouts(cfg, flag):
-    """The slab-major target-side stream layout (k_scatter_slab) against the oracle, hubs (long CSC columns) included;
-    the three layouts agree with each other to fp32 reassociation."""
-    f_in, f_out, aggrs, h, b = cfg
-    n = 3000
-    ei = random_graph(n, 30000, seed=33, hub=900)
-    o, c = oracle_and_cuda(f_in, f_out, aggrs, h, b, seed=9)
-    c.bwd_flags = getattr(_lib, "BWD_" + flag)
-    torch.manual_seed(10)
-    x, go = torch.randn(n, f_in), torch.randn(n, f_out)
-    assert_close(run_both(o, c, x, ei, ei.to(DEV), go))
-
-
-@pytest.mark.parametrize("cfg", SLAB_CONFIGS[:2], ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}-h{c[3]}b{c[4]}")
-@pytest.mark.parametrize("flag", ["SLAB16", "SLAB32"])
-def test_backward_feature_slab_layouts_larger_graph(cfg, flag):
-    """Same at a size where every persistent warp owns a few dozen columns (index buffers wrap, several hubs)."""
-    f_in, f_out, aggrs, h, b = cfg
-    n = 40000
-    ei = random_graph(n, 500000, seed=35, hub=5000)
-    extra = random_graph(n, 10, seed=36, hub=700)[:, 10:]                 # a second pair of hubs
-    ei = torch.cat([ei, (extra + 11) % (n - 2)], 1)
-    o, c = oracle_and_cuda(f_in, f_out, aggrs, h, b, seed=11)
-    c.bwd_flags = getattr(_lib, "BWD_" + flag)
-    torch.manual_seed(12)
-    x, go = torch.randn(n, f_in), torch.randn(n, f_out)
-    assert_close(run_both(o, c, x, ei, ei.to(DEV), go))
-
-
 @pytest.mark.parametrize("loops,sigmoid,bias", list(itertools.product([True, False], [True, False], [True, False])))
 def test_layer_flags(loops, sigmoid, bias):
     n = 500

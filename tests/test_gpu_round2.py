@@ -82,7 +82,7 @@ def test_deterministic_flag_needs_csr2csc_at_the_c_abi():
     P = _lib.ptr
     rc = lib.egc_aggregate_bwd(desc, P(g.rowptr), P(g.col), None, P(g.colptr), P(g.rowidx), None, None, None,
                                g.csc_plan.struct, P(bases), P(w), P(saved), P(saved_arg), P(go), P(d_w), P(d_b), None, None,
-                               _lib.BWD_DETERMINISTIC, P(ws), nbytes, torch.cuda.current_stream().cuda_stream)
+                               _lib.BWD_DETERMINISTIC, 0, P(ws), nbytes, torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"csr2csc" in lib.egc_last_error_string()
 
 
@@ -165,3 +165,38 @@ def test_regconv_rebuilds_a_different_adjacency_under_the_same_key():
     fresh.load_state_dict(m.state_dict())
     assert torch.equal(fresh(x, {rel[0]: a2})["a"], y2)
     assert torch.equal(m(x, {rel[0]: a1})["a"], y1)
+
+
+# ------------------------------------------------------------------------------------------------
+# column phases of the backward (row-partitioned callers: halo columns first, then the own columns)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("aggrs,heads,bd,bases_n", [(["symnorm", "std", "mean"], 4, 128, 4), (["symnorm", "max", "std"], 4, 128, 4),
+                                                    (["symnorm"], 8, 64, 4), (["sum", "min", "var"], 4, 30, 3), (["max"], 4, 64, 4)])
+@pytest.mark.parametrize("det", [False, True])
+def test_backward_column_phases_equal_the_single_call(aggrs, heads, bd, bases_n, det):
+    from egc_b200.functional import aggregate_backward, aggregate_combine, make_desc
+    n = 2500
+    g = egc_b200.GraphStructure.from_edge_index(random_graph(n, 25000, seed=75, hub=700).to(DEV), n, "symnorm" in aggrs, True)
+    desc = make_desc(g, heads, bases_n, bd // bases_n, aggrs, False)
+    torch.manual_seed(6)
+    bases = torch.randn(n, bd, device=DEV)
+    w = torch.randn(n, heads * len(aggrs) * bases_n, device=DEV)
+    go = torch.randn(n, heads * (bd // bases_n), device=DEV)
+    _, _, _, saved, saved_arg = aggregate_combine(desc, g, bases, w, None, want_saved=True)
+    flags = _lib.BWD_DETERMINISTIC if det else 0
+    ref = aggregate_backward(desc, g, bases, w, saved, saved_arg, go, True, flags, want_lin_colsum=True)
+    seen = {}
+    for split in (0, 1, 1234, n - 1, n):
+        got = aggregate_backward(desc, g, bases, w, saved, saved_arg, go, True, flags, want_lin_colsum=True, col_split=split,
+                                 between_phases=lambda d: seen.setdefault(split, d[split:].clone()))
+        routed = any(a in ("max", "min") for a in aggrs)
+        for a, r in zip(got, ref):
+            if routed:                                        # routed-first vs routed-last: one more rounding per entry
+                assert rel_err(a, r) < 2e-6
+            else:
+                assert torch.equal(a, r)
+        # what the HEAD phase hands to the exchange (columns >= split) is already final
+        if routed and not det:
+            assert rel_err(seen[split], ref[1][split:]) < 2e-6 if split < n else True
+        else:
+            assert torch.equal(seen[split], got[1][split:])
