@@ -65,7 +65,9 @@ struct TcParams {
   int n_terms;                             // 3: 3xTF32, 1: TF32
   int num_tiles;
   int use_tma_store;                       // epilogue writes C through TMA tensor stores (128B-swizzled 32 x 32 staging tiles)
-  int use_tma;                             // A chunks arrive by TMA tensor copies (4 x [128 rows x 16 B] boxes per chunk) instead of LDGSTS
+  int use_tma;                             // A chunks arrive by TMA tensor copies instead of LDGSTS: 1 = four [128 rows x 16 B]
+                                           // boxes per chunk (no-swizzle core matrices), 2 = ONE [128 rows x 64 B] box per
+                                           // chunk in the 64-byte swizzle (4x fewer, 4x wider requests)
   int ablate;                              // diagnostics (EGC_TC_ABLATE, results become wrong): 1 no lo conversion, 2 no epilogue,
                                            // 4 no MMA, 8 no A copies, 16 no global stores  (tools/gemm_ablate.sh)
 };
@@ -110,37 +112,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
 
   // ---- stage this group's weights once: hi / lo split, canonical K-major layout (zero padded).
-  // Batches of 8 independent loads per thread keep the (L2-resident) weight fetch off the critical path.
+  // A task = one 16-byte piece of the layout (4 consecutive k of one output column); a thread keeps the 4 x kPieces
+  // loads of its batch in flight, so the (L2-resident) weight fetch costs a few L2 round trips, not one per element.
   {
-    const int total = p.k_pad * n_pad;
-    constexpr int kBatch = 8;
-    for (int e0 = tid; e0 < total; e0 += kTcThreads * kBatch) {
-      float v[kBatch];
-      uint32_t off[kBatch];
+    const int pieces = (p.k_pad >> 2) * n_pad;
+    constexpr int kPieces = 3;
+    for (int e0 = tid; e0 < pieces; e0 += kTcThreads * kPieces) {
+      float v[kPieces][4];
+      uint32_t off[kPieces];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < kPieces; ++u) {
         const int e = e0 + u * kTcThreads;
-        v[u] = 0.f;
         off[u] = 0xffffffffu;
-        if (e < total) {
-          const int k = e / n_pad, n = e - k * n_pad;
-          off[u] = static_cast<uint32_t>(k >> 2) * lbo_b + (k & 3) * 4 + static_cast<uint32_t>(n) * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[u][j] = 0.f;
+        if (e < pieces) {
+          const int kq = e / n_pad, n = e - kq * n_pad;
+          off[u] = static_cast<uint32_t>(kq) * lbo_b + static_cast<uint32_t>(n) * 16;
           const int ng = n_begin + n;
-          if (n < n_count && k < K) {
-            const int kb = k >= p.k1 ? 1 : 0, nb = ng >= p.n1 ? 1 : 0;
-            const float* src = p.b[nb][kb];
-            if (src != nullptr)
-              v[u] = __ldg(src + static_cast<int64_t>(ng - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
-                           static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+          if (n < n_count) {
+            const int nb = ng >= p.n1 ? 1 : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = 4 * kq + j;
+              if (k < K) {
+                const int kb = k >= p.k1 ? 1 : 0;
+                const float* src = p.b[nb][kb];
+                if (src != nullptr)
+                  v[u][j] = __ldg(src + static_cast<int64_t>(ng - (nb ? p.n1 : 0)) * p.b_sn[nb][kb] +
+                                  static_cast<int64_t>(k - (kb ? p.k1 : 0)) * p.b_sk[nb][kb]);
+              }
+            }
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < kPieces; ++u) {
         if (off[u] != 0xffffffffu) {
-          const float hi = tf32_hi(v[u]);
-          *reinterpret_cast<float*>(b_hi + off[u]) = hi;
-          *reinterpret_cast<float*>(b_lo + off[u]) = v[u] - hi;
+          const float4 hi = make_float4(tf32_hi(v[u][0]), tf32_hi(v[u][1]), tf32_hi(v[u][2]), tf32_hi(v[u][3]));
+          *reinterpret_cast<float4*>(b_hi + off[u]) = hi;
+          *reinterpret_cast<float4*>(b_lo + off[u]) = make_float4(v[u][0] - hi.x, v[u][1] - hi.y, v[u][2] - hi.z, v[u][3] - hi.w);
         }
       }
     }
@@ -171,11 +182,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
         mbar_wait(raw_empty(stage), phase ^ 1u);
         mbar_arrive_expect_tx(raw_full(stage), kChunkBytes);
         const uint32_t dst = raw_addr + stage * kChunkBytes;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int k = j * kChunkK + 4 * c4;
+        if (p.use_tma == 2) {
+          // one [128 rows x 16 floats] box in the 64-byte swizzle (k1 is a multiple of 16: a chunk never straddles A1 | A2)
+          const int k = j * kChunkK;
           const bool second = k >= p.k1 && p.k2 > 0;
-          tma_load_2d(dst + c4 * (kTileM * 16), second ? &tm_a2 : &tm_a1, second ? k - p.k1 : k, row_base, raw_full(stage));
+          tma_load_2d(dst, second ? &tm_a2 : &tm_a1, second ? k - p.k1 : k, row_base, raw_full(stage));
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int k = j * kChunkK + 4 * c4;
+            const bool second = k >= p.k1 && p.k2 > 0;
+            tma_load_2d(dst + c4 * (kTileM * 16), second ? &tm_a2 : &tm_a1, second ? k - p.k1 : k, row_base, raw_full(stage));
+          }
         }
         if (++stage == R) { stage = 0; phase ^= 1u; }
         if (++j == n_chunks) { j = 0; ++t; }
@@ -253,7 +271,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
                            (static_cast<uint32_t>(kTileM >> 4) << 24);
     constexpr uint32_t a_lbo = kTileM * 16, sbo = 128;
     // descriptors advance by adding (byte offset >> 4) to the 14-bit start-address field
-    const uint64_t da_raw0 = make_desc(raw_addr, a_lbo, sbo), da_lo0 = make_desc(lo_addr, a_lbo, sbo);
+    const bool sw64 = p.use_tma == 2;
+    const uint64_t da_raw0 = sw64 ? make_desc_sw64(raw_addr) : make_desc(raw_addr, a_lbo, sbo);
+    const uint64_t da_lo0 = sw64 ? make_desc_sw64(lo_addr) : make_desc(lo_addr, a_lbo, sbo);
+    const uint32_t a_kstep = sw64 ? (32u >> 4) : ((2 * a_lbo) >> 4);      // second k-step of a chunk: +32 B inside the swizzle atom
     const uint64_t db_hi0 = make_desc(smem_u32(b_hi), lbo_b, sbo), db_lo0 = make_desc(smem_u32(b_lo), lbo_b, sbo);
     const uint32_t b_kstep = (2 * lbo_b) >> 4;
     const bool three = p.n_terms == 3;
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_project_tc(const __grid_const
           const uint64_t db_lo = db_lo0 + static_cast<uint32_t>(2 * j) * b_kstep;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const uint32_t ao = s * ((2 * a_lbo) >> 4), bo = s * b_kstep;
+            const uint32_t ao = s * a_kstep, bo = s * b_kstep;
             umma_tf32(d_tmem, da_hi + ao, db_hi + bo, idesc, (j | s) != 0 ? 1u : 0u);
             if (three) {
               umma_tf32(d_tmem, da_hi + ao, db_lo + bo, idesc, 1u);
@@ -470,6 +491,18 @@ static bool make_a_map(CUtensorMap* m, const float* base, int k, int64_t ld, int
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [M rows x k floats] row-major operand, boxes of 128 rows x 16 floats in the 64-byte swizzle
+static bool make_a_map_sw64(CUtensorMap* m, const float* base, int k, int64_t ld, int M) {
+  EncodeTiledFn fn = encode_tiled();
+  if (fn == nullptr || base == nullptr || k <= 0) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(M)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(kTileM)};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_tc(TcParams& p, cudaStream_t st) {
   const int K = p.k1 + p.k2, N = p.n1 + p.n2;
   TcPlan plan;
@@ -492,8 +525,14 @@ static int launch_tc(TcParams& p, cudaStream_t st) {
   memset(&tm2, 0, sizeof(tm2));
   static const bool want_tma = getenv("EGC_TC_NO_TMA") == nullptr;
   p.use_tma = 0;
-  if (want_tma && p.k1 % 4 == 0 && p.lda1 % 4 == 0 && (p.k2 == 0 || (p.k2 % 4 == 0 && p.lda2 % 4 == 0)) &&
-      make_a_map(&tm1, p.a1, p.k1, p.lda1, p.M) && (p.k2 == 0 || make_a_map(&tm2, p.a2, p.k2, p.lda2, p.M)))
+  // 64-byte swizzled boxes (default; EGC_TC_NO_SWIZZLE=1 keeps the four 16-byte boxes per chunk): one request per row and
+  // chunk instead of four.  A chunk of 16 floats must not straddle the A1 | A2 boundary.
+  static const bool want_sw64 = getenv("EGC_TC_NO_SWIZZLE") == nullptr;
+  const bool tma_ok = want_tma && p.k1 % 4 == 0 && p.lda1 % 4 == 0 && (p.k2 == 0 || (p.k2 % 4 == 0 && p.lda2 % 4 == 0));
+  if (tma_ok && want_sw64 && (p.k2 == 0 || p.k1 % kChunkK == 0) && make_a_map_sw64(&tm1, p.a1, p.k1, p.lda1, p.M) &&
+      (p.k2 == 0 || make_a_map_sw64(&tm2, p.a2, p.k2, p.lda2, p.M)))
+    p.use_tma = 2;
+  else if (tma_ok && make_a_map(&tm1, p.a1, p.k1, p.lda1, p.M) && (p.k2 == 0 || make_a_map(&tm2, p.a2, p.k2, p.lda2, p.M)))
     p.use_tma = 1;
   // TMA tensor stores of the output (EGC_TC_TMA_STORE=1; experimental): column blocks of 32 must not straddle c1 | c2
   alignas(64) CUtensorMap tc1, tc2;

@@ -90,6 +90,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                                   // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
 
+// K-major operand in the 64-byte swizzle (what a TMA tensor copy with CU_TENSOR_MAP_SWIZZLE_64B of a [rows x 16 fp32]
+// box produces at a 512-byte aligned address): rows are 64 B apart, the four 16-byte pieces of a row are XOR-permuted
+// with bits 7-8 of the address, 8-row groups are SBO = 512 B apart, LBO is unused.  One kind::tf32 MMA consumes 32 B of
+// K: the second k-step of a chunk starts 32 B further (the swizzle is a function of the address bits, so advancing the
+// start address inside the atom is legal).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>(1) << 16;                       // LBO: unused with swizzled K-major operands
+  d |= static_cast<uint64_t>((512u >> 4) & 0x3fff) << 32;    // SBO
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(4) << 61;                       // layout_type SWIZZLE_64B
+  return d;
+}
+
 // 16-byte global -> shared async copy (L2 only); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");

@@ -34,19 +34,25 @@ def _grads(c, x, g_gpu, go):
     return torch.autograd.grad(out, [xc] + list(c.parameters()), go.to(DEV))
 
 
-@pytest.mark.parametrize("ties", [False, True], ids=["distinct", "ties"])
 @pytest.mark.parametrize("cfg", DET_CONFIGS, ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}-h{c[3]}b{c[4]}{'-valued' if c[5] else ''}")
-def test_deterministic_routing_is_bit_reproducible_and_matches_the_oracle(cfg, ties):
+def test_deterministic_routing_is_bit_reproducible_and_matches_the_oracle(cfg):
+    """max / min are discontinuous: a 1e-6 rounding difference in the projected bases can change a winner and move a
+    whole gradient entry (seen here: ~1 flip per 4e5 (row, feature) pairs against the fp64 oracle, a 5e-3 'error' in
+    grad_x that is no error).  So the inputs are dyadic - x in multiples of 1/4, basis weights in multiples of 1/16 -
+    which makes the projection EXACT in fp32, TF32x3 and fp64 alike: winners are then decided by values that are
+    bit-identical on both sides, with plenty of exact ties (coarse grid) settled by nnz position."""
     f_in, f_out, aggrs, h, b, valued = cfg
     n = 3000
     ei = random_graph(n, 30000, seed=71, hub=900)             # hub columns > 256 entries: chunk partials + ordered merge
     o, c = oracle_and_cuda(f_in, f_out, aggrs, h, b, seed=9)
+    with torch.no_grad():
+        wq = torch.round(o.bases_weight * 16) / 16
+        o.bases_weight.copy_(wq)
+        c.bases_weight.copy_(wq.to(DEV))
     torch.manual_seed(10)
-    x, go = torch.randn(n, f_in), torch.randn(n, f_out)
-    if ties:
-        x[::7] = x[3]                                         # exact ties between neighbours: first-wins by position
+    x, go = torch.round(torch.randn(n, f_in) * 4) / 4, torch.randn(n, f_out)
     if valued:
-        val = torch.rand(ei.size(1)) + 0.5
+        val = torch.randint(1, 5, (ei.size(1),)).float() / 2   # dyadic edge weights too
         rowptr, col, v = to_adj_csr(ei, n, val)
         g_cpu = (rowptr, col, v)
         g_gpu = egc_b200.SparseTensor(rowptr=rowptr.to(DEV), col=col.to(DEV), value=v.to(DEV), sparse_sizes=(n, n), is_sorted=True)
