@@ -10,6 +10,7 @@
 // The epoch lives in device memory and is advanced by a kernel, so a whole training step (pushes, signals, waits
 // included) can be captured once in a CUDA graph and replayed.  The reference has no multi-GPU path; the contract
 // is "same numbers as the single-GPU layer" (tests/test_gpu_dist.py).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -301,7 +302,10 @@ int egc_peer_push_rows(int32_t n_seg, const float* const* src, float* const* dst
   }
   const int total = seg_ptr[n_seg];
   cudaStream_t st = as_stream(stream);
-  const int grid = std::max(1, std::min(ceil_div(total, 8), sm_count() * 8));   // an empty push still raises its flags
+  // one warp per row; the grid is capped so that a push running next to a compute kernel (the backward push overlaps
+  // pass 2 of the own columns) leaves that kernel its share of every SM.  EGC_PEER_PUSH_CTAS_PER_SM: A/B runs.
+  static const int ctas_per_sm = [] { const char* e = getenv("EGC_PEER_PUSH_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
+  const int grid = std::max(1, std::min(ceil_div(total, 8), sm_count() * ctas_per_sm));   // an empty push still raises its flags
   {
     LaunchScope ls("k_peer_push", st);
     if (vec) k_peer_push<4><<<grid, 256, 0, st>>>(p);

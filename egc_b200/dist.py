@@ -230,6 +230,9 @@ class PartitionedGraph:
         # a row subset runs slower than the contiguous whole-graph launch (per-row staging), and with ~15 nnz per
         # row and 20 % remote sources only a few rows are interior.  Below one half: wait, then ONE contiguous launch.
         self.overlap_interior = part.interior_rows.numel() * 2 >= max(part.n_local, 1)
+        # backward: halo columns of pass 2 first, their push on a side stream while the own columns run (A/B switch)
+        import os
+        self.split_backward = os.environ.get("EGC_DIST_SPLIT_BWD", "1") == "1"
         self.group = group
         self._peer_ctx = {}
 
@@ -358,11 +361,17 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 with torch.cuda.stream(peer.side_stream):
                     peer.push_backward(d_ext)
 
-            d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
-                                                          grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
-                                                          out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
-                                                          between_phases=push_halo)
-            main.wait_stream(peer.side_stream)
+            if pg.split_backward:
+                d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
+                                                              grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
+                                                              out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
+                                                              between_phases=push_halo)
+                main.wait_stream(peer.side_stream)
+            else:
+                d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
+                                                              grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
+                                                              out_bias=v_b, out_lin_colsum=v_bc)
+                peer.push_backward(d_bases_ext)
             peer.wait(P.SLOT_BWD)
             d_bases = d_bases_ext[:part.n_local]
             peer.reduce_into(d_bases)                      # fixed peer order: deterministic

@@ -17,6 +17,7 @@ No NCCL call, no host synchronisation and no allocation is on that path, so a wh
 in a CUDA graph (`egc_b200.dist.GraphedStep`).  The reference has no multi-GPU counterpart.
 """
 import ctypes
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -237,9 +238,11 @@ class PeerLayerContext:
         check(_lib.load().egc_peer_wait(self.flags.data_ptr(), self.world, self.rank, slot, self.epoch.data_ptr(), lag,
                                         int(advance), self.timeout_ns, self.err.data_ptr(), self._stream()), "egc_peer_wait")
 
-    def _push(self, n_seg, src, dst, seg_ptr, index, width, slots, fused=True):
-        # the flags are raised by the push kernel's last CTA (one system-scope fence per CTA after a CTA barrier);
-        # fused=False keeps the separate one-warp signal kernel
+    def _push(self, n_seg, src, dst, seg_ptr, index, width, slots, fused=None):
+        # fused=True: the flags are raised by the push kernel's last CTA (one system-scope fence per CTA after a CTA
+        # barrier); fused=False: a separate one-warp signal kernel after the push (EGC_PEER_FUSED_SIGNAL picks, A/B)
+        if fused is None:
+            fused = os.environ.get("EGC_PEER_FUSED_SIGNAL", "0") == "1"
         mask = sum(1 << s for s in slots)
         check(_lib.load().egc_peer_push_rows(n_seg, src, dst, seg_ptr, index, width, self.flag_ptrs, self.world, self.rank,
                                              mask if fused else 0, self.epoch.data_ptr(), self.counter.data_ptr(),
