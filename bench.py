@@ -895,6 +895,73 @@ def run_minibatch(args, m):
     nnz = sum(nnz_per_step) / n_batches                   # mean aggregated nnz (edges + self-loops) per layer and step
     nodes = sum(int(pk[0].size(0)) for pk in packed) / n_batches
 
+    # ---- fixed-shape path: every batch padded on the host (the DataLoader's collate step) to the same node / edge counts,
+    # so the WHOLE step - collation, CSR + CSC build, 4 layers forward + backward, readout, loss - is one CUDA graph
+    # replayed per batch (the eager path above pays ~65 launches and two device-to-host reads of graph preparation)
+    from egc_b200.dist import GraphedStep
+    e_cap = max(int(pk[1].size(1)) for pk in packed) + 1
+    q_max = e_cap - min(int(pk[1].size(1)) for pk in packed)
+    n_cap = max(int(pk[0].size(0)) for pk in packed) + max(64, (q_max + 63) // 64)
+    padded = [egc_b200.pad_batch(pk[0], pk[1], pk[2], n_cap, e_cap) for pk in packed]
+    nnz_static = {p_[3] for p_ in padded}
+    static_ok = len(nnz_static) == 1 and not args.no_graph
+    ms_static = ms_static_e2e = parity_static = None
+    if static_ok:
+        nnz_cap = nnz_static.pop()
+        padded_pinned = [tuple(t.pin_memory() for t in p_[:3]) for p_ in padded]
+        padded_dev = [tuple(t.to(dev) for t in p_) for p_ in padded_pinned]
+        xs = torch.zeros((n_cap, m["f_in"]), device=dev, requires_grad=True)
+        els = torch.zeros((2, e_cap), dtype=torch.int64, device=dev)
+        pts = torch.zeros((2, m["graphs"] + 2), dtype=torch.int32, device=dev)
+        keep = {}
+
+        def static_step():
+            edge_index, _ = egc_b200.collate_arrays(els, pts[1], pts[0], num_nodes=n_cap, validate=False)
+            g = egc_b200.GraphStructure.from_edge_index(edge_index, n_cap, sym, True, expect={"nnz": nnz_cap})
+            keep["g"] = g
+            h = xs
+            for layer in model:
+                h = torch.relu(layer(h, g))
+            loss = egc_b200.global_mean_pool(h, pts[0, :m["graphs"] + 1]).pow(2).sum(1).mean()
+            return (loss,) + torch.autograd.grad(loss, [xs] + params)
+
+        def load_static(src):
+            with torch.no_grad():
+                xs.copy_(src[0], non_blocking=True)
+                els.copy_(src[1], non_blocking=True)
+                pts.copy_(src[2], non_blocking=True)
+
+        load_static(padded_dev[0])
+        graphed = GraphedStep(static_step, warmup=2)
+        g_static = keep["g"]
+
+        def step_static():
+            k = state["k"]; state["k"] = k + 1
+            load_static(padded_dev[k % n_batches])
+            return graphed.replay()
+
+        def step_static_e2e():
+            k = state["k"]; state["k"] = k + 1
+            load_static(padded_pinned[k % n_batches])
+            return float(graphed.replay()[0].item())
+
+        # parity of the padded replay against the eager, unpadded step on the same batch (parameter gradients)
+        load_static(padded_dev[3])
+        res = graphed.replay()
+        x3, el3, pt3, _ = resident[3]
+        x3 = x3.detach().requires_grad_(True)
+        ei3, _ = egc_b200.collate_arrays(el3, pt3[1], pt3[0], num_nodes=int(x3.size(0)), validate=False)
+        g3 = egc_b200.GraphStructure.from_edge_index(ei3, int(x3.size(0)), sym, True)
+        h3 = x3
+        for layer in model:
+            h3 = torch.relu(layer(h3, g3))
+        loss3 = egc_b200.global_mean_pool(h3, pt3[0]).pow(2).sum(1).mean()
+        ref3 = torch.autograd.grad(loss3, [x3] + params)
+        errs = [rel_err(res[0], loss3), rel_err(res[1][:x3.size(0)], ref3[0])] + [rel_err(a, b) for a, b in zip(res[2:], ref3[1:])]
+        g_static.verify()
+        parity_static = {"against": "the eager, unpadded step on the same batch (loss, d_x rows, parameter gradients)",
+                         "max_rel_err": max(errs), "tol": 1e-5, "ok": bool(max(errs) < 1e-5)}
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -910,8 +977,13 @@ def run_minibatch(args, m):
 
     steps = max(args.steps, n_batches)
     with ClockSampler(dev.index or 0) as clocks:
-        ms, launches = timed(step, steps, args.warmup)
-        ms_e2e, _ = timed(step_e2e, steps, 2)
+        ms_eager, launches = timed(step, steps, args.warmup)
+        ms_eager_e2e, _ = timed(step_e2e, steps, 2)
+        if static_ok:
+            ms_static, _ = timed(step_static, steps, args.warmup)
+            ms_static_e2e, _ = timed(step_static_e2e, steps, 2)
+            g_static.verify()                             # the replayed builds still match the declared shape
+    ms, ms_e2e = (ms_static, ms_static_e2e) if static_ok else (ms_eager, ms_eager_e2e)
     _lib.profile_enable(True)
     for _ in range(steps):
         step()
@@ -950,7 +1022,12 @@ def run_minibatch(args, m):
                    "structure": "cold: CSR / CSC / symnorm built every step (once per batch, shared by the layers)",
                    "l2": "working set < L2 (launch-latency regime); batches cycle over 8 different graph lists",
                    "algorithmic_bytes_per_step": (bf + bb) * m["layers"], "us_per_step": ms * 1e3,
-                   "gpu_kernel_ms_per_step": gpu_kernel_ms},
+                   "gpu_kernel_ms_per_step": gpu_kernel_ms,
+                   "launch_mode": (f"fixed-shape batches (host-side padding to {n_cap} nodes / {e_cap} edges), the whole step - "
+                                   "collation, CSR + CSC build, layers, readout, backward - replayed from ONE CUDA graph"
+                                   if static_ok else "eager launches")},
+        "eager": {"ms_per_step": ms_eager, "e2e_ms_per_step": ms_eager_e2e, "launches_per_step": launches / steps},
+        "parity_check": parity_static,
         "clocks": clocks.summary(),
         "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -961,6 +1038,123 @@ def run_minibatch(args, m):
         "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
     }
     print(json.dumps(line))
+
+
+def run_minibatch_dp(args, m):
+    """Data-parallel mini-batch training over N ranks (BASELINE configs[4]: CIFAR-shaped EGC-M batches, and configs[0]):
+    every rank runs the SAME replicated stack on its OWN batch of `graphs` small graphs per step (weak scaling), the
+    parameter gradients are all-reduced per layer from inside the backward pass (NCCL, overlapped with the backward of
+    the layers below).  Before timing: the all-reduced gradients are compared with ONE process on the concatenation of
+    every rank's batch (`parity_check`)."""
+    import torch.distributed as dist
+
+    import egc_b200
+    from egc_b200 import _lib
+    from egc_b200.dist import OverlappedGradientAllReduce
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    dims = [m["f_in"]] + [m["hidden"]] * m["layers"]
+    sym = "symnorm" in m["aggrs"]
+
+    def make_model():
+        torch.manual_seed(0)                              # identical replicated parameters on every rank
+        return torch.nn.ModuleList([egc_b200.EGConv(dims[i], dims[i + 1], aggrs=m["aggrs"], num_heads=m["heads"],
+                                                    num_bases=m["bases"]) for i in range(m["layers"])]).to(dev)
+
+    def pack(graphs):
+        counts = torch.tensor([[g[2], g[1].size(1)] for g in graphs])
+        ptrs = torch.zeros((2, len(graphs) + 1), dtype=torch.int32)
+        ptrs[:, 1:] = counts.cumsum(0).t().to(torch.int32)
+        return (torch.cat([g[0] for g in graphs]).pin_memory(), torch.cat([g[1] for g in graphs], 1).pin_memory(),
+                ptrs.pin_memory(), len(graphs))
+
+    def loss_of(model, x, edge_local, ptrs):
+        n = int(x.size(0))
+        edge_index, _ = egc_b200.collate_arrays(edge_local, ptrs[1], ptrs[0], num_nodes=n, validate=False)
+        g = egc_b200.GraphStructure.from_edge_index(edge_index, n, sym, True)
+        h = x
+        for layer in model:
+            h = torch.relu(layer(h, g))
+        return egc_b200.global_mean_pool(h, ptrs[0]).pow(2).sum(1).mean(), g.nnz
+
+    model = make_model()
+    sync = OverlappedGradientAllReduce(list(model))
+    n_batches = 8
+    host = [synth_small_graphs(args.workload, m["graphs"], (args.seed * 100 + b) * 64 + rank, m["f_in"]) for b in range(n_batches)]
+    packed = [pack(g) for g in host]
+    resident = [tuple(t.to(dev) if torch.is_tensor(t) else t for t in pk) for pk in packed]
+    state = {"k": 0}
+
+    def step_on(x, el, ptrs, read_loss):
+        for p_ in model.parameters():
+            p_.grad = None
+        sync.begin(1.0 / world)                           # every rank holds the same number of graphs
+        loss, nnz = loss_of(model, x, el, ptrs)
+        loss.backward()
+        sync.finish()
+        return (float(loss.item()) if read_loss else loss), nnz
+
+    def step():
+        k = state["k"]; state["k"] = k + 1
+        x, el, ptrs, _ = resident[k % n_batches]
+        return step_on(x, el, ptrs, False)
+
+    def step_e2e():
+        k = state["k"]; state["k"] = k + 1
+        x, el, ptrs, _ = packed[k % n_batches]
+        return step_on(x.to(dev, non_blocking=True), el.to(dev, non_blocking=True), ptrs.to(dev, non_blocking=True), True)
+
+    # ---- parity: DP gradients of batch 0 == one process on the concatenation of every rank's batch 0
+    step_on(*resident[0][:3], False)
+    dp_grads = [p_.grad.detach().clone() for p_ in model.parameters()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [(x.clone(), ei.clone(), n) for x, ei, n in host[0]])
+    ref_model = make_model()
+    xa, ea, pa, _ = pack([g for part in gathered for g in part])
+    ref_loss, _ = loss_of(ref_model, xa.to(dev), ea.to(dev), pa.to(dev))
+    ref_grads = torch.autograd.grad(ref_loss, list(ref_model.parameters()))
+    err = torch.tensor([max(rel_err(a, b) for a, b in zip(dp_grads, ref_grads))], device=dev, dtype=torch.float64)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    tol = 2e-5
+    parity = {"against": "one process on the concatenation of every rank's batch (loss = mean over all graphs)",
+              "max_rel_err": float(err.item()), "tol": tol, "ok": bool(float(err.item()) < tol)}
+    del ref_model, ref_grads
+
+    nnz_local = sum(step()[1] for _ in range(n_batches)) / n_batches      # also the warm-up of every kernel shape
+    steps = max(args.steps, n_batches)
+    with ClockSampler(dev.index or 0) as clocks:
+        ms, launches = cuda_timed(step, steps, args.warmup, dist.barrier)
+        ms_e2e, _ = cuda_timed(step_e2e, steps, 2, dist.barrier)
+    t = torch.tensor([ms, ms_e2e, nnz_local * m["layers"], launches], device=dev, dtype=torch.float64)
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms, ms_e2e = float(tmax[0]), float(tmax[1])
+        edges = float(tsum[2])
+        n_param = sum(p_.numel() for p_ in model.parameters())
+        h2d = sum(pk[0].numel() * 4 + pk[1].numel() * 8 + pk[2].numel() * 4 for pk in packed) / n_batches
+        print(json.dumps({
+            "metric": "EGConv fwd+bwd edges/s", "value": edges / (ms * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": m["desc"] + f", data-parallel over {world} GPUs ({m['graphs']} graphs per GPU and step)",
+                       "graphs_per_step": m["graphs"] * world, "layers": m["layers"],
+                       "edges_counted": "aggregated nnz (edges + self-loops) x layers, summed over the ranks",
+                       "structure": "cold: CSR / CSC / symnorm built every step on every rank",
+                       "all_reduce": f"{n_param * 4} B of parameter gradients per step, one NCCL all-reduce per layer launched from "
+                                     "inside backward (overlaps the backward of the layers below)",
+                       "l2": "working set < L2 (launch-latency regime); batches cycle over 8 different graph lists per rank"},
+            "parity_check": parity, "clocks": clocks.summary(),
+            "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                    "input_pipeline": "pinned host arrays of the batch -> device collation -> stack -> loss read back"},
+            "gpu_launches": int(float(tsum[3])), "roofline": None, "cpu_baseline": None}))
+    dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.exit(f"bench.py: data-parallel gradients differ from the single-process run: {parity}")
 
 
 def minibatch_cpu_step_factory(m, graphs):
@@ -1226,10 +1420,11 @@ def main():
             run_rmag(args)
         return
     if args.workload in MINIBATCH:
-        if rank != 0:
-            return                                          # replicas only: the batches are independent
         if args.impl == "reference":
-            run_minibatch_reference_arm(args, MINIBATCH[args.workload])
+            if rank == 0:
+                run_minibatch_reference_arm(args, MINIBATCH[args.workload])
+        elif int(os.environ.get("WORLD_SIZE", 1)) > 1:      # data-parallel: per-rank batches, overlapped gradient all-reduce
+            run_minibatch_dp(args, MINIBATCH[args.workload])
         else:
             run_minibatch(args, MINIBATCH[args.workload])
         return

@@ -14,10 +14,11 @@ Public surface (mirrors the reference operator API, /root/reference/experiments/
 """
 from ._lib import (BWD_DETERMINISTIC, GEMM_3XTF32, GEMM_AUTO, GEMM_FP32_SIMT, GEMM_TF32, EGCError, build,  # noqa: F401
                    load)
-from .batch import Batch, collate, collate_arrays, global_add_pool, global_max_pool, global_mean_pool, segment_ptr  # noqa: F401
+from .batch import (Batch, collate, collate_arrays, global_add_pool, global_max_pool, global_mean_pool, pad_batch,  # noqa: F401
+                    segment_ptr)
 from .compat import EfficientGraphConv, convert_paper_state_dict, paper_to_egconv_perm  # noqa: F401
 from .conv import EGConv  # noqa: F401
-from .dist import GradientAllReduce, GraphedStep  # noqa: F401
+from .dist import GradientAllReduce, GraphedStep, OverlappedGradientAllReduce  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
 from .hetero import REGConv  # noqa: F401
 from .stack import EGC  # noqa: F401

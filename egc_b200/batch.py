@@ -137,7 +137,7 @@ class _SegmentPool(torch.autograd.Function):
         node_ptr, arg = ctx.saved_tensors
         d_out = d_out.contiguous()
         g, f = int(d_out.size(0)), int(d_out.size(1))
-        d_x = torch.empty((ctx.n, f), dtype=torch.float32, device=d_out.device)
+        d_x = torch.zeros((ctx.n, f), dtype=torch.float32, device=d_out.device)     # nodes outside every segment: 0
         with torch.cuda.device(d_out.device):
             check(lib.egc_segment_pool_bwd(ptr(d_out), ptr(node_ptr), ptr(arg), g, f, ctx.mode, ptr(d_x), _stream()),
                   "egc_segment_pool_bwd")
@@ -166,3 +166,36 @@ def global_mean_pool(x: Tensor, batch, size: Optional[int] = None) -> Tensor:
 
 def global_max_pool(x: Tensor, batch, size: Optional[int] = None) -> Tensor:
     return _pool(x, batch, size, "max")
+
+
+# ---------------------------------------------------------------------------------------------------
+# fixed-shape batches: what lets a whole training step (collation, CSR / CSC build, layers, readout) replay from ONE
+# CUDA graph.  The host side (the DataLoader's collate function) pads every batch to the same node and edge counts with
+# one extra "pad graph" that no readout segment covers: its nodes only talk to each other, so nothing computed for the
+# real graphs changes, and every gradient they could contribute is multiplied by a zero grad_out.
+# ---------------------------------------------------------------------------------------------------
+def pad_batch(x: Tensor, edge_local: Tensor, ptrs: Tensor, n_cap: int, e_cap: int):
+    """HOST tensors of one collated batch -> the same batch padded to exactly `n_cap` nodes and `e_cap` edges.
+
+    x [n, F]; edge_local [2, E] graph-local ids; ptrs int32 [2, G + 1] (row 0: node offsets, row 1: edge offsets).
+    Returns (x_pad [n_cap, F], edge_pad [2, e_cap], ptrs_pad [2, G + 2], nnz_expected): graph G is the pad graph - a ring
+    over its n_cap - n nodes carrying the e_cap - E extra edges.  `ptrs_pad[0, :G + 1]` are the readout segments.
+    `nnz_expected` = edges that are not self-loops + one loop per node = nnz of the prepared graph (add_self_loops)."""
+    n, e = int(x.size(0)), int(edge_local.size(1))
+    p, q = n_cap - n, e_cap - e
+    if p < 2 or q < 1:
+        raise ValueError(f"pad_batch: capacity too small (nodes {n} -> {n_cap}, edges {e} -> {e_cap}; need >= 2 pad nodes "
+                         "and >= 1 pad edge)")
+    if q > p * (_lib.EGC_CHUNK_EDGES // 2):
+        raise ValueError(f"pad_batch: {q} pad edges over {p} pad nodes would create rows longer than the chunk size")
+    x_pad = torch.zeros((n_cap, x.size(1)), dtype=x.dtype)
+    x_pad[:n] = x
+    k = torch.arange(q, dtype=torch.int64)
+    ring = torch.stack([(k + p - 1) % p, k % p])                 # edge 0 leaves the LAST pad node: the largest id is always used
+    edge_pad = torch.cat([edge_local.to(torch.int64), ring], 1)
+    g = ptrs.size(1) - 1
+    ptrs_pad = torch.empty((2, g + 2), dtype=torch.int32)
+    ptrs_pad[:, :g + 1] = ptrs
+    ptrs_pad[0, g + 1], ptrs_pad[1, g + 1] = n_cap, e_cap
+    loops = int((edge_local[0] == edge_local[1]).sum())          # graph-local ids: a loop is a loop
+    return x_pad, edge_pad, ptrs_pad, (e - loops) + q + n_cap

@@ -475,3 +475,69 @@ class GradientAllReduce:
                     p.grad = flat[off:off + n].view_as(p).clone()
                 else:
                     p.grad.copy_(flat[off:off + n].view_as(p))
+
+
+class OverlappedGradientAllReduce:
+    """`GradientAllReduce` launched from inside the backward pass: one persistent flat bucket per module of
+    `modules` (a layer each), all-reduced asynchronously as soon as the LAST gradient of that bucket has been
+    accumulated (`register_post_accumulate_grad_hook`), i.e. while autograd is still running the backward of the
+    layers below it ("bucketed all-reduce of grads per step overlapped with the previous layer's
+    backward").  Protocol per step:  `begin(weight)` -> `loss.backward()` -> `finish()`; afterwards every `p.grad`
+    holds  sum_r weight_r * grad_r  (weight = this rank's share of the global batch, default 1 / world_size).
+    Works with NCCL (GPU) and gloo (CPU tests)."""
+
+    def __init__(self, modules, group=None):
+        self.group = group
+        self.buckets = []                                   # [flat, [(param, offset, numel)], pending, handle]
+        self._of = {}
+        for m in modules:
+            ps = [p for p in m.parameters() if p.requires_grad]
+            if not ps:
+                continue
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+            views, off = [], 0
+            for p in ps:
+                views.append((p, off, p.numel()))
+                off += p.numel()
+            b = {"flat": flat, "views": views, "pending": 0, "handle": None}
+            self.buckets.append(b)
+            for p in ps:
+                self._of[p] = b
+                p.register_post_accumulate_grad_hook(self._hook)
+        self._weight = None
+
+    def begin(self, weight: float = None):
+        world = dist.get_world_size(self.group)
+        self._weight = (1.0 / world) if weight is None else float(weight)
+        for b in self.buckets:
+            b["pending"], b["handle"] = len(b["views"]), None
+
+    def _hook(self, p):
+        if self._weight is None:                            # backward outside a begin() / finish() pair: plain local grads
+            return
+        b = self._of[p]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            with torch.no_grad():
+                for q, off, n in b["views"]:
+                    torch.mul(q.grad.reshape(-1), self._weight, out=b["flat"][off:off + n])
+            b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    @torch.no_grad()
+    def finish(self):
+        for b in self.buckets:
+            if b["handle"] is None:                         # a bucket whose parameters received no gradient this step
+                for q, off, n in b["views"]:
+                    if q.grad is None:
+                        b["flat"][off:off + n].zero_()
+                    else:
+                        torch.mul(q.grad.reshape(-1), self._weight, out=b["flat"][off:off + n])
+                b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        for b in self.buckets:
+            b["handle"].wait()
+            for q, off, n in b["views"]:
+                if q.grad is None:
+                    q.grad = b["flat"][off:off + n].view_as(q).clone()
+                else:
+                    q.grad.copy_(b["flat"][off:off + n].view_as(q))
+        self._weight = None

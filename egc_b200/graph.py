@@ -208,7 +208,12 @@ class GraphStructure:
         return g
 
     @staticmethod
-    def from_edge_index(edge_index: Tensor, num_nodes: int, symnorm: bool, add_self_loops: bool) -> "GraphStructure":
+    def from_edge_index(edge_index: Tensor, num_nodes: int, symnorm: bool, add_self_loops: bool,
+                        expect: Optional[dict] = None) -> "GraphStructure":
+        """`expect` (fixed-shape mini-batches, see `egc_b200.batch.pad_batch`): {"nnz": ..} - the caller KNOWS the size of
+        the prepared graph (and that no row or column exceeds EGC_CHUNK_EDGES entries), so the one device-to-host read
+        of graph preparation is skipped and the whole build can be captured in a CUDA graph; `verify()` compares the
+        device-side counters with the expectation afterwards."""
         if not edge_index.is_cuda:
             raise RuntimeError("egc_b200: edge_index must live on a CUDA device (there is no CPU path)")
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
@@ -231,7 +236,7 @@ class GraphStructure:
         with torch.cuda.device(dev):
             check(lib.egc_csr_from_edges(ptr(ei[0]), ptr(ei[1]), n_edges, num_nodes, loops, ptr(g.rowptr), ptr(col_cap),
                                          ptr(meta), ptr(ws), nbytes, _stream()), "egc_csr_from_edges")
-            g._finish(meta, col_cap, None, symnorm, keep_values=False)
+            g._finish(meta, col_cap, None, symnorm, keep_values=False, expect=expect)
         return g
 
     @staticmethod
@@ -288,10 +293,17 @@ class GraphStructure:
         g.val_lin = val_lin.to(dev, torch.float32).contiguous() if val_lin is not None else None
         return g
 
-    def _finish(self, meta: Tensor, col_cap: Tensor, val_cap: Optional[Tensor], symnorm: bool, keep_values: bool):
+    def _finish(self, meta: Tensor, col_cap: Tensor, val_cap: Optional[Tensor], symnorm: bool, keep_values: bool,
+                expect: Optional[dict] = None):
         lib = _lib.load()
-        m = meta.cpu().tolist()                    # the one host sync of graph preparation
-        _raise_on_flags(m[_lib.META_ERRFLAGS])
+        if expect is None:
+            m = meta.cpu().tolist()                # the one host sync of graph preparation
+            _raise_on_flags(m[_lib.META_ERRFLAGS])
+        else:                                      # trusted shape: no host read, checked later by verify()
+            m = [0] * _lib.META_SLOTS
+            m[_lib.META_NNZ] = int(expect["nnz"])
+            self._expected = [(meta, {_lib.META_NNZ: int(expect["nnz"]), _lib.META_N_LONG: 0, _lib.META_N_CHUNKS: 0,
+                                      _lib.META_ERRFLAGS: 0}, "CSR")]
         self.nnz, self.max_deg = m[_lib.META_NNZ], m[_lib.META_MAX_DEG]
         self.n_loops = m[_lib.META_N_LOOPS]
         self.col = col_cap[: self.nnz]
@@ -308,6 +320,18 @@ class GraphStructure:
         if keep_values and values is not None:
             self.val_lin = values
         self.plan = _Plan(self.rowptr, self.n_dst, m[_lib.META_N_LONG], m[_lib.META_N_CHUNKS])
+
+    def verify(self) -> None:
+        """Fixed-shape graphs (`expect=`): compare the counters the build kernels left on the device with what the caller
+        promised (synchronises).  Raises if the graph has a different nnz, an id out of range or a row / column too
+        long for the plan-free kernels - the results computed from it are then invalid."""
+        for meta, want, what in getattr(self, "_expected", []):
+            got = meta.cpu().tolist()
+            _raise_on_flags(got[_lib.META_ERRFLAGS])
+            for k, v in want.items():
+                if got[k] != v:
+                    raise ValueError(f"egc_b200: fixed-shape graph does not match its declared shape ({what}: counter {k} is "
+                                     f"{got[k]}, declared {v}) - pad the batch with egc_b200.pad_batch or drop `expect`")
 
     def ensure_csc(self) -> None:
         """CSC view + CSC-ordered weights + its chunk plan (backward only; cached)."""
@@ -332,7 +356,11 @@ class GraphStructure:
                     check(lib.egc_permute_f32(ptr(v), ptr(self.csr2csc), self.nnz, ptr(out), _stream()),
                           "egc_permute_f32")
                     setattr(self, "csc_" + name, out)
-            m = meta.cpu().tolist()
+            if getattr(self, "_expected", None):       # fixed-shape graph: no long columns by declaration, no host read
+                self._expected.append((meta, {_lib.META_N_LONG: 0, _lib.META_N_CHUNKS: 0}, "CSC"))
+                m = [0] * _lib.META_SLOTS
+            else:
+                m = meta.cpu().tolist()
             self.csc_plan = _Plan(self.colptr, self.n_src, m[_lib.META_N_LONG], m[_lib.META_N_CHUNKS])
 
     def source_ids(self, arg: Tensor) -> Tensor:

@@ -215,3 +215,102 @@ def test_zinc_shaped_egc_s_four_layers(gemm):
 def test_cifar_shaped_egc_m_four_layers(gemm):
     """BASELINE config 5: EGC-M (symnorm + max + std, 4 heads, 4 bases, hidden 128, 4 layers), kNN superpixel graphs."""
     _stack_case(OB.cifar_like_graphs(32, 5), 128, 128, ["symnorm", "max", "std"], 4, 4, "mean", 1, gemm)
+
+
+# ------------------------------------------------------------------------------------------------
+# fixed-shape batches: host-side padding + sync-free graph build, replayed from one CUDA graph
+# ------------------------------------------------------------------------------------------------
+def _pack(graphs):
+    counts = torch.tensor([[g[2], g[1].size(1)] for g in graphs])
+    ptrs = torch.zeros((2, len(graphs) + 1), dtype=torch.int32)
+    ptrs[:, 1:] = counts.cumsum(0).t().to(torch.int32)
+    return torch.cat([g[0] for g in graphs]), torch.cat([g[1] for g in graphs], 1), ptrs
+
+
+def test_pad_batch_host_arrays():
+    import egc_b200
+    graphs = OB.zinc_like_graphs(6, seed=5)
+    graphs = [(torch.randn(n, 4), ei, n) for _, ei, n in graphs]
+    x, el, ptrs = _pack(graphs)
+    n, e = x.size(0), el.size(1)
+    xp, ep, pp, nnz = egc_b200.pad_batch(x, el, ptrs, n + 10, e + 25)
+    assert xp.shape == (n + 10, 4) and ep.shape == (2, e + 25) and pp.shape == (2, 8)
+    assert torch.equal(xp[:n], x) and float(xp[n:].abs().sum()) == 0.0 and torch.equal(ep[:, :e], el)
+    assert pp[0, -1] == n + 10 and pp[1, -1] == e + 25 and torch.equal(pp[:, :-1], ptrs)
+    ring = ep[:, e:]
+    assert int(ring.max()) == 9 and int(ring.min()) == 0 and bool((ring[0] != ring[1]).all())     # pad-graph local ids
+    assert int(torch.bincount(ring[1], minlength=10).max()) <= 3                                   # short rows only
+    assert nnz == e + 25 + n + 10
+    with pytest.raises(ValueError):
+        egc_b200.pad_batch(x, el, ptrs, n + 1, e + 5)
+    with pytest.raises(ValueError):
+        egc_b200.pad_batch(x, el, ptrs, n + 2, e + 2000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aggrs,heads", [(["sum"], 8), (["symnorm", "max", "std"], 4)])
+def test_fixed_shape_step_replays_from_one_cuda_graph(aggrs, heads):
+    """Padded batches of different sizes through ONE captured step == the eager, unpadded step on each batch; a batch
+    that breaks the declared shape is caught by verify()."""
+    import egc_b200
+    from egc_b200.dist import GraphedStep
+    dev = "cuda:0"
+    torch.manual_seed(3)
+    f = 32
+    model = torch.nn.ModuleList([egc_b200.EGConv(f, f, aggrs=aggrs, num_heads=heads, num_bases=4) for _ in range(2)]).to(dev)
+    params = list(model.parameters())
+    sym = "symnorm" in aggrs
+    batches = []
+    for seed in (1, 2, 3):
+        gs = OB.zinc_like_graphs(16 + seed, seed=seed)[:16]
+        gen = torch.Generator().manual_seed(seed)
+        batches.append(_pack([(torch.randn(n, f, generator=gen), ei, n) for _, ei, n in gs]))
+    n_cap = max(b[0].size(0) for b in batches) + 16
+    e_cap = max(b[1].size(1) for b in batches) + 1
+    padded = [egc_b200.pad_batch(*b, n_cap, e_cap) for b in batches]
+    assert len({p[3] for p in padded}) == 1
+    xs = torch.zeros((n_cap, f), device=dev, requires_grad=True)
+    els = torch.zeros((2, e_cap), dtype=torch.int64, device=dev)
+    pts = torch.zeros((2, 18), dtype=torch.int32, device=dev)
+    keep = {}
+
+    def loss_of(x, el, pt, n_graphs, expect):
+        n = int(x.size(0))
+        ei, _ = egc_b200.collate_arrays(el, pt[1], pt[0], num_nodes=n, validate=False)
+        g = egc_b200.GraphStructure.from_edge_index(ei, n, sym, True, expect=expect)
+        keep["g"] = g
+        h = x
+        for layer in model:
+            h = torch.relu(layer(h, g))
+        return egc_b200.global_mean_pool(h, pt[0, :n_graphs + 1]).pow(2).sum(1).mean()
+
+    def static_step():
+        loss = loss_of(xs, els, pts, 16, {"nnz": padded[0][3]})
+        return (loss,) + torch.autograd.grad(loss, [xs] + params)
+
+    def load(p):
+        with torch.no_grad():
+            xs.copy_(p[0].to(dev)); els.copy_(p[1].to(dev)); pts.copy_(p[2].to(dev))
+
+    load(padded[0])
+    graphed = GraphedStep(static_step, warmup=2)
+    g_static = keep["g"]                                      # the graph object of the captured build: its counters are static buffers
+    for b, p in zip(batches, padded):
+        load(p)
+        res = graphed.replay()
+        g_static.verify()
+        x = b[0].to(dev).requires_grad_(True)
+        loss = loss_of(x, b[1].to(dev), b[2].to(dev), 16, None)
+        ref = torch.autograd.grad(loss, [x] + params)
+        assert rel_err(res[0], loss) < 1e-6
+        assert rel_err(res[1][:x.size(0)], ref[0]) < 1e-5 and float(res[1][x.size(0):].abs().max()) == 0.0
+        for a, r in zip(res[2:], ref[1:]):
+            assert rel_err(a, r) < 1e-5
+    # a batch whose real edges contain a self-loop has one nnz less than declared: verify() must say so
+    bad = list(padded[1])
+    bad[1] = bad[1].clone()
+    bad[1][1, 0] = bad[1][0, 0]
+    load(bad)
+    graphed.replay()
+    with pytest.raises(ValueError):
+        g_static.verify()

@@ -157,6 +157,19 @@ def _dp_worker(rank, world, port, ret):
         sync(weight=len(mine) / len(graphs))
         for p, q in zip(model.parameters(), ref.parameters()):
             assert rel_err(p.grad, q.grad) < 1e-11
+        # the same through the overlapped variant: per-layer buckets launched from inside backward, two steps in a row
+        from egc_b200.dist import OverlappedGradientAllReduce
+        model2 = _dp_model(7)
+        over = OverlappedGradientAllReduce(list(model2))
+        assert len(over.buckets) == 2
+        for _ in range(2):
+            for p in model2.parameters():
+                p.grad = None
+            over.begin(weight=len(mine) / len(graphs))
+            _dp_loss(model2, mine).backward()
+            over.finish()
+            for p, q in zip(model2.parameters(), ref.parameters()):
+                assert rel_err(p.grad, q.grad) < 1e-11
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
