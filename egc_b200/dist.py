@@ -230,9 +230,12 @@ class PartitionedGraph:
         # a row subset runs slower than the contiguous whole-graph launch (per-row staging), and with ~15 nnz per
         # row and 20 % remote sources only a few rows are interior.  Below one half: wait, then ONE contiguous launch.
         self.overlap_interior = part.interior_rows.numel() * 2 >= max(part.n_local, 1)
-        # backward: halo columns of pass 2 first, their push on a side stream while the own columns run (A/B switch)
+        # backward: halo columns of pass 2 first, their push on a side stream while the own columns run.  Measured on
+        # 2 x B200 (profiles/r02c): with a routed (min / max) aggregator the column phases cost more than they hide - the
+        # routing has to come first, so d_bases is zeroed and pass 2 turns into a read-modify-write (0.91 vs 0.82 ms per
+        # arxiv-shaped EGC-M step) - so "auto" splits only layers without min / max.  EGC_DIST_SPLIT_BWD=0|1 forces it.
         import os
-        self.split_backward = os.environ.get("EGC_DIST_SPLIT_BWD", "1") == "1"
+        self.split_backward = os.environ.get("EGC_DIST_SPLIT_BWD", "auto")
         self.group = group
         self._peer_ctx = {}
 
@@ -314,7 +317,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         out, _, _, saved, saved_arg = outs
         if needs_grad:
             ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg)
-        ctx.pg, ctx.desc, ctx.algo, ctx.peer, ctx.bwd_flags = pg, desc, algo, peer, int(bwd_flags)
+        ctx.pg, ctx.desc, ctx.algo, ctx.peer, ctx.bwd_flags, ctx.aggrs = pg, desc, algo, peer, int(bwd_flags), tuple(aggrs)
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
@@ -361,7 +364,8 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 with torch.cuda.stream(peer.side_stream):
                     peer.push_backward(d_ext)
 
-            if pg.split_backward:
+            routed = any(a in ("max", "min") for a in ctx.aggrs)
+            if pg.split_backward == "1" or (pg.split_backward == "auto" and not routed):
                 d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
                                                               out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
