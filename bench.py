@@ -841,6 +841,66 @@ def synth_small_graphs(kind: str, num_graphs: int, seed: int, f_in: int):
     return out
 
 
+class StaticBatchStep:
+    """Fixed-shape mini-batch step: every batch padded on the host (the DataLoader's collate step) to the same node /
+    edge counts, so the WHOLE step - collation, CSR + CSC build, the layer stack forward + backward, readout, loss -
+    is captured once and replayed from ONE CUDA graph per batch.  `flat_scale` (data-parallel runs): the parameter
+    gradients are also packed, scaled, into one flat buffer inside the graph (`self.flat`) for a single all-reduce."""
+
+    def __init__(self, model, packed, n_graphs, f_in, sym, dev, flat_scale=None):
+        import egc_b200
+        from egc_b200.dist import GraphedStep
+        self.n_graphs = n_graphs
+        e_cap = max(int(pk[1].size(1)) for pk in packed) + 1
+        q_max = e_cap - min(int(pk[1].size(1)) for pk in packed)
+        n_cap = max(int(pk[0].size(0)) for pk in packed) + max(64, (q_max + 63) // 64)
+        padded = [egc_b200.pad_batch(pk[0], pk[1], pk[2], n_cap, e_cap) for pk in packed]
+        shapes = {p_[3] for p_ in padded}
+        if len(shapes) != 1:
+            raise ValueError("batches with self-loops in their edge lists do not share one prepared-graph size")
+        nnz_cap = shapes.pop()
+        self.n_cap, self.e_cap = n_cap, e_cap
+        self.pinned = [tuple(t.pin_memory() for t in p_[:3]) for p_ in padded]
+        self.resident = [tuple(t.to(dev) for t in p_) for p_ in self.pinned]
+        self.xs = torch.zeros((n_cap, f_in), device=dev, requires_grad=True)
+        self.els = torch.zeros((2, e_cap), dtype=torch.int64, device=dev)
+        self.pts = torch.zeros((2, n_graphs + 2), dtype=torch.int32, device=dev)
+        params = list(model.parameters())
+        self.flat = torch.zeros(sum(p_.numel() for p_ in params), device=dev) if flat_scale is not None else None
+        keep = {}
+
+        def static_step():
+            edge_index, _ = egc_b200.collate_arrays(self.els, self.pts[1], self.pts[0], num_nodes=n_cap, validate=False)
+            g = egc_b200.GraphStructure.from_edge_index(edge_index, n_cap, sym, True, expect={"nnz": nnz_cap})
+            keep["g"] = g
+            h = self.xs
+            for layer in model:
+                h = torch.relu(layer(h, g))
+            loss = egc_b200.global_mean_pool(h, self.pts[0, :n_graphs + 1]).pow(2).sum(1).mean()
+            grads = torch.autograd.grad(loss, [self.xs] + params)
+            if self.flat is not None:
+                torch.cat([gr.reshape(-1) for gr in grads[1:]], out=self.flat)
+                self.flat.mul_(flat_scale)
+            return (loss,) + grads
+
+        self.load(0)
+        self.graphed = GraphedStep(static_step, warmup=2)
+        self.graph = keep["g"]                            # its counters are static buffers of the captured build
+
+    def load(self, k, pinned=False):
+        src = (self.pinned if pinned else self.resident)[k % len(self.resident)]
+        with torch.no_grad():
+            self.xs.copy_(src[0], non_blocking=True)
+            self.els.copy_(src[1], non_blocking=True)
+            self.pts.copy_(src[2], non_blocking=True)
+
+    def replay(self):
+        return self.graphed.replay()
+
+    def verify(self):
+        self.graph.verify()
+
+
 def run_minibatch(args, m):
     """One step = one collated batch of small graphs through `layers` x (EGConv -> ReLU), mean readout, squared-norm
     loss, backward.  The graph structure is NOT cached (every batch is new, as in the reference's mini-batch training):
@@ -895,59 +955,32 @@ def run_minibatch(args, m):
     nnz = sum(nnz_per_step) / n_batches                   # mean aggregated nnz (edges + self-loops) per layer and step
     nodes = sum(int(pk[0].size(0)) for pk in packed) / n_batches
 
-    # ---- fixed-shape path: every batch padded on the host (the DataLoader's collate step) to the same node / edge counts,
-    # so the WHOLE step - collation, CSR + CSC build, 4 layers forward + backward, readout, loss - is one CUDA graph
-    # replayed per batch (the eager path above pays ~65 launches and two device-to-host reads of graph preparation)
-    from egc_b200.dist import GraphedStep
-    e_cap = max(int(pk[1].size(1)) for pk in packed) + 1
-    q_max = e_cap - min(int(pk[1].size(1)) for pk in packed)
-    n_cap = max(int(pk[0].size(0)) for pk in packed) + max(64, (q_max + 63) // 64)
-    padded = [egc_b200.pad_batch(pk[0], pk[1], pk[2], n_cap, e_cap) for pk in packed]
-    nnz_static = {p_[3] for p_ in padded}
-    static_ok = len(nnz_static) == 1 and not args.no_graph
+    # ---- fixed-shape path (StaticBatchStep): the eager path above pays ~50 launches and two device-to-host reads of
+    # graph preparation per step; padded to one shape the whole step replays from ONE CUDA graph
+    static = None
     ms_static = ms_static_e2e = parity_static = None
+    n_cap = e_cap = None
+    if not args.no_graph:
+        try:
+            static = StaticBatchStep(model, packed, m["graphs"], m["f_in"], sym, dev)
+            n_cap, e_cap = static.n_cap, static.e_cap
+        except ValueError:
+            static = None
+    static_ok = static is not None
     if static_ok:
-        nnz_cap = nnz_static.pop()
-        padded_pinned = [tuple(t.pin_memory() for t in p_[:3]) for p_ in padded]
-        padded_dev = [tuple(t.to(dev) for t in p_) for p_ in padded_pinned]
-        xs = torch.zeros((n_cap, m["f_in"]), device=dev, requires_grad=True)
-        els = torch.zeros((2, e_cap), dtype=torch.int64, device=dev)
-        pts = torch.zeros((2, m["graphs"] + 2), dtype=torch.int32, device=dev)
-        keep = {}
-
-        def static_step():
-            edge_index, _ = egc_b200.collate_arrays(els, pts[1], pts[0], num_nodes=n_cap, validate=False)
-            g = egc_b200.GraphStructure.from_edge_index(edge_index, n_cap, sym, True, expect={"nnz": nnz_cap})
-            keep["g"] = g
-            h = xs
-            for layer in model:
-                h = torch.relu(layer(h, g))
-            loss = egc_b200.global_mean_pool(h, pts[0, :m["graphs"] + 1]).pow(2).sum(1).mean()
-            return (loss,) + torch.autograd.grad(loss, [xs] + params)
-
-        def load_static(src):
-            with torch.no_grad():
-                xs.copy_(src[0], non_blocking=True)
-                els.copy_(src[1], non_blocking=True)
-                pts.copy_(src[2], non_blocking=True)
-
-        load_static(padded_dev[0])
-        graphed = GraphedStep(static_step, warmup=2)
-        g_static = keep["g"]
-
         def step_static():
             k = state["k"]; state["k"] = k + 1
-            load_static(padded_dev[k % n_batches])
-            return graphed.replay()
+            static.load(k)
+            return static.replay()
 
         def step_static_e2e():
             k = state["k"]; state["k"] = k + 1
-            load_static(padded_pinned[k % n_batches])
-            return float(graphed.replay()[0].item())
+            static.load(k, pinned=True)
+            return float(static.replay()[0].item())
 
+        static.load(3)
+        res = static.replay()
         # parity of the padded replay against the eager, unpadded step on the same batch (parameter gradients)
-        load_static(padded_dev[3])
-        res = graphed.replay()
         x3, el3, pt3, _ = resident[3]
         x3 = x3.detach().requires_grad_(True)
         ei3, _ = egc_b200.collate_arrays(el3, pt3[1], pt3[0], num_nodes=int(x3.size(0)), validate=False)
@@ -958,7 +991,7 @@ def run_minibatch(args, m):
         loss3 = egc_b200.global_mean_pool(h3, pt3[0]).pow(2).sum(1).mean()
         ref3 = torch.autograd.grad(loss3, [x3] + params)
         errs = [rel_err(res[0], loss3), rel_err(res[1][:x3.size(0)], ref3[0])] + [rel_err(a, b) for a, b in zip(res[2:], ref3[1:])]
-        g_static.verify()
+        static.verify()
         parity_static = {"against": "the eager, unpadded step on the same batch (loss, d_x rows, parameter gradients)",
                          "max_rel_err": max(errs), "tol": 1e-5, "ok": bool(max(errs) < 1e-5)}
 
@@ -982,7 +1015,7 @@ def run_minibatch(args, m):
         if static_ok:
             ms_static, _ = timed(step_static, steps, args.warmup)
             ms_static_e2e, _ = timed(step_static_e2e, steps, 2)
-            g_static.verify()                             # the replayed builds still match the declared shape
+            static.verify()                               # the replayed builds still match the declared shape
     ms, ms_e2e = (ms_static, ms_static_e2e) if static_ok else (ms_eager, ms_eager_e2e)
     _lib.profile_enable(True)
     for _ in range(steps):
@@ -1124,9 +1157,48 @@ def run_minibatch_dp(args, m):
 
     nnz_local = sum(step()[1] for _ in range(n_batches)) / n_batches      # also the warm-up of every kernel shape
     steps = max(args.steps, n_batches)
+
+    # fixed-shape path: the whole local step replays from ONE CUDA graph, which also packs the (scaled) parameter
+    # gradients into one flat buffer; then ONE NCCL all-reduce of that buffer.  Every rank pads to its own capacity.
+    static = None
+    if not args.no_graph:
+        try:
+            static = StaticBatchStep(model, packed, m["graphs"], m["f_in"], sym, dev, flat_scale=1.0 / world)
+        except ValueError:
+            static = None
+    ok_all = torch.tensor([1.0 if static is not None else 0.0], device=dev)
+    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    use_static = bool(ok_all.item() > 0)
+
+    def step_static(pinned=False, read_loss=False):
+        k = state["k"]; state["k"] = k + 1
+        static.load(k, pinned=pinned)
+        res = static.replay()
+        dist.all_reduce(static.flat, op=dist.ReduceOp.SUM)
+        return float(res[0].item()) if read_loss else res[0]
+
+    parity_static = None
+    if use_static:
+        # same batch as the eager parity above (batch 0): flat buffer == the eager overlapped all-reduce result
+        static.load(0)
+        static.replay()
+        dist.all_reduce(static.flat, op=dist.ReduceOp.SUM)
+        e = torch.tensor([rel_err(static.flat, torch.cat([g_.reshape(-1) for g_ in dp_grads]))], device=dev, dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        static.verify()
+        parity_static = {"against": "the eager data-parallel step on the same batches (all-reduced parameter gradients)",
+                         "max_rel_err": float(e.item()), "tol": 1e-5, "ok": bool(float(e.item()) < 1e-5)}
     with ClockSampler(dev.index or 0) as clocks:
-        ms, launches = cuda_timed(step, steps, args.warmup, dist.barrier)
-        ms_e2e, _ = cuda_timed(step_e2e, steps, 2, dist.barrier)
+        ms_eager, launches = cuda_timed(step, steps, args.warmup, dist.barrier)
+        ms_eager_e2e, _ = cuda_timed(step_e2e, steps, 2, dist.barrier)
+        if use_static:
+            ms, _ = cuda_timed(step_static, steps, args.warmup, dist.barrier)
+            ms_e2e, _ = cuda_timed(lambda: step_static(True, True), steps, 2, dist.barrier)
+            static.verify()
+        else:
+            ms, ms_e2e = ms_eager, ms_eager_e2e
+    eag = torch.tensor([ms_eager, ms_eager_e2e], device=dev, dtype=torch.float64)
+    dist.all_reduce(eag, op=dist.ReduceOp.MAX)
     t = torch.tensor([ms, ms_e2e, nnz_local * m["layers"], launches], device=dev, dtype=torch.float64)
     tmax, tsum = t.clone(), t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -1147,14 +1219,20 @@ def run_minibatch_dp(args, m):
                        "all_reduce": f"{n_param * 4} B of parameter gradients per step, one NCCL all-reduce per layer launched from "
                                      "inside backward (overlaps the backward of the layers below)",
                        "l2": "working set < L2 (launch-latency regime); batches cycle over 8 different graph lists per rank"},
-            "parity_check": parity, "clocks": clocks.summary(),
+            "parity_check": parity, "parity_check_graph_replay": parity_static,
+            "launch_mode": ("fixed-shape batches: the local step replayed from ONE CUDA graph (it packs the scaled gradients "
+                            "into one flat buffer), then ONE NCCL all-reduce" if use_static else
+                            "eager launches, one NCCL all-reduce per layer launched from inside backward"),
+            "eager_overlapped": {"ms_per_step": float(eag[0]), "e2e_ms_per_step": float(eag[1]),
+                                 "note": "eager launches, per-layer all-reduce launched from backward hooks (host-launch-bound)"},
+            "clocks": clocks.summary(),
             "e2e": {"value": edges / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "input_pipeline": "pinned host arrays of the batch -> device collation -> stack -> loss read back"},
             "gpu_launches": int(float(tsum[3])), "roofline": None, "cpu_baseline": None}))
     dist.destroy_process_group()
-    if not parity["ok"]:
-        sys.exit(f"bench.py: data-parallel gradients differ from the single-process run: {parity}")
+    if not parity["ok"] or (parity_static is not None and not parity_static["ok"]):
+        sys.exit(f"bench.py: data-parallel gradients differ from the single-process run: {parity} {parity_static}")
 
 
 def minibatch_cpu_step_factory(m, graphs):

@@ -51,22 +51,43 @@ __device__ __forceinline__ void raise_flags_of(uint32_t* const* flags, int world
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_peer_push(const __grid_constant__ PushParams p) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  const int total = p.seg_ptr[p.n_seg];
-  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < total; k += warps_total) {
-    int s = 0;
+  // A task = one VEC-float piece of one row; a thread keeps kPushUnroll pieces in flight (all loads, then all posted
+  // stores), so narrow rows (256 B at the mag shape) use every lane and the copy runs at link speed instead of at the
+  // latency of one  index -> row -> store  chain per warp.
+  constexpr int kPushUnroll = 4;
+  const int ppr = p.width / VEC;                                   // pieces per row
+  const int64_t total = static_cast<int64_t>(p.seg_ptr[p.n_seg]) * ppr;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t0 < total; t0 += stride * kPushUnroll) {
+    float v[kPushUnroll][VEC];
+    float* dst[kPushUnroll];
 #pragma unroll
-    for (int t = 1; t < EGC_MAX_PEERS; ++t) s += (t < p.n_seg && k >= p.seg_ptr[t]) ? 1 : 0;
-    const int local = k - p.seg_ptr[s];
-    const int64_t row = p.index != nullptr ? __ldg(p.index + k) : local;
-    const float* src = p.src[s] + row * p.width;
-    float* dst = p.dst[s] + static_cast<int64_t>(local) * p.width;
-    if constexpr (VEC == 4) {
-      for (int c = lane * 4; c < p.width; c += 128)
-        *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
-    } else {
-      for (int c = lane; c < p.width; c += 32) dst[c] = __ldg(src + c);
+    for (int u = 0; u < kPushUnroll; ++u) {
+      const int64_t t = t0 + u * stride;
+      dst[u] = nullptr;
+      if (t < total) {
+        const int k = static_cast<int>(t / ppr), piece = static_cast<int>(t - static_cast<int64_t>(k) * ppr);
+        int s = 0;
+#pragma unroll
+        for (int q = 1; q < EGC_MAX_PEERS; ++q) s += (q < p.n_seg && k >= p.seg_ptr[q]) ? 1 : 0;
+        const int local = k - p.seg_ptr[s];
+        const int64_t row = p.index != nullptr ? __ldg(p.index + k) : local;
+        const float* src = p.src[s] + row * p.width + piece * VEC;
+        dst[u] = p.dst[s] + static_cast<int64_t>(local) * p.width + piece * VEC;
+        if constexpr (VEC == 4) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+          v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
+        } else {
+          v[u][0] = __ldg(src);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) {
+      if (dst[u] != nullptr) {
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst[u]) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        else dst[u][0] = v[u][0];
+      }
     }
   }
   if (p.slot_mask == 0u) return;
@@ -137,18 +158,27 @@ __global__ void k_peer_wait(const uint32_t* flags, int world, int rank, int slot
 // ---- deterministic accumulation of what the peers pushed ----------------------------------------------
 // One warp per local row that at least one peer contributed to: into[row] += sum over its entries (ascending
 // peer order, fixed at plan time) of staging[entry].
+template <int VEC>
 __global__ void __launch_bounds__(256) k_peer_reduce_rows(const float* __restrict__ staging, const int32_t* __restrict__ rows,
                                                           const int32_t* __restrict__ ptr, const int32_t* __restrict__ entry,
                                                           int n_rows, int width, float* __restrict__ into) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps_total) {
-    float* dst = into + static_cast<int64_t>(__ldg(rows + r)) * width;
+  const int ppr = width / VEC;
+  const int64_t total = static_cast<int64_t>(n_rows) * ppr, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int r = static_cast<int>(t / ppr), c = static_cast<int>(t - static_cast<int64_t>(r) * ppr) * VEC;
+    float* dst = into + static_cast<int64_t>(__ldg(rows + r)) * width + c;
     const int b = __ldg(ptr + r), e = __ldg(ptr + r + 1);
-    for (int c = lane; c < width; c += 32) {
-      float acc = dst[c];
-      for (int t = b; t < e; ++t) acc += __ldcs(staging + static_cast<int64_t>(__ldg(entry + t)) * width + c);
-      dst[c] = acc;
+    if constexpr (VEC == 4) {
+      float4 acc = *reinterpret_cast<const float4*>(dst);
+      for (int k = b; k < e; ++k) {                               // ascending peer order, fixed at plan time
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(staging + static_cast<int64_t>(__ldg(entry + k)) * width + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(dst) = acc;
+    } else {
+      float acc = dst[0];
+      for (int k = b; k < e; ++k) acc += __ldcs(staging + static_cast<int64_t>(__ldg(entry + k)) * width + c);
+      dst[0] = acc;
     }
   }
 }
@@ -302,10 +332,11 @@ int egc_peer_push_rows(int32_t n_seg, const float* const* src, float* const* dst
   }
   const int total = seg_ptr[n_seg];
   cudaStream_t st = as_stream(stream);
-  // one warp per row; the grid is capped so that a push running next to a compute kernel (the backward push overlaps
-  // pass 2 of the own columns) leaves that kernel its share of every SM.  EGC_PEER_PUSH_CTAS_PER_SM: A/B runs.
-  static const int ctas_per_sm = [] { const char* e = getenv("EGC_PEER_PUSH_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
-  const int grid = std::max(1, std::min(ceil_div(total, 8), sm_count() * ctas_per_sm));   // an empty push still raises its flags
+  // one thread per 16-byte piece, 4 pieces in flight per thread (EGC_PEER_PUSH_CTAS_PER_SM: A/B runs; 1 CTA per SM measured
+  // 10 % slower on the mag shape, profiles/r02d)
+  static const int ctas_per_sm = [] { const char* e = getenv("EGC_PEER_PUSH_CTAS_PER_SM"); return e ? std::max(1, atoi(e)) : 8; }();
+  const int64_t pieces = static_cast<int64_t>(total) * (vec ? width / 4 : width);
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((pieces + 1023) / 1024, static_cast<int64_t>(sm_count()) * ctas_per_sm)));
   {
     LaunchScope ls("k_peer_push", st);
     if (vec) k_peer_push<4><<<grid, 256, 0, st>>>(p);
@@ -363,10 +394,13 @@ int egc_peer_reduce_rows(const float* staging, const int32_t* rows, const int32_
   if (n_rows == 0) return EGC_OK;
   EGC_REQUIRE(staging && rows && ptr && entry && into, "egc_peer_reduce_rows: null pointer");
   cudaStream_t st = as_stream(stream);
-  const int grid = std::min(ceil_div(n_rows, 8), sm_count() * 8);
+  const bool vec = width % 4 == 0 && aligned16(staging) && aligned16(into);
+  const int64_t pieces = static_cast<int64_t>(n_rows) * (vec ? width / 4 : width);
+  const int grid = static_cast<int>(std::min<int64_t>((pieces + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
   {
     LaunchScope ls("k_peer_reduce_rows", st);
-    k_peer_reduce_rows<<<grid, 256, 0, st>>>(staging, rows, ptr, entry, n_rows, width, into);
+    if (vec) k_peer_reduce_rows<4><<<grid, 256, 0, st>>>(staging, rows, ptr, entry, n_rows, width, into);
+    else k_peer_reduce_rows<1><<<grid, 256, 0, st>>>(staging, rows, ptr, entry, n_rows, width, into);
   }
   EGC_LAUNCH_CHECK("k_peer_reduce_rows");
   return EGC_OK;

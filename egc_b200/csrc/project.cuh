@@ -28,5 +28,15 @@ bool wgrad_tc_supported(int n, int f_in, int bd, int hab);
 size_t wgrad_tc_workspace(int n, int f_in, int bd, int hab);
 int wgrad_tc(const float* x, const float* d_bases, const float* d_lin, int n, int f_in, int bd, int hab,
              float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// deterministic sum of the per-CTA partial tiles [n_cta][128][n_pad]: accumulator column n < n1 -> dW_b[m][n], column
+// n2_col0 + j (j < n2) -> dW_c[j][m]
+int wgrad_reduce(const float* partial, int n_cta, int f_in, int n1, int n2, int n_pad, int n2_col0, float* d_w_bases,
+                 float* d_w_comb, cudaStream_t st);
+
+// the same product with MN-major operands straight from TMA (wgrad_mn.cu): no register transposes
+bool wgrad_mn_supported(int n, int f_in, int bd, int hab);
+size_t wgrad_mn_workspace(int n, int f_in, int bd, int hab);
+int wgrad_mn(const float* x, const float* d_bases, const float* d_lin, int n, int f_in, int bd, int hab,
+             float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace egc

@@ -568,8 +568,8 @@ int project_fwd_tc(const float* x, const float* w_bases, const float* w_comb, co
 }
 
 size_t project_bwd_tc_workspace(int n, int f_in, int bd, int hab) {
-  return std::max(project_bwd_simt_workspace(n, f_in, bd, hab),
-                  wgrad_tc_workspace(n, f_in, bd, hab) + project_bwd_simt_workspace(n, f_in, bd, hab));
+  const size_t wg = std::max(wgrad_tc_workspace(n, f_in, bd, hab), wgrad_mn_workspace(n, f_in, bd, hab));
+  return std::max(project_bwd_simt_workspace(n, f_in, bd, hab), wg + project_bwd_simt_workspace(n, f_in, bd, hab));
 }
 
 int project_bwd_tc(const float* x, const float* w_bases, const float* w_comb, const float* d_bases, const float* d_lin,
@@ -586,10 +586,18 @@ int project_bwd_tc(const float* x, const float* w_bases, const float* w_comb, co
     p.n_terms = n_terms;
     if (int rc = launch_tc(p, st)) return rc;
   }
-  // parameter gradients: contraction over the node dimension
-  if ((d_w_bases != nullptr || d_w_comb != nullptr) && wgrad_tc_supported(n, f_in, bd, hab) && aligned16(x) &&
-      aligned16(d_bases) && aligned16(d_lin)) {
-    const size_t wg_bytes = wgrad_tc_workspace(n, f_in, bd, hab);
+  // parameter gradients: contraction over the node dimension (MN-major operands straight from TMA when the shape allows,
+  // else the transposing kernel)
+  const bool wg_ok = (d_w_bases != nullptr || d_w_comb != nullptr) && aligned16(x) && aligned16(d_bases) && aligned16(d_lin);
+  if (wg_ok && wgrad_mn_supported(n, f_in, bd, hab)) {
+    const size_t wg_bytes = std::max(wgrad_tc_workspace(n, f_in, bd, hab), wgrad_mn_workspace(n, f_in, bd, hab));
+    if (int rc = wgrad_mn(x, d_bases, d_lin, n, f_in, bd, hab, d_w_bases, d_w_comb, n_terms, workspace, wg_bytes, st)) return rc;
+    d_w_bases = nullptr;
+    d_w_comb = nullptr;
+    workspace = static_cast<char*>(workspace) + wg_bytes;
+    workspace_bytes -= wg_bytes;
+  } else if (wg_ok && wgrad_tc_supported(n, f_in, bd, hab)) {
+    const size_t wg_bytes = std::max(wgrad_tc_workspace(n, f_in, bd, hab), wgrad_mn_workspace(n, f_in, bd, hab));
     if (int rc = wgrad_tc(x, d_bases, d_lin, n, f_in, bd, hab, d_w_bases, d_w_comb, n_terms, workspace, wg_bytes, st)) return rc;
     d_w_bases = nullptr;
     d_w_comb = nullptr;

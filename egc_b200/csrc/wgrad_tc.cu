@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const __grid_constan
 // instead of the 37 of a one-thread-per-output walk over 148 partials (23 us -> a few us).
 constexpr int kWgRedSplit = 8;
 __global__ void __launch_bounds__(32 * kWgRedSplit) k_wgrad_reduce(const float* __restrict__ partial, int n_cta, int f_in, int n1,
-                                                                    int n2, int n_pad, float* __restrict__ d_w_bases,
+                                                                    int n2, int n_pad, int n2_col0, float* __restrict__ d_w_bases,
                                                                     float* __restrict__ d_w_comb) {
   __shared__ float sub[kWgRedSplit][32];
   const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(32 * kWgRedSplit) k_wgrad_reduce(const float* 
   const int N = n1 + n2;
   const bool ok = idx < f_in * N;
   const int m = ok ? idx / N : 0, n = ok ? idx - m * N : 0;
-  const float* src = partial + static_cast<int64_t>(m) * n_pad + n;
+  const float* src = partial + static_cast<int64_t>(m) * n_pad + (n < n1 ? n : n2_col0 + (n - n1));
   const int64_t stride = static_cast<int64_t>(kWgM) * n_pad;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
   if (ok) {
@@ -276,6 +276,17 @@ __global__ void __launch_bounds__(32 * kWgRedSplit) k_wgrad_reduce(const float* 
   for (int k = 0; k < kWgRedSplit; ++k) t += sub[k][lane];
   if (n < n1) { if (d_w_bases != nullptr) d_w_bases[static_cast<int64_t>(m) * n1 + n] = t; }
   else if (d_w_comb != nullptr) d_w_comb[static_cast<int64_t>(n - n1) * f_in + m] = t;
+}
+
+int wgrad_reduce(const float* partial, int n_cta, int f_in, int n1, int n2, int n_pad, int n2_col0, float* d_w_bases,
+                 float* d_w_comb, cudaStream_t st) {
+  const int total = f_in * (n1 + n2);
+  {
+    LaunchScope ls("k_wgrad_reduce", st);
+    k_wgrad_reduce<<<ceil_div(total, 32), 32 * kWgRedSplit, 0, st>>>(partial, n_cta, f_in, n1, n2, n_pad, n2_col0, d_w_bases, d_w_comb);
+  }
+  EGC_LAUNCH_CHECK("k_wgrad_reduce");
+  return EGC_OK;
 }
 
 static int round16w(int v) { return (v + 15) / 16 * 16; }
@@ -328,13 +339,7 @@ int wgrad_tc(const float* x, const float* d_bases, const float* d_lin, int n, in
     k_wgrad_tc<<<grid, kWgThreads, smem, st>>>(p);
   }
   EGC_LAUNCH_CHECK("k_wgrad_tc");
-  const int total = f_in * (bd + hab);
-  {
-    LaunchScope ls("k_wgrad_reduce", st);
-    k_wgrad_reduce<<<ceil_div(total, 32), 32 * kWgRedSplit, 0, st>>>(p.partial, grid, f_in, bd, hab, p.n_pad, d_w_bases, d_w_comb);
-  }
-  EGC_LAUNCH_CHECK("k_wgrad_reduce");
-  return EGC_OK;
+  return wgrad_reduce(p.partial, grid, f_in, bd, hab, p.n_pad, bd, d_w_bases, d_w_comb, st);
 }
 
 }  // namespace egc
