@@ -5,11 +5,12 @@
 // The contraction runs over the NODE dimension and both operands are feature-contiguous in memory, i.e. MN-major.
 // k_wgrad_tc (wgrad_tc.cu) transposes them through registers into the K-major no-swizzle layout - its four converter
 // warps move 19 KB in and 38 KB out of shared memory per 16 nodes and bound the kernel.  Here the operands stay as they
-// are: a TMA tensor copy of a [32 nodes x 32 features] box with the 128-byte swizzle lands exactly in the canonical
-// MN-major SWIZZLE_128B layout of the UMMA descriptors (32 contiguous features = one 128-byte row per node, 8-node groups
-// 1 KB apart = SBO, 32-feature blocks one box apart = LBO), so the raw tile IS the hi operand (kind::tf32 ignores the low
-// mantissa bits) and the converters only produce  lo = a - tf32(a)  elementwise - no transposes, half the shared-memory
-// traffic per node.
+// are: a TMA tensor copy of a [32 nodes x 32 features] box in the "128-byte span, 32-byte atom" swizzle lands exactly in
+// the one MN-major layout kind::tf32 accepts, SWIZZLE_128B_BASE32B (32 contiguous features = one 128-byte row per node,
+// the four 32-byte chunks of a row XOR-permuted with the row index mod 4; 4-node groups 512 B apart = SBO, 32-feature
+// blocks one box apart = LBO), so the raw tile IS the hi operand (kind::tf32 ignores the low mantissa bits) and the
+// converters only produce  lo = a - tf32(a)  elementwise - no transposes, half the shared-memory traffic per node.
+// (The plain 16-byte-atom SWIZZLE_128B MN-major layout is rejected by the tf32 MMA: it yields zeros.)
 //   warp  9     copy      one lane: 4 + ceil(n1/32) + ceil(n2/32) boxes per 32-node chunk, mbarrier transaction bytes
 //   warps 5-8   convert   lo tile of the chunk (same offsets: layout-agnostic)
 //   warp  4     MMA       one elected lane; per 8-node k-step: x_hi.d_hi + x_hi.d_lo + x_lo.d_hi into a 128 x N_pad fp32
@@ -51,15 +52,15 @@ struct MnParams {
   float* partial;                        // [grid][kMnM][n_pad]
 };
 
-// MN-major operand in the 128-byte swizzle: 32 contiguous features per node row (128 B), 8-node groups SBO = 1 KB apart,
-// 32-feature blocks LBO apart
+// MN-major tf32 operand, SWIZZLE_128B_BASE32B: 32 contiguous features per node row (128 B), swizzle atom = 4 node rows
+// (512 B); SBO = distance between 4-node groups, LBO = distance between 32-feature blocks
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= static_cast<uint64_t>((1024u >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>((512u >> 4) & 0x3fff) << 32;
   d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                       // layout_type SWIZZLE_128B
+  d |= static_cast<uint64_t>(1) << 61;                       // layout_type SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -241,7 +242,7 @@ static MnEncodeTiledFn mn_encode_tiled() {
   return fn;
 }
 
-// [n_nodes rows x width floats] row-major, boxes of 32 nodes x 32 features in the 128-byte swizzle
+// [n_nodes rows x width floats] row-major, boxes of 32 nodes x 32 features, 128-byte span / 32-byte atom swizzle
 static bool make_mn_map(CUtensorMap* m, const float* base, int width, int n_nodes) {
   MnEncodeTiledFn fn = mn_encode_tiled();
   if (fn == nullptr || base == nullptr || width <= 0) return false;
@@ -250,7 +251,7 @@ static bool make_mn_map(CUtensorMap* m, const float* base, int width, int n_node
   const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kMnChunk)};
   const cuuint32_t es[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int mn_round16(int v) { return (v + 15) / 16 * 16; }
