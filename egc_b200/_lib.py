@@ -27,7 +27,8 @@ AGGR_CODES = {"sum": 0, "mean": 1, "symnorm": 2, "min": 3, "max": 4, "var": 5, "
 class LayerDesc(Structure):
     """mirrors `egc_layer_desc`"""
     _fields_ = [("n_dst", c_int32), ("n_src", c_int32), ("heads", c_int32), ("bases", c_int32),
-                ("dim", c_int32), ("n_aggr", c_int32), ("aggr", c_int32 * EGC_MAX_AGGR), ("sigmoid", c_int32)]
+                ("dim", c_int32), ("n_aggr", c_int32), ("aggr", c_int32 * EGC_MAX_AGGR), ("sigmoid", c_int32),
+                ("relu", c_int32)]
 
 
 class RowPlan(Structure):
@@ -66,7 +67,7 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
-                                    _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "egc_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), _P]),
     "egc_peer_free": (c_int32, [_P]),

@@ -58,6 +58,7 @@ struct AggParams {
   int aggr[EGC_MAX_AGGR];
   int arg_slot[EGC_MAX_AGGR];   // index into saved_arg for min/max aggregators, else -1
   int sigmoid;
+  int relu;      // fused output activation: out = max(out, 0)
   // lane geometry
   int nvec;      // VEC-wide pieces per basis row
   int G;         // lanes per group (power of two, <= 32)

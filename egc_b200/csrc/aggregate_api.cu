@@ -22,6 +22,7 @@ int fill_agg_params(AggParams& p, const egc_layer_desc& d, bool vec4) {
   p.n_arg = n_arg;
   p.n_saved = n_saved_slots(d);
   p.sigmoid = d.sigmoid;
+  p.relu = d.relu;
   const int vec = vec4 ? 4 : 1;
   p.nvec = (p.BD + vec - 1) / vec;
   int g = 1;
@@ -216,12 +217,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
-                      float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum, int32_t flags,
-                      int32_t col_split, void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* out_act, float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum,
+                      int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
   EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
               "egc_aggregate_bwd: null pointer");
+  EGC_REQUIRE((desc->relu != 0) == (out_act != nullptr), "egc_aggregate_bwd: out_act must be given exactly when desc->relu is set");
   const BwdLayout L = bwd_layout(*desc, csc_plan);
   const bool det_route = (flags & EGC_BWD_DETERMINISTIC) != 0 && L.has_route;
   EGC_REQUIRE(!det_route || csr2csc != nullptr, "egc_aggregate_bwd: EGC_BWD_DETERMINISTIC needs csr2csc");
@@ -265,7 +267,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   if (!tail) {
     CombineBwdParams c{};
     c.rowptr = rowptr; c.col = col; c.val_lin = val_lin; c.n_rows = desc->n_dst;
-    c.weightings = weightings; c.grad_out = grad_out; c.saved = saved; c.saved_arg = saved_arg;
+    c.weightings = weightings; c.grad_out = grad_out; c.out_act = out_act; c.saved = saved; c.saved_arg = saved_arg;
     c.d_weightings = d_weightings; c.tstreams = tstreams; c.d_bases = d_bases;
     c.n_saved = n_saved_slots(*desc); c.n_arg = n_arg;
     c.n_ts = L.n_ts; c.ts_sym = L.ts_sym; c.ts_lin = L.ts_lin; c.ts_sq = L.ts_sq;
@@ -289,7 +291,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     c.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;       // interleaved: [n_dst][n_ts][BD]
     c.ts_stream_stride = bd;
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
-               aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
+               aligned16(out_act) && aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
     const bool linw = val_lin != nullptr;
     const int grid = combine_bwd_grid(desc->n_dst);
@@ -431,6 +433,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   }
 
   if (!tail && !fuse_colsum) {
+    EGC_REQUIRE(out_act == nullptr || d_bias == nullptr,
+                "egc_aggregate_bwd: the fused ReLU needs the bias gradient from pass 1 (layer too wide for the fused column sums)");
     if (d_bias != nullptr) {
       if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
     }

@@ -34,6 +34,10 @@ __device__ __forceinline__ void combine_epilogue(const AggParams& p, const float
 #pragma unroll
       for (int k = 0; k < EV; ++k) acc[k] += __ldg(p.bias + o0 + k);
     }
+    if (p.relu) {
+#pragma unroll
+      for (int k = 0; k < EV; ++k) acc[k] = fmaxf(acc[k], 0.f);
+    }
     st_stream<EV>(out + o0, acc);
   }
 }

@@ -271,13 +271,13 @@ class PartitionedGraph:
 class _PartitionedEGConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, pg, heads, num_bases, aggrs, sigmoid, algo, key,
-                grad_mode=True, bwd_flags=0):
+                grad_mode=True, bwd_flags=0, relu=False):
         from . import functional as F
         from . import peer as P
         part, g = pg.part, pg.graph
         x = F._require_cuda_f32("x", x)
         bd = bases_weight.size(1)
-        desc = F.make_desc(g, heads, num_bases, bd // num_bases, aggrs, sigmoid)
+        desc = F.make_desc(g, heads, num_bases, bd // num_bases, aggrs, sigmoid, relu)
         needs_grad = grad_mode and any(ctx.needs_input_grad[:5])       # needs_input_grad ignores torch.no_grad()
         peer = None
         with torch.cuda.device(x.device):
@@ -316,7 +316,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 peer.signal(P.SLOT_CONS)
         out, _, _, saved, saved_arg = outs
         if needs_grad:
-            ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg)
+            ctx.save_for_backward(x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg, out if relu else None)
         ctx.pg, ctx.desc, ctx.algo, ctx.peer, ctx.bwd_flags, ctx.aggrs = pg, desc, algo, peer, int(bwd_flags), tuple(aggrs)
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
@@ -325,7 +325,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         from . import functional as F
         from . import peer as P
-        x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg = ctx.saved_tensors
+        x, bases_weight, comb_weight, bases_ext, weightings, saved, saved_arg, out_act = ctx.saved_tensors
         pg, part, peer = ctx.pg, ctx.pg.part, ctx.peer
         grad_out = F._require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
@@ -335,7 +335,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             if peer is None:
                 d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
                                                                       saved_arg, grad_out, want_b, ctx.bwd_flags,
-                                                                      want_lin_colsum=True)
+                                                                      want_lin_colsum=True, out_act=out_act)
                 d_bases = d_bases_ext[:part.n_local]
                 pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
                 d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
@@ -345,7 +345,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 for t in (d_wb, d_wc, d_bc, d_bias):                          # parameters are replicated
                     if t is not None:
                         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg.group)
-                return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
+                return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 10
             # ---- peer transport: flat parameter-gradient vector [d_wb | d_wc | d_bc | d_bias] in the exchange context
             n_wb, n_wc, hab = bases_weight.numel(), comb_weight.numel(), comb_weight.size(0)
             hd = ctx.desc.heads * ctx.desc.dim
@@ -369,12 +369,12 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
                                                               out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
-                                                              between_phases=push_halo)
+                                                              between_phases=push_halo, out_act=out_act)
                 main.wait_stream(peer.side_stream)
             else:
                 d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
-                                                              out_bias=v_b, out_lin_colsum=v_bc)
+                                                              out_bias=v_b, out_lin_colsum=v_bc, out_act=out_act)
                 peer.push_backward(d_bases_ext)
             peer.wait(P.SLOT_BWD)
             d_bases = d_bases_ext[:part.n_local]
@@ -386,7 +386,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
             d_wc = total[n_wb:n_wb + n_wc].view_as(comb_weight).clone() if need_wc else None
             d_bc = total[n_wb + n_wc:n_wb + n_wc + hab].clone() if want_bc else None
             d_bias = total[n_wb + n_wc + hab:n_wb + n_wc + hab + hd].clone() if want_b else None
-        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
+        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 10
 
 
 def _bwd_flags_of(conv) -> int:
@@ -394,14 +394,14 @@ def _bwd_flags_of(conv) -> int:
     return (_lib.BWD_DETERMINISTIC if getattr(conv, "deterministic", False) else 0) | int(getattr(conv, "bwd_flags", 0))
 
 
-def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv) -> Tensor:
+def partitioned_egconv(x_local: Tensor, pg: PartitionedGraph, conv, relu: bool = False) -> Tensor:
     """Run `conv` (an `egc_b200.EGConv` with replicated parameters) on this rank's rows of a partitioned graph.
     Output rows / input gradients are local; parameter gradients are summed over the ranks (= single-GPU values).
     With the peer transport every layer keeps its own exchange buffers (keyed by the module), one step in flight."""
     return _PartitionedEGConvFunction.apply(x_local, conv.bases_weight, conv.comb_weight.weight, conv.comb_weight.bias,
                                             conv.bias, pg, conv.num_heads, conv.num_bases, tuple(conv.aggregators),
                                             bool(conv.sigmoid), int(conv.gemm_algo), id(conv), torch.is_grad_enabled(),
-                                            (_bwd_flags_of(conv)))
+                                            _bwd_flags_of(conv), bool(relu))
 
 
 class GraphedStep:

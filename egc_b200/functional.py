@@ -16,7 +16,8 @@ from ._lib import LayerDesc, check, ptr
 from .graph import GraphStructure, _stream, _ws
 
 
-def make_desc(graph: GraphStructure, heads: int, bases: int, dim: int, aggrs: Sequence[str], sigmoid: bool) -> LayerDesc:
+def make_desc(graph: GraphStructure, heads: int, bases: int, dim: int, aggrs: Sequence[str], sigmoid: bool,
+              relu: bool = False) -> LayerDesc:
     if len(aggrs) < 1 or len(aggrs) > _lib.EGC_MAX_AGGR:
         raise ValueError(f"between 1 and {_lib.EGC_MAX_AGGR} aggregators are supported, got {len(aggrs)}")
     d = LayerDesc()
@@ -28,6 +29,7 @@ def make_desc(graph: GraphStructure, heads: int, bases: int, dim: int, aggrs: Se
             raise ValueError(f'Unknown aggregator "{a}".')           # ref :246
         d.aggr[i] = _lib.AGGR_CODES[a]
     d.sigmoid = int(bool(sigmoid))
+    d.relu = int(bool(relu))
     return d
 
 
@@ -102,11 +104,13 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
 def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Tensor, saved: Tensor,
                        saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
                        want_lin_colsum: bool = False, out_bias: Optional[Tensor] = None,
-                       out_lin_colsum: Optional[Tensor] = None, col_split: Optional[int] = None, between_phases=None):
+                       out_lin_colsum: Optional[Tensor] = None, col_split: Optional[int] = None, between_phases=None,
+                       out_act: Optional[Tensor] = None):
     """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
     with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias).
     `col_split` (row-partitioned callers): run the source columns >= col_split first (EGC_BWD_COLS_HEAD), call
-    `between_phases(d_bases)` - typically the NVLink push of those rows on a side stream - then the rest (COLS_TAIL)."""
+    `between_phases(d_bases)` - typically the NVLink push of those rows on a side stream - then the rest (COLS_TAIL).
+    `out_act`: the forward's output when the layer carries the fused ReLU (desc.relu): grad_out is masked with it."""
     lib = _lib.load()
     dev = bases.device
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
@@ -132,7 +136,7 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
         check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
                                     ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
                                     graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
-                                    ptr(grad_out), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags | phase_flags,
+                                    ptr(grad_out), ptr(out_act), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags | phase_flags,
                                     int(col_split or 0), ptr(ws), nbytes, _stream()),
               "egc_aggregate_bwd")
 
@@ -176,7 +180,7 @@ def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bas
 class _EGConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, graph, heads, num_bases, aggrs, sigmoid, algo,
-                bwd_flags, grad_mode=True):
+                bwd_flags, grad_mode=True, relu=False):
         x = _require_cuda_f32("x", x)
         bases_weight = _require_cuda_f32("bases_weight", bases_weight)
         comb_weight = _require_cuda_f32("comb_weight.weight", comb_weight)
@@ -185,7 +189,7 @@ class _EGConvFunction(torch.autograd.Function):
         if x.dim() != 2 or x.size(0) != graph.n_src or graph.n_src != graph.n_dst:
             raise ValueError(f"x must be [num_nodes, in_channels] with num_nodes == {graph.n_src}")
         dim = bases_weight.size(1) // num_bases
-        desc = make_desc(graph, heads, num_bases, dim, aggrs, sigmoid)
+        desc = make_desc(graph, heads, num_bases, dim, aggrs, sigmoid, relu)
         # needs_input_grad ignores torch.no_grad(); the caller samples the grad mode before apply()
         needs_grad = grad_mode and any(ctx.needs_input_grad[:5])
         with torch.cuda.device(x.device):
@@ -193,34 +197,37 @@ class _EGConvFunction(torch.autograd.Function):
             out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias,
                                                             want_saved=needs_grad)
         if needs_grad:
-            ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings, saved, saved_arg)
+            # the fused ReLU's backward needs the sign of the output: `out` itself is saved (it is the next layer's
+            # input anyway), nothing extra is written
+            ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, out if relu else None)
         ctx.graph, ctx.desc, ctx.algo, ctx.bwd_flags = graph, desc, algo, bwd_flags
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, bases_weight, comb_weight, bases, weightings, saved, saved_arg = ctx.saved_tensors
+        x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, out_act = ctx.saved_tensors
         grad_out = _require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
         with torch.cuda.device(x.device):
             want_bc = bool(need_bc and ctx.has_comb_bias)
             d_w, d_bases, d_bias, d_bc = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg,
                                                             grad_out, need_b and ctx.has_bias, ctx.bwd_flags,
-                                                            want_lin_colsum=True)
+                                                            want_lin_colsum=True, out_act=out_act)
             d_x, d_wb, d_wc, _ = project_backward(x, bases_weight, comb_weight, d_bases, d_w, need_x, need_wb,
                                                   need_wc, False, ctx.algo)
             if not want_bc:
                 d_bc = None
-        return d_x, d_wb, d_wc, d_bc, d_bias, None, None, None, None, None, None, None, None
+        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
 
 
 def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
            bias: Optional[Tensor], num_heads: int, num_bases: int, aggrs: Sequence[str], sigmoid: bool = False,
-           algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0) -> Tensor:
-    """Differentiable EGConv layer body on a prepared graph."""
+           algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0, relu: bool = False) -> Tensor:
+    """Differentiable EGConv layer body on a prepared graph.  `relu=True` fuses the ReLU that follows the layer in the
+    reference's stacks (mag/models.py:63) into the aggregation epilogue and its mask into the backward's first pass."""
     return _EGConvFunction.apply(x, bases_weight, comb_weight, comb_bias, bias, graph, num_heads, num_bases,
-                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags), torch.is_grad_enabled())
+                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags), torch.is_grad_enabled(), bool(relu))
 
 
 class _ProjectFunction(torch.autograd.Function):

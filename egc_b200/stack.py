@@ -6,6 +6,9 @@ Same constructor arguments, `convs` ModuleList (so `state_dict` keys match: `con
 `reset_parameters()` and `forward(x, adj_t)`.
 
 Differences in execution only:
+  * the ReLU after every hidden layer (ref :63) runs inside the layer: `max(., 0)` in the aggregation kernel's epilogue,
+    `grad * (out > 0)` while the backward's first pass stages the gradient row - no separate elementwise kernels, no
+    extra [N, F] round trips;
   * every layer of the stack uses the same aggregator list, so the prepared graph (CSR, CSC, symnorm weights, plans)
     is built ONCE and shared by the layers (the reference caches one copy per layer, `cached=True`);
   * `forward` also accepts a `PartitionedGraph` (row-partitioned multi-GPU run, `egc_b200.dist`): `x` then holds
@@ -56,14 +59,13 @@ class EGC(torch.nn.Module):
         from .dist import PartitionedGraph, partitioned_egconv
         g = self.prepare(x, adj_t)
         if isinstance(g, PartitionedGraph):
-            def run(conv, h):
-                return partitioned_egconv(h, g, conv)
+            def run(conv, h, relu):
+                return partitioned_egconv(h, g, conv, relu=relu)
         else:
-            def run(conv, h):
-                return conv(h, g)
+            def run(conv, h, relu):
+                return conv(h, g, relu=relu)
         for conv in self.convs[:-1]:                                   # ref :61-65
-            x = run(conv, x)
-            x = F.relu(x)
+            x = run(conv, x, True)                                     # conv + ReLU: fused epilogue / backward mask
             x = F.dropout(x, p=self.dropout, training=self.training)
-        x = run(self.convs[-1], x)[:, :self.out_true]                   # ref :68
+        x = run(self.convs[-1], x, False)[:, :self.out_true]            # ref :68
         return x.log_softmax(dim=-1)                                   # ref :69

@@ -70,6 +70,8 @@ typedef struct egc_layer_desc {
   int32_t n_aggr;                /* A = len(aggrs), 1..EGC_MAX_AGGR                               */
   int32_t aggr[EGC_MAX_AGGR];    /* egc_aggr codes in the order given to the constructor          */
   int32_t sigmoid;               /* weightings went through sigmoid (ref :183-184)                */
+  int32_t relu;                  /* fused epilogue of the stack around the layer (ref mag/models.py:63): out = max(out, 0);
+                                    the backward then masks grad_out with out > 0 (egc_aggregate_bwd `out_act`)   */
 } egc_layer_desc;
 
 /* Row plan: how long rows of a CSR (or columns of its CSC) are split into chunks so that no
@@ -227,7 +229,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
  * min/max aggregator) = CSR position of every CSC entry.  The routed min/max gradients are added AFTER pass 2, which
  * writes every row of d_bases.  d_bias (may be NULL) = column sums of grad_out; d_lin_colsum (may be NULL) = column sums of
  * d_weightings = gradient of the comb-weight bias (ref :108, :182), produced here because pass 1 has the rows in
- * registers - egc_project_bwd then takes d_b_comb = NULL.  flags: EGC_BWD_* bits. */
+ * registers - egc_project_bwd then takes d_b_comb = NULL.  out_act: the forward's `out` (required iff desc->relu, else
+ * NULL): pass 1 uses grad_out[i, c] * (out_act[i, c] > 0).  flags: EGC_BWD_* bits. */
 #define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients with a compare-and-add gather over the CSC instead of fp32
                                    atomics: bit-reproducible from run to run (needs csr2csc; two more gathered rows per
                                    entry and min/max slot) */
@@ -244,8 +247,9 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan,
                       const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
-                      const float* grad_out, float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum,
-                      int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes, void* stream);
+                      const float* grad_out, const float* out_act, float* d_weightings, float* d_bases, float* d_bias,
+                      float* d_lin_colsum, int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row exchange for row-partitioned graphs (no reference counterpart; see DESIGN.md "multi-GPU")

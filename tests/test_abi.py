@@ -38,7 +38,7 @@ def test_abi_version_and_build_info():
 def test_struct_layouts_match_header():
     assert _lib.LayerDesc.aggr.offset == 24 and _lib.LayerDesc.sigmoid.offset == 24 + 4 * 8
     import ctypes
-    assert ctypes.sizeof(_lib.LayerDesc) == 60
+    assert ctypes.sizeof(_lib.LayerDesc) == 64 and _lib.LayerDesc.relu.offset == 60
     assert ctypes.sizeof(_lib.RowPlan) == 8 + 4 * 8
 
 

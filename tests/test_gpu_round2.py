@@ -87,7 +87,7 @@ def test_deterministic_flag_needs_csr2csc_at_the_c_abi():
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     P = _lib.ptr
     rc = lib.egc_aggregate_bwd(desc, P(g.rowptr), P(g.col), None, P(g.colptr), P(g.rowidx), None, None, None,
-                               g.csc_plan.struct, P(bases), P(w), P(saved), P(saved_arg), P(go), P(d_w), P(d_b), None, None,
+                               g.csc_plan.struct, P(bases), P(w), P(saved), P(saved_arg), P(go), None, P(d_w), P(d_b), None, None,
                                _lib.BWD_DETERMINISTIC, 0, P(ws), nbytes, torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"csr2csc" in lib.egc_last_error_string()
 
@@ -206,3 +206,34 @@ def test_backward_column_phases_equal_the_single_call(aggrs, heads, bd, bases_n,
             assert rel_err(seen[split], ref[1][split:]) < 2e-6 if split < n else True
         else:
             assert torch.equal(seen[split], got[1][split:])
+
+
+# ------------------------------------------------------------------------------------------------
+# fused ReLU epilogue
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(128, 128, ["symnorm", "max", "std"], 4, 4), (128, 128, ["symnorm"], 8, 4),
+                                 (64, 84, ["sum", "mean", "min", "var"], 4, 4), (32, 40, ["max", "std", "sum"], 4, 3),
+                                 (128, 352, ["mean"], 8, 4)], ids=lambda c: f"{c[0]}x{c[1]}-{'+'.join(c[2])}")
+def test_fused_relu_equals_relu_after_the_layer(cfg):
+    """conv(x, g, relu=True) == torch.relu(conv(x, g)): identical bits forward, and - because the backward mask
+    grad * (out > 0) is what torch applies - identical gradients up to the atomic order of min/max routing."""
+    f_in, f_out, aggrs, h, b = cfg
+    n = 3000
+    ei = random_graph(n, 30000, seed=81, hub=600).to(DEV)
+    torch.manual_seed(12)
+    c = egc_b200.EGConv(f_in, f_out, aggrs=aggrs, num_heads=h, num_bases=b).to(DEV)
+    with torch.no_grad():
+        c.bias.uniform_(-0.5, 0.5)
+    c.deterministic = True                                    # bit-stable routing: the two runs can be compared exactly
+    x, go = torch.randn(n, f_in, device=DEV), torch.randn(n, f_out, device=DEV)
+    xa = x.clone().requires_grad_(True)
+    ya = torch.relu(c(xa, ei))
+    ga = torch.autograd.grad(ya, [xa] + list(c.parameters()), go)
+    xb = x.clone().requires_grad_(True)
+    yb = c(xb, ei, relu=True)
+    gb = torch.autograd.grad(yb, [xb] + list(c.parameters()), go)
+    assert torch.equal(ya, yb) and float((yb == 0).float().mean()) > 0.2
+    for u, v in zip(ga, gb):
+        assert torch.equal(u, v)
+    with torch.no_grad():
+        assert torch.equal(c(x, ei, relu=True), torch.relu(c(x, ei)))
