@@ -66,6 +66,7 @@ struct AggParams {
   // per-warp shared memory layout (float offsets)
   int sm_agg, sm_w, sm_per_warp;
   int mode;      // 0: chunk tasks then row tasks, 1: merge tasks (one per long row)
+  int rows_per_task;   // row-block kernel: consecutive rows per task (<= EGC_ROWS_PER_TASK); fewer when the launch is small
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -269,13 +269,14 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
   // interior / boundary rows of a partitioned graph): kRowsPerTask consecutive entries of row_map, each row's range
   // staged on its own.  Lane l < nrows holds row l of the block: its id, [rp, rpn) and its offset in the window.
   const bool subset = p.row_map != nullptr;
-  const int n_blocks = (p.n_row_tasks + kRowsPerTask - 1) / kRowsPerTask;
+  const int rpt = p.rows_per_task;                               // <= kRowsPerTask (the staging areas are sized for it)
+  const int n_blocks = (p.n_row_tasks + rpt - 1) / rpt;
   int task = 0;
   if (lane == 0) task = atomicAdd(task_counter, 1);
   task = __shfl_sync(kFull, task, 0);
   while (task < n_blocks) {
-    const int r0 = task * kRowsPerTask;
-    const int nrows = min(kRowsPerTask, p.n_row_tasks - r0);
+    const int r0 = task * rpt;
+    const int nrows = min(rpt, p.n_row_tasks - r0);
     int row_id, rp, rpn;
     if (subset) {
       row_id = __ldg(p.row_map + r0 + min(lane, nrows - 1));
@@ -403,14 +404,26 @@ inline int rows_smem_bytes(const AggParams& p) {
   return RowsSmem(p.A * p.BD, p.HAB).per_warp * kAggWarps * static_cast<int>(sizeof(float));
 }
 
+// Rows per task: kRowsPerTask when there is enough work for every resident warp to get several tasks; a launch over few
+// rows (one rank of an 8-way partition: ~21 k rows against 3552 resident warps) takes fewer, otherwise the kernel lasts
+// as long as ONE serial 8-row task while most warps idle.
+inline int pick_rows_per_task(int n_row_tasks) {
+  const int64_t warps = static_cast<int64_t>(sm_count()) * EGC_ROWS_CTAS * kAggWarps;
+  int rpt = kRowsPerTask;
+  while (rpt > 1 && static_cast<int64_t>(n_row_tasks) < 3 * warps * rpt) rpt >>= 1;
+  return rpt;
+}
+
 template <class Cfg, bool ARG>
-int launch_rows_one(const AggParams& p, int* task_counter, cudaStream_t st) {
+int launch_rows_one(const AggParams& p_in, int* task_counter, cudaStream_t st) {
+  AggParams p = p_in;
+  p.rows_per_task = pick_rows_per_task(p.n_row_tasks);
   auto kern = k_aggregate_rows<Cfg, ARG>;
   const int smem_bytes = rows_smem_bytes(p);
   if (smem_bytes > 48 * 1024) {
     EGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   }
-  const int n_blocks = ceil_div(p.n_row_tasks, kRowsPerTask);
+  const int n_blocks = ceil_div(p.n_row_tasks, p.rows_per_task);
   const int64_t warps_wanted = std::max<int64_t>(n_blocks, p.n_chunks);
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div(warps_wanted, kAggWarps), static_cast<int64_t>(sm_count()) * EGC_ROWS_CTAS));
   {

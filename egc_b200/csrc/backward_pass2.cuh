@@ -16,6 +16,7 @@ struct ScatterParams {
   const float* val_lin;     // CSC order
   int n_cols;
   int col_begin, col_end;   // this launch covers source columns [col_begin, col_end) (and the long columns among them)
+  int cols_per_task;        // column-block kernel: consecutive columns per task (<= kColsPerTask); fewer for small launches
   int n_long, n_chunks;
   const int32_t* long_rows;
   const int32_t* long_chunk_ptr;
@@ -396,13 +397,14 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
   }
 
   // =========================== phase 1: blocks of consecutive columns (dynamic) ===========================
-  const int n_blocks = (p.col_end - p.col_begin + kColsPerTask - 1) / kColsPerTask;
+  const int cpt = p.cols_per_task;
+  const int n_blocks = (p.col_end - p.col_begin + cpt - 1) / cpt;
   int task = 0;
   if (lane == 0) task = atomicAdd(task_counter, 1);
   task = __shfl_sync(kFull, task, 0);
   while (task < n_blocks) {
-    const int c0 = p.col_begin + task * kColsPerTask;
-    const int ncols = min(kColsPerTask, p.col_end - c0);
+    const int c0 = p.col_begin + task * cpt;
+    const int ncols = min(cpt, p.col_end - c0);
     const int cp = __ldg(p.colptr + c0 + min(lane, ncols));    // lanes 0..ncols hold the block's column pointers
     int next_task = 0;
     if (lane == 0) next_task = atomicAdd(task_counter, 1);      // consumed at the end of this task
@@ -431,9 +433,16 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
 }
 
 template <int G>
-static int launch_scatter_cols(const ScatterParams& p, int tsmask, int* task_counter, cudaStream_t st) {
-  const int n_blocks = ceil_div(p.col_end - p.col_begin, kColsPerTask);
+static int launch_scatter_cols(const ScatterParams& p_in, int tsmask, int* task_counter, cudaStream_t st) {
+  ScatterParams p = p_in;
   const int resident = (tsmask & (tsmask - 1)) == 0 ? 4 : 3;     // CTAs per SM, as the launch bounds
+  {   // fewer columns per task when the launch is small (see pick_rows_per_task, aggregate_rows.cuh)
+    const int64_t warps = static_cast<int64_t>(sm_count()) * resident * kAggWarps;
+    int cpt = kColsPerTask;
+    while (cpt > 1 && static_cast<int64_t>(p.col_end - p.col_begin) < 3 * warps * cpt) cpt >>= 1;
+    p.cols_per_task = cpt;
+  }
+  const int n_blocks = ceil_div(p.col_end - p.col_begin, p.cols_per_task);
   const int grid = std::max(1, std::min(ceil_div(std::max(n_blocks, p.n_chunks), kAggWarps), sm_count() * resident));
   {
     LaunchScope egc_ls_("k_scatter_bwd", st);

@@ -8,6 +8,9 @@ N=${2:-8}
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${T}_bench_${N}gpu.json 2> gpurun_out/${T}_bench_${N}gpu.err
 echo "bench rc=$?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
+  bench.py --gpus $N --workload mag --steps 20 --warmup 5 --no-extras > gpurun_out/${T}_bench_${N}gpu_mag.json 2> gpurun_out/${T}_bench_${N}gpu_mag.err
+echo "mag rc=$?"
 for w in cifar zinc; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --gpus $N --workload $w --steps 24 --warmup 5 > gpurun_out/${T}_bench_${N}gpu_$w.json 2> gpurun_out/${T}_bench_${N}gpu_$w.err
