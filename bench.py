@@ -163,10 +163,13 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()                       # nvidia-smi needs a moment to start: a short timed region must not
+            while not self.samples and time.time() - t0 < 3.0:      # end before the first sample exists
+                time.sleep(0.05)
         except OSError:
             self.proc = None
         return self
@@ -176,6 +179,8 @@ class ClockSampler:
             self.samples.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        if self.proc is not None and len(self.samples) < 3:
+            time.sleep(0.25)                       # at least a few samples taken right at the end of the timed region
         if self.proc is not None:
             self.proc.terminate()
             try:
