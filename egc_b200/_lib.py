@@ -10,7 +10,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libegc_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 EGC_MAX_AGGR = 8
 EGC_CHUNK_EDGES = 256
 META_SLOTS = 8
@@ -29,6 +29,11 @@ class LayerDesc(Structure):
     _fields_ = [("n_dst", c_int32), ("n_src", c_int32), ("heads", c_int32), ("bases", c_int32),
                 ("dim", c_int32), ("n_aggr", c_int32), ("aggr", c_int32 * EGC_MAX_AGGR), ("sigmoid", c_int32),
                 ("relu", c_int32)]
+
+
+class Epilogue(Structure):
+    """mirrors `egc_epilogue`"""
+    _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("add", c_void_p)]
 
 
 class RowPlan(Structure):
@@ -63,11 +68,11 @@ SIGNATURES = {
     "egc_saved_slots": (c_int32, [POINTER(LayerDesc)]),
     "egc_saved_arg_slots": (c_int32, [POINTER(LayerDesc)]),
     "egc_aggregate_fwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan)]),
-    "egc_aggregate_fwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, _P, c_int32,
+    "egc_aggregate_fwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, POINTER(Epilogue), _P, c_int32,
                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
-                                    _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "egc_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), _P]),
     "egc_peer_free": (c_int32, [_P]),

@@ -96,18 +96,23 @@ class EGConv(torch.nn.Module):
             setattr(self, cache_attr, g)
         return g
 
-    def forward(self, x: Tensor, edge_index, relu: bool = False) -> Tensor:
-        """`relu=True` (extension, used by `egc_b200.EGC`): returns relu(layer(x)) with the activation fused into the
-        aggregation epilogue and its backward mask into the first backward pass - same values as `torch.relu(layer(x))`."""
+    def forward(self, x: Tensor, edge_index, relu: bool = False, scale: Optional[Tensor] = None,
+                shift: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
+        """Extensions (keyword arguments the reference does not have; used by `egc_b200.EGC` / `egc_b200.EGCBlock`): the
+        stack around the layer fused into the aggregation kernel's epilogue -
+        `relu(layer(x) * scale + shift) + residual`, with `scale` / `shift` an eval-mode BatchNorm folded to constants
+        (`egc_b200.fold_batchnorm`).  Same values as the separate torch ops; the backward masks / scales the incoming
+        gradient inside its first pass."""
         if not x.is_cuda:
             raise RuntimeError("egc_b200.EGConv runs on CUDA (sm_100a) only; move the module and inputs to the GPU")
         if x.size(self.node_dim) == 0:                         # zero-node batch: empty output, zero parameter gradients
             keep = sum(p.sum() for p in self.parameters()) * 0.0
-            return x.new_zeros((0, self.out_channels)) + keep + x.sum() * 0.0     # relu(empty) = empty
+            return x.new_zeros((0, self.out_channels)) + keep + x.sum() * 0.0     # every epilogue of nothing is nothing
         graph = self._prepare(x, edge_index)
         flags = (_lib.BWD_DETERMINISTIC if self.deterministic else 0) | int(getattr(self, "bwd_flags", 0))
         return egconv(x, graph, self.bases_weight, self.comb_weight.weight, self.comb_weight.bias, self.bias,
-                      self.num_heads, self.num_bases, self.aggregators, self.sigmoid, self.gemm_algo, flags, relu)
+                      self.num_heads, self.num_bases, self.aggregators, self.sigmoid, self.gemm_algo, flags, relu,
+                      scale, shift, residual)
 
     def __repr__(self):                                                                          # ref :280-286
         return "{}({}, {}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels,

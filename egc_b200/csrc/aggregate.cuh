@@ -47,6 +47,9 @@ struct AggParams {
   const float* bases;        // [n_src, BD]
   const float* weightings;   // [n_rows, HAB]
   const float* bias;         // [HD] or null
+  const float* epi_scale;    // fused epilogue (egc_epilogue): y = y * scale + shift, [HD] each, or null
+  const float* epi_shift;
+  const float* epi_add;      // [n_rows, HD] added after the activation, or null (may alias out)
   float* out;                // [n_rows, HD] or null
   float* agg_out;            // [n_rows, A, BD] or null   (reference `aggregated`)
   int32_t* arg_out;          // [n_rows, A, BD] or null

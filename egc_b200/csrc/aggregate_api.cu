@@ -139,7 +139,7 @@ size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_r
 
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col, const float* val_sym,
                       const float* val_lin, const egc_row_plan* plan, const float* bases, const float* weightings,
-                      const float* bias, const int32_t* row_subset, int32_t n_subset, float* out, float* agg_out,
+                      const float* bias, const egc_epilogue* epilogue, const int32_t* row_subset, int32_t n_subset, float* out, float* agg_out,
                       int32_t* arg_out, float* saved, int32_t* saved_arg, void* workspace, size_t workspace_bytes,
                       void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_fwd")) return rc;
@@ -170,6 +170,11 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   p.long_counter = reinterpret_cast<int*>(static_cast<char*>(workspace) +
                                           align_up(static_cast<size_t>(p.n_chunks) * p.n_slots * bd * 4, 256));
   p.bases = bases; p.weightings = weightings; p.bias = bias;
+  if (epilogue != nullptr) {
+    EGC_REQUIRE((epilogue->scale == nullptr) == (epilogue->shift == nullptr), "egc_aggregate_fwd: epilogue scale and shift come together");
+    EGC_REQUIRE(out != nullptr || (!epilogue->scale && !epilogue->add), "egc_aggregate_fwd: an epilogue needs the `out` output");
+    p.epi_scale = epilogue->scale; p.epi_shift = epilogue->shift; p.epi_add = epilogue->add;
+  }
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);
   const bool want_arg = (arg_out != nullptr || saved_arg != nullptr) && n_arg > 0;
@@ -179,7 +184,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   p.mode = 0;
   const int hd = desc->heads * desc->dim;
   const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
-                    hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) && (desc->dim % 4 != 0 || aligned16(bias));
+                    hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) &&
+                    (desc->dim % 4 != 0 || (aligned16(bias) && aligned16(p.epi_scale) && aligned16(p.epi_shift) && aligned16(p.epi_add)));
   const int static_idx = fast ? static_cfg_index(*desc) : -1;
   // row-block kernel: whole-graph calls of the specialised shapes (EGC_FWD_WARP_PER_ROW=1 keeps the warp-per-row kernel)
   static const bool legacy_rows = getenv("EGC_FWD_WARP_PER_ROW") != nullptr;
@@ -217,8 +223,9 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
-                      const float* out_act, float* d_weightings, float* d_bases, float* d_bias, float* d_lin_colsum,
-                      int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes, void* stream) {
+                      const float* out_act, const float* epi_scale, float* d_weightings, float* d_bases, float* d_bias,
+                      float* d_lin_colsum, int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
   EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
@@ -267,7 +274,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   if (!tail) {
     CombineBwdParams c{};
     c.rowptr = rowptr; c.col = col; c.val_lin = val_lin; c.n_rows = desc->n_dst;
-    c.weightings = weightings; c.grad_out = grad_out; c.out_act = out_act; c.saved = saved; c.saved_arg = saved_arg;
+    c.weightings = weightings; c.grad_out = grad_out; c.out_act = out_act; c.epi_scale = epi_scale; c.saved = saved; c.saved_arg = saved_arg;
     c.d_weightings = d_weightings; c.tstreams = tstreams; c.d_bases = d_bases;
     c.n_saved = n_saved_slots(*desc); c.n_arg = n_arg;
     c.n_ts = L.n_ts; c.ts_sym = L.ts_sym; c.ts_lin = L.ts_lin; c.ts_sq = L.ts_sq;
@@ -291,7 +298,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     c.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;       // interleaved: [n_dst][n_ts][BD]
     c.ts_stream_stride = bd;
     c.vec16 = (hab % 4 == 0 && hd % 4 == 0 && bd % 4 == 0 && aligned16(weightings) && aligned16(grad_out) &&
-               aligned16(out_act) && aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
+               aligned16(out_act) && aligned16(epi_scale) && aligned16(saved) && aligned16(saved_arg)) ? 1 : 0;
     const bool ev4 = (desc->dim % 4 == 0) && aligned16(tstreams);
     const bool linw = val_lin != nullptr;
     const int grid = combine_bwd_grid(desc->n_dst);
@@ -433,8 +440,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   }
 
   if (!tail && !fuse_colsum) {
-    EGC_REQUIRE(out_act == nullptr || d_bias == nullptr,
-                "egc_aggregate_bwd: the fused ReLU needs the bias gradient from pass 1 (layer too wide for the fused column sums)");
+    EGC_REQUIRE((out_act == nullptr && epi_scale == nullptr) || d_bias == nullptr,
+                "egc_aggregate_bwd: a fused epilogue needs the bias gradient from pass 1 (layer too wide for the fused column sums)");
     if (d_bias != nullptr) {
       if (int rc = colsum_f32(grad_out, desc->n_dst, hd, d_bias, colsum_ws, L.colsum_bytes, st)) return rc;
     }

@@ -42,6 +42,25 @@ __device__ __forceinline__ void stg_f4_hint(float* p, const float (&v)[4], uint6
                ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(pol) : "memory");
 }
 
+// tail of the output epilogue after bias: BatchNorm-eval affine -> ReLU -> post-activation add (egc_epilogue order)
+__device__ __forceinline__ void epilogue_tail4(const AggParams& p, float (&r)[4], int64_t row, int o, int HD) {
+  if (p.epi_scale != nullptr) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.epi_scale + o)), sh = __ldg(reinterpret_cast<const float4*>(p.epi_shift + o));
+    r[0] = fmaf(r[0], sc.x, sh.x); r[1] = fmaf(r[1], sc.y, sh.y); r[2] = fmaf(r[2], sc.z, sh.z); r[3] = fmaf(r[3], sc.w, sh.w);
+  }
+  if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+  if (p.epi_add != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(p.epi_add + row * HD + o);
+    r[0] += a.x; r[1] += a.y; r[2] += a.z; r[3] += a.w;
+  }
+}
+__device__ __forceinline__ float epilogue_tail1(const AggParams& p, float r, int64_t row, int o, int HD) {
+  if (p.epi_scale != nullptr) r = fmaf(r, __ldg(p.epi_scale + o), __ldg(p.epi_shift + o));
+  if (p.relu) r = fmaxf(r, 0.f);
+  if (p.epi_add != nullptr) r += p.epi_add[row * HD + o];
+  return r;
+}
+
 // x / c with r = 1 / c (IEEE reciprocal): one Newton correction of the quotient (correctly rounded up to rare
 // double-rounding cases; exact whenever the quotient is representable)
 __device__ __forceinline__ float div_by(float x, float c, float r) {
@@ -410,14 +429,14 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_aggregate_fast(const __grid_
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + o));
               r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
             }
-            if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+            epilogue_tail4(p, r, row, o, GC::HD(p));
             stg_f4_hint(out + o, r, pol_stream);
           } else {
             float r = 0.f;
 #pragma unroll 4
             for (int ab = 0; ab < AB; ++ab) r = fmaf(wh[ab], ad[ab * D], r);
             if (p.bias != nullptr) r += __ldg(p.bias + o);
-            if (p.relu) r = fmaxf(r, 0.f);
+            r = epilogue_tail1(p, r, row, o, GC::HD(p));
             __stcs(out + o, r);
           }
         }

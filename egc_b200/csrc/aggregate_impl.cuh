@@ -34,9 +34,11 @@ __device__ __forceinline__ void combine_epilogue(const AggParams& p, const float
 #pragma unroll
       for (int k = 0; k < EV; ++k) acc[k] += __ldg(p.bias + o0 + k);
     }
-    if (p.relu) {
 #pragma unroll
-      for (int k = 0; k < EV; ++k) acc[k] = fmaxf(acc[k], 0.f);
+    for (int k = 0; k < EV; ++k) {                            // BatchNorm-eval affine -> ReLU -> post-activation add
+      if (p.epi_scale != nullptr) acc[k] = fmaf(acc[k], __ldg(p.epi_scale + o0 + k), __ldg(p.epi_shift + o0 + k));
+      if (p.relu) acc[k] = fmaxf(acc[k], 0.f);
+      if (p.epi_add != nullptr) acc[k] += p.epi_add[static_cast<int64_t>(row) * p.HD + o0 + k];
     }
     st_stream<EV>(out + o0, acc);
   }

@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(kAggThreads, EGC_ROWS_CTAS) k_aggregate_rows(c
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + o));
             r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
           }
-          if (p.relu) { r[0] = fmaxf(r[0], 0.f); r[1] = fmaxf(r[1], 0.f); r[2] = fmaxf(r[2], 0.f); r[3] = fmaxf(r[3], 0.f); }
+          epilogue_tail4(p, r, row, o, GC::HD(p));
           stg_f4_hint(out + o, r, pol_stream);
         } else {
           float r = 0.f;
 #pragma unroll 4
           for (int ab = 0; ab < AB; ++ab) r = fmaf(wh[ab], ad[ab * D], r);
           if (p.bias != nullptr) r += __ldg(p.bias + o);
-          if (p.relu) r = fmaxf(r, 0.f);
+          r = epilogue_tail1(p, r, row, o, GC::HD(p));
           __stcs(out + o, r);
         }
       }

@@ -24,6 +24,7 @@ struct CombineBwdParams {
   const float* weightings;
   const float* grad_out;
   const float* out_act;       // the forward's out when the layer carries the fused ReLU (grad_out is masked with out > 0), else null
+  const float* epi_scale;     // [HD] scale of the forward's fused affine epilogue (the masked gradient is multiplied by it), or null
   const float* saved;
   const int32_t* saved_arg;
   float* d_weightings;
@@ -106,18 +107,29 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_combine_bwd(const __grid_con
     const float inv_cnt = __frcp_rn(cntf);
     cp_async_wait_all();
     __syncwarp();
-    if (p.out_act != nullptr) {                              // fused ReLU: g <- g * (out > 0), in the staged row
+    if (p.out_act != nullptr || p.epi_scale != nullptr) {    // fused epilogue: g <- g * (out > 0) * scale, in the staged row
       float* gs = sm + GB::sm_g(p);
-      const float* oa = p.out_act + static_cast<int64_t>(row) * HD;
+      const float* oa = p.out_act != nullptr ? p.out_act + static_cast<int64_t>(row) * HD : nullptr;
       if (v16) {
         for (int t = lane * 4; t < HD; t += 128) {
-          const float4 o = __ldcs(reinterpret_cast<const float4*>(oa + t));
           float4 gv = *reinterpret_cast<float4*>(gs + t);
-          gv.x = o.x > 0.f ? gv.x : 0.f; gv.y = o.y > 0.f ? gv.y : 0.f; gv.z = o.z > 0.f ? gv.z : 0.f; gv.w = o.w > 0.f ? gv.w : 0.f;
+          if (oa != nullptr) {
+            const float4 o = __ldcs(reinterpret_cast<const float4*>(oa + t));
+            gv.x = o.x > 0.f ? gv.x : 0.f; gv.y = o.y > 0.f ? gv.y : 0.f; gv.z = o.z > 0.f ? gv.z : 0.f; gv.w = o.w > 0.f ? gv.w : 0.f;
+          }
+          if (p.epi_scale != nullptr) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.epi_scale + t));
+            gv.x *= sc.x; gv.y *= sc.y; gv.z *= sc.z; gv.w *= sc.w;
+          }
           *reinterpret_cast<float4*>(gs + t) = gv;
         }
       } else {
-        for (int t = lane; t < HD; t += 32) gs[t] = __ldcs(oa + t) > 0.f ? gs[t] : 0.f;
+        for (int t = lane; t < HD; t += 32) {
+          float gv = gs[t];
+          if (oa != nullptr) gv = __ldcs(oa + t) > 0.f ? gv : 0.f;
+          if (p.epi_scale != nullptr) gv *= __ldg(p.epi_scale + t);
+          gs[t] = gv;
+        }
       }
       __syncwarp();
     }

@@ -242,12 +242,13 @@ static MnEncodeTiledFn mn_encode_tiled() {
   return fn;
 }
 
-// [n_nodes rows x width floats] row-major, boxes of 32 nodes x 32 features, 128-byte span / 32-byte atom swizzle
-static bool make_mn_map(CUtensorMap* m, const float* base, int width, int n_nodes) {
+// [n_nodes rows x width floats] with a row pitch of ld floats, boxes of 32 nodes x 32 features, 128-byte span / 32-byte atom
+// swizzle; columns past `width` read as zeros (a column range of a wider matrix: base = first column, ld = full width)
+static bool make_mn_map(CUtensorMap* m, const float* base, int width, int ld, int n_nodes) {
   MnEncodeTiledFn fn = mn_encode_tiled();
   if (fn == nullptr || base == nullptr || width <= 0) return false;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(n_nodes)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(width) * 4};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
   const cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kMnChunk)};
   const cuuint32_t es[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -264,36 +265,47 @@ static int mn_raw_stages(int bd, int hab) {
   return static_cast<int>(std::min<size_t>(kMnMaxRaw, (kMnMaxSmem - fixed) / stage));
 }
 
+// Wide layers (more than 256 accumulator columns, e.g. REGConv's paper type: d_lin carries the combination weights of the
+// root term and of every relation): the columns are cut into launches of <= 256 - the first takes d_bases and the leading
+// d_lin columns, the others 256 d_lin columns each (x is streamed once per launch).
+static int mn_first_lin_cols(int bd, int hab) {
+  if (mn_n_pad(bd, hab) <= 256) return hab;
+  return std::max(0, (256 - 32 * ceil_div(bd, 32)) / 32 * 32);
+}
+
 bool wgrad_mn_supported(int n, int f_in, int bd, int hab) {
   static const bool off = getenv("EGC_WGRAD_TRANSPOSE") != nullptr;       // A/B: keep the transposing kernel
-  if (off || n < 1 || f_in % 4 || bd % 4 || hab % 4 || f_in > kMnM || hab < 1) return false;
-  return mn_n_pad(bd, hab) <= 256 && mn_raw_stages(bd, hab) >= 2 && mn_encode_tiled() != nullptr;
+  if (off || n < 1 || f_in % 4 || bd % 4 || hab % 4 || f_in > kMnM || hab < 1 || mn_encode_tiled() == nullptr) return false;
+  const int first = mn_first_lin_cols(bd, hab);
+  if (first < hab && (first < 32 || mn_raw_stages(0, std::min(hab - first, 256)) < 2)) return false;
+  return mn_raw_stages(bd, first) >= 2;
 }
 
 size_t wgrad_mn_workspace(int n, int f_in, int bd, int hab) {
   (void)n; (void)f_in;
-  return static_cast<size_t>(sm_count()) * kMnM * mn_n_pad(bd, hab) * sizeof(float) + 256;
+  return static_cast<size_t>(sm_count()) * kMnM * std::min(256, mn_n_pad(bd, hab)) * sizeof(float) + 256;
 }
 
-int wgrad_mn(const float* x, const float* d_bases, const float* d_lin, int n, int f_in, int bd, int hab,
-             float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  EGC_REQUIRE(workspace_bytes >= wgrad_mn_workspace(n, f_in, bd, hab), "wgrad_mn: workspace too small");
+// one launch: C[F_in, n1 + n2] = x^T . [d1 | d2], d1 / d2 column ranges with row pitches ld1 / ld2 (n1 may be 0)
+static int wgrad_mn_part(const float* x, const float* d1, int n1, int ld1, const float* d2, int n2, int ld2, int n, int f_in,
+                         float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, cudaStream_t st) {
   MnParams p{};
-  p.f_in = f_in; p.n1 = bd; p.n2 = hab; p.n_nodes = n;
-  p.nb1 = ceil_div(bd, 32); p.nb2 = ceil_div(hab, 32);
-  p.n_pad = mn_n_pad(bd, hab);
+  p.f_in = f_in; p.n1 = n1; p.n2 = n2; p.n_nodes = n;
+  p.nb1 = ceil_div(n1, 32); p.nb2 = ceil_div(n2, 32);
+  p.n_pad = mn_n_pad(n1, n2);
   p.n_terms = n_terms;
-  p.raw_stages = mn_raw_stages(bd, hab);
-  EGC_REQUIRE(p.raw_stages >= 2, "wgrad_mn: shape does not fit shared memory");
-  p.stage_bytes = mn_stage_bytes(bd, hab);
+  p.raw_stages = mn_raw_stages(n1, n2);
+  EGC_REQUIRE(p.n_pad <= 256 && p.raw_stages >= 2, "wgrad_mn: shape does not fit the accumulator / shared memory");
+  p.stage_bytes = mn_stage_bytes(n1, n2);
   p.chunks_total = ceil_div(n, kMnChunk);
   const int grid = std::min(sm_count(), p.chunks_total);
   p.chunks_per_cta = ceil_div(p.chunks_total, grid);
   p.partial = static_cast<float*>(workspace);
   alignas(64) CUtensorMap tmx, tm1, tm2;
   memset(&tmx, 0, sizeof(tmx)); memset(&tm1, 0, sizeof(tm1)); memset(&tm2, 0, sizeof(tm2));
-  EGC_REQUIRE(make_mn_map(&tmx, x, f_in, n) && make_mn_map(&tm1, d_bases, bd, n) && make_mn_map(&tm2, d_lin, hab, n),
-              "wgrad_mn: tensor-map encoding failed");
+  EGC_REQUIRE(make_mn_map(&tmx, x, f_in, f_in, n) && make_mn_map(&tm2, d2, n2, ld2, n) &&
+              (n1 == 0 || make_mn_map(&tm1, d1, n1, ld1, n)), "wgrad_mn: tensor-map encoding failed");
+  if (n1 == 0) tm1 = tm2;                                      // never used: no d1 boxes are issued
   const size_t smem = static_cast<size_t>(p.raw_stages + kMnLoStages) * p.stage_bytes + (3 * kMnMaxRaw + kMnLoStages + 4) * 8 + 64 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -305,7 +317,21 @@ int wgrad_mn(const float* x, const float* d_bases, const float* d_lin, int n, in
     k_wgrad_mn<<<grid, kMnThreads, smem, st>>>(p, tmx, tm1, tm2);
   }
   EGC_LAUNCH_CHECK("k_wgrad_mn");
-  return wgrad_reduce(p.partial, grid, f_in, bd, hab, p.n_pad, 32 * p.nb1, d_w_bases, d_w_comb, st);
+  return wgrad_reduce(p.partial, grid, f_in, n1, n2, p.n_pad, 32 * p.nb1, d_w_bases, d_w_comb, st);
+}
+
+int wgrad_mn(const float* x, const float* d_bases, const float* d_lin, int n, int f_in, int bd, int hab,
+             float* d_w_bases, float* d_w_comb, int n_terms, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  EGC_REQUIRE(workspace_bytes >= wgrad_mn_workspace(n, f_in, bd, hab), "wgrad_mn: workspace too small");
+  const int first = mn_first_lin_cols(bd, hab);
+  if (int rc = wgrad_mn_part(x, d_bases, bd, bd, d_lin, first, hab, n, f_in, d_w_bases, d_w_comb, n_terms, workspace, st)) return rc;
+  for (int c0 = first; c0 < hab; c0 += 256) {                  // stream-ordered: the partial tiles are reused
+    const int cols = std::min(256, hab - c0);
+    if (int rc = wgrad_mn_part(x, nullptr, 0, 0, d_lin + c0, cols, hab, n, f_in, nullptr,
+                               d_w_comb != nullptr ? d_w_comb + static_cast<int64_t>(c0) * f_in : nullptr, n_terms, workspace, st))
+      return rc;
+  }
+  return EGC_OK;
 }
 
 }  // namespace egc

@@ -75,10 +75,11 @@ def alloc_aggregate_outputs(desc: LayerDesc, device, want_out=True, want_agg=Fal
 def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, weightings: Optional[Tensor],
                       bias: Optional[Tensor], want_out: bool = True, want_agg: bool = False, want_arg: bool = False,
                       want_saved: bool = False, row_subset: Optional[Tensor] = None, use_plan: bool = True,
-                      outputs=None):
+                      outputs=None, epilogue=None):
     """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg, saved, saved_arg); unrequested ones
     are None.  `saved` / `saved_arg` are what the backward pass consumes (see include/egc_b200.h).
-    `row_subset` (int32 device tensor) restricts the row tasks; `outputs` reuses buffers of a previous call."""
+    `row_subset` (int32 device tensor) restricts the row tasks; `outputs` reuses buffers of a previous call.
+    `epilogue` = (scale, shift, add) tensors or None each: the fused tail  y*scale+shift -> relu (desc.relu) -> +add."""
     lib = _lib.load()
     dev = bases.device
     if outputs is None:
@@ -94,8 +95,13 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
     n_subset = int(row_subset.numel()) if row_subset is not None else 0
     if row_subset is not None and n_subset == 0 and not (use_plan and graph.plan.n_long):
         return outputs
+    epi = None
+    if epilogue is not None and any(t is not None for t in epilogue):
+        scale, shift, add = epilogue
+        epi = _lib.Epilogue(scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
+                            add.data_ptr() if add is not None else None)
     check(lib.egc_aggregate_fwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin), plan,
-                                ptr(bases), ptr(weightings), ptr(bias), ptr(row_subset) if n_subset else None, n_subset,
+                                ptr(bases), ptr(weightings), ptr(bias), epi, ptr(row_subset) if n_subset else None, n_subset,
                                 ptr(out), ptr(agg), ptr(arg), ptr(saved), ptr(saved_arg), ptr(ws), nbytes, _stream()),
           "egc_aggregate_fwd")
     return outputs
@@ -105,12 +111,13 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
                        saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
                        want_lin_colsum: bool = False, out_bias: Optional[Tensor] = None,
                        out_lin_colsum: Optional[Tensor] = None, col_split: Optional[int] = None, between_phases=None,
-                       out_act: Optional[Tensor] = None):
+                       out_act: Optional[Tensor] = None, epi_scale: Optional[Tensor] = None):
     """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
     with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias).
     `col_split` (row-partitioned callers): run the source columns >= col_split first (EGC_BWD_COLS_HEAD), call
     `between_phases(d_bases)` - typically the NVLink push of those rows on a side stream - then the rest (COLS_TAIL).
-    `out_act`: the forward's output when the layer carries the fused ReLU (desc.relu): grad_out is masked with it."""
+    `out_act`: the forward's post-activation output (before an epilogue `add`) when the layer carries the fused ReLU
+    (desc.relu): grad_out is masked with it; `epi_scale`: the fused affine epilogue's scale (multiplies the gradient)."""
     lib = _lib.load()
     dev = bases.device
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
@@ -136,7 +143,8 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
         check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
                                     ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
                                     graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
-                                    ptr(grad_out), ptr(out_act), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum), flags | phase_flags,
+                                    ptr(grad_out), ptr(out_act), ptr(epi_scale), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum),
+                                    flags | phase_flags,
                                     int(col_split or 0), ptr(ws), nbytes, _stream()),
               "egc_aggregate_bwd")
 
@@ -180,8 +188,14 @@ def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bas
 class _EGConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bases_weight, comb_weight, comb_bias, bias, graph, heads, num_bases, aggrs, sigmoid, algo,
-                bwd_flags, grad_mode=True, relu=False):
+                bwd_flags, grad_mode=True, relu=False, epi_scale=None, epi_shift=None, epi_add=None):
         x = _require_cuda_f32("x", x)
+        epi_scale, epi_shift = _require_cuda_f32("scale", epi_scale), _require_cuda_f32("shift", epi_shift)
+        epi_add = _require_cuda_f32("residual", epi_add)
+        if (epi_scale is None) != (epi_shift is None):
+            raise ValueError("the fused affine epilogue needs both `scale` and `shift`")
+        if (epi_scale is not None and epi_scale.requires_grad) or (epi_shift is not None and epi_shift.requires_grad):
+            raise ValueError("`scale` / `shift` of the fused epilogue are constants (a folded eval-mode BatchNorm): detach them")
         bases_weight = _require_cuda_f32("bases_weight", bases_weight)
         comb_weight = _require_cuda_f32("comb_weight.weight", comb_weight)
         comb_bias = _require_cuda_f32("comb_weight.bias", comb_bias)
@@ -194,40 +208,55 @@ class _EGConvFunction(torch.autograd.Function):
         needs_grad = grad_mode and any(ctx.needs_input_grad[:5])
         with torch.cuda.device(x.device):
             bases, weightings = project(x, bases_weight, comb_weight, comb_bias, sigmoid, algo)
-            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias,
-                                                            want_saved=needs_grad)
-        if needs_grad:
-            # the fused ReLU's backward needs the sign of the output: `out` itself is saved (it is the next layer's
-            # input anyway), nothing extra is written
-            ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, out if relu else None)
+            hd = heads * dim
+            for name, t, shape in (("scale", epi_scale, (hd,)), ("shift", epi_shift, (hd,)), ("residual", epi_add, (graph.n_dst, hd))):
+                if t is not None and tuple(t.shape) != shape:
+                    raise ValueError(f"`{name}` of the fused epilogue must have shape {shape} (got {tuple(t.shape)})")
+            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias, want_saved=needs_grad,
+                                                            epilogue=(epi_scale, epi_shift, epi_add))
+        if needs_grad or (epi_add is not None and ctx.needs_input_grad[16] and grad_mode):
+            # the fused ReLU's backward needs the sign of the post-activation value: `out` itself (the next layer's input
+            # anyway, nothing extra is written) - or out - add when a residual was added after the activation
+            act = None
+            if relu:
+                act = out if epi_add is None else out - epi_add
+            ctx.save_for_backward(x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, act, epi_scale)
         ctx.graph, ctx.desc, ctx.algo, ctx.bwd_flags = graph, desc, algo, bwd_flags
         ctx.has_bias, ctx.has_comb_bias = bias is not None, comb_bias is not None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, out_act = ctx.saved_tensors
+        x, bases_weight, comb_weight, bases, weightings, saved, saved_arg, out_act, epi_scale = ctx.saved_tensors
         grad_out = _require_cuda_f32("grad_out", grad_out)
         need_x, need_wb, need_wc, need_bc, need_b = ctx.needs_input_grad[:5]
+        d_add = grad_out if ctx.needs_input_grad[16] else None      # the residual is added after the activation
+        if saved is None:                                           # only the residual needed a gradient
+            return (None,) * 16 + (d_add,)
         with torch.cuda.device(x.device):
             want_bc = bool(need_bc and ctx.has_comb_bias)
             d_w, d_bases, d_bias, d_bc = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg,
                                                             grad_out, need_b and ctx.has_bias, ctx.bwd_flags,
-                                                            want_lin_colsum=True, out_act=out_act)
+                                                            want_lin_colsum=True, out_act=out_act, epi_scale=epi_scale)
             d_x, d_wb, d_wc, _ = project_backward(x, bases_weight, comb_weight, d_bases, d_w, need_x, need_wb,
                                                   need_wc, False, ctx.algo)
             if not want_bc:
                 d_bc = None
-        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 9
+        return (d_x, d_wb, d_wc, d_bc, d_bias) + (None,) * 11 + (d_add,)
 
 
 def egconv(x: Tensor, graph: GraphStructure, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
            bias: Optional[Tensor], num_heads: int, num_bases: int, aggrs: Sequence[str], sigmoid: bool = False,
-           algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0, relu: bool = False) -> Tensor:
-    """Differentiable EGConv layer body on a prepared graph.  `relu=True` fuses the ReLU that follows the layer in the
-    reference's stacks (mag/models.py:63) into the aggregation epilogue and its mask into the backward's first pass."""
+           algo: int = _lib.GEMM_AUTO, bwd_flags: int = 0, relu: bool = False, scale: Optional[Tensor] = None,
+           shift: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
+    """Differentiable EGConv layer body on a prepared graph.  Fused epilogue of the stack around the layer:
+    `scale` / `shift` [F_out] = an eval-mode BatchNorm folded to an affine map (constants), `relu=True` the ReLU that
+    follows (mag/models.py:63, arxiv/norm_models.py:35-36), `residual` [N, F_out] added after the activation (:38-39):
+    out = relu(layer(x) * scale + shift) + residual, all inside the aggregation kernel's epilogue; the backward masks and
+    scales grad_out while its first pass stages the row."""
     return _EGConvFunction.apply(x, bases_weight, comb_weight, comb_bias, bias, graph, num_heads, num_bases,
-                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags), torch.is_grad_enabled(), bool(relu))
+                                 tuple(aggrs), bool(sigmoid), int(algo), int(bwd_flags), torch.is_grad_enabled(), bool(relu),
+                                 scale, shift, residual)
 
 
 class _ProjectFunction(torch.autograd.Function):
@@ -263,8 +292,9 @@ class _AggregateCombineFunction(torch.autograd.Function):
     is whatever the caller made of the comb-weight projection (column order h * (A * B) + a * B + b)."""
 
     @staticmethod
-    def forward(ctx, bases, weightings, bias, graph, heads, num_bases, aggrs, bwd_flags, grad_mode=True):
+    def forward(ctx, bases, weightings, bias, graph, heads, num_bases, aggrs, bwd_flags, grad_mode=True, add=None):
         bases = _require_cuda_f32("bases", bases)
+        add = _require_cuda_f32("add", add)
         weightings = _require_cuda_f32("weightings", weightings)
         bias = _require_cuda_f32("bias", bias)
         if bases.dim() != 2 or bases.size(0) != graph.n_src:
@@ -279,8 +309,11 @@ class _AggregateCombineFunction(torch.autograd.Function):
             raise ValueError(f"bias must have H * D = {heads * dim} entries (got {bias.numel()})")
         desc = make_desc(graph, heads, num_bases, dim, aggrs, False)
         needs_grad = grad_mode and any(ctx.needs_input_grad[:3])
+        if add is not None and tuple(add.shape) != (graph.n_dst, heads * dim):
+            raise ValueError(f"`add` must be [n_dst, H * D] = [{graph.n_dst}, {heads * dim}] (got {tuple(add.shape)})")
         with torch.cuda.device(bases.device):
-            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias, want_saved=needs_grad)
+            out, _, _, saved, saved_arg = aggregate_combine(desc, graph, bases, weightings, bias, want_saved=needs_grad,
+                                                            epilogue=(None, None, add))
         if needs_grad:
             ctx.save_for_backward(bases, weightings, saved, saved_arg)
         ctx.graph, ctx.desc, ctx.bwd_flags, ctx.has_bias = graph, desc, bwd_flags, bias is not None
@@ -288,12 +321,15 @@ class _AggregateCombineFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        bases, weightings, saved, saved_arg = ctx.saved_tensors
         grad_out = _require_cuda_f32("grad_out", grad_out)
+        d_add = grad_out if ctx.needs_input_grad[9] else None        # out = f(bases, weightings) + add
+        if not ctx.saved_tensors:
+            return (None,) * 9 + (d_add,)
+        bases, weightings, saved, saved_arg = ctx.saved_tensors
         with torch.cuda.device(bases.device):
             d_w, d_bases, d_bias = aggregate_backward(ctx.desc, ctx.graph, bases, weightings, saved, saved_arg, grad_out,
                                                       ctx.needs_input_grad[2] and ctx.has_bias, ctx.bwd_flags)
-        return d_bases, d_w, d_bias, None, None, None, None, None, None
+        return d_bases, d_w, d_bias, None, None, None, None, None, None, d_add
 
 
 def project_autograd(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_bias: Optional[Tensor],
@@ -303,7 +339,9 @@ def project_autograd(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, comb_
 
 
 def aggregate_combine_autograd(bases: Tensor, weightings: Tensor, bias: Optional[Tensor], graph: GraphStructure,
-                               num_heads: int, num_bases: int, aggrs: Sequence[str], bwd_flags: int = 0) -> Tensor:
-    """Differentiable fused aggregation + combination on a prepared graph."""
+                               num_heads: int, num_bases: int, aggrs: Sequence[str], bwd_flags: int = 0,
+                               add: Optional[Tensor] = None) -> Tensor:
+    """Differentiable fused aggregation + combination on a prepared graph; `add` [n_dst, H * D] is added in the kernel's
+    epilogue (accumulate-into-output: REGConv's running sum over relations, ref rmag/models.py:146)."""
     return _AggregateCombineFunction.apply(bases, weightings, bias, graph, num_heads, num_bases, tuple(aggrs),
-                                           int(bwd_flags), torch.is_grad_enabled())
+                                           int(bwd_flags), torch.is_grad_enabled(), add)

@@ -8,7 +8,8 @@ per relation (s,r,t):  out[t] += combine(rel_combs[s_r_t](x[t]), [mean | max ove
 B200 execution: ONE tensor-core projection per node type produces bases[t] together with the combination weights of
 the root term and of EVERY relation that targets t (their Linear layers are concatenated row-wise); the root term is
 the fused aggregate+combine kernel on the identity graph; each relation is one launch of the same kernel on its
-rectangular CSR (n_dst x n_src, aggregators mean + max, no self-loops), with the usual CSC backward.
+rectangular CSR (n_dst x n_src, aggregators mean + max, no self-loops) whose epilogue adds the running sum of the
+previous terms (accumulate-into-output, no separate elementwise add), with the usual CSC backward.
 State-dict keys, parameter shapes and initialisation follow the reference.
 """
 from typing import Dict, Optional, Sequence, Tuple
@@ -112,7 +113,8 @@ class REGConv(torch.nn.Module):
                 if g.n_dst != x.size(0) or g.n_src != bases[k[0]].size(0):
                     raise ValueError(f"adjacency of {k} is {g.n_dst} x {g.n_src}, expected {x.size(0)} x {bases[k[0]].size(0)}")
                 w_rel = weights[t][:, hb + 2 * hb * i: hb + 2 * hb * (i + 1)].contiguous()
-                out[t] = out[t] + aggregate_combine_autograd(bases[k[0]], w_rel, None, g, h, b, ("mean", "max"))
+                # root_combined[t] += ... (ref :146): the running sum is the `add` input of the kernel's epilogue
+                out[t] = aggregate_combine_autograd(bases[k[0]], w_rel, None, g, h, b, ("mean", "max"), add=out[t])
         return out
 
     def __repr__(self):

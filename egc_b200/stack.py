@@ -69,3 +69,44 @@ class EGC(torch.nn.Module):
             x = F.dropout(x, p=self.dropout, training=self.training)
         x = run(self.convs[-1], x, False)[:, :self.out_true]            # ref :68
         return x.log_softmax(dim=-1)                                   # ref :69
+
+
+def fold_batchnorm(bn: torch.nn.BatchNorm1d):
+    """(scale, shift) of an eval-mode BatchNorm1d:  bn(y) = y * scale + shift  with scale = gamma / sqrt(running_var +
+    eps), shift = beta - running_mean * scale (gamma = 1, beta = 0 without affine).  Constants: detached."""
+    if bn.running_mean is None or bn.running_var is None:
+        raise ValueError("fold_batchnorm needs running statistics (track_running_stats=True)")
+    with torch.no_grad():
+        scale = torch.rsqrt(bn.running_var + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight
+        shift = -bn.running_mean * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class EGCBlock(torch.nn.Module):
+    """One block of the reference's normalised stacks (/root/reference/experiments/arxiv/norm_models.py:33-40, the same
+    pattern in zinc/models.py:60-74):  conv -> BatchNorm -> ReLU -> dropout -> (+ identity).
+
+    In eval mode (inference, or fine-tuning with frozen statistics) the whole tail runs inside the layer's aggregation
+    kernel: the BatchNorm folded to an affine map, the ReLU and the residual add are its epilogue - one kernel, no extra
+    [N, F] round trips.  In training mode BatchNorm needs the batch statistics of the layer's complete output first, so the
+    tail stays ordinary torch ops after the layer (the ReLU cannot be fused either: it follows the normalisation)."""
+
+    def __init__(self, conv: EGConv, dropout: float = 0.0, residual: bool = False):
+        super().__init__()
+        if residual and conv.in_channels != conv.out_channels:
+            raise ValueError("a residual block needs in_channels == out_channels")
+        self.conv = conv
+        self.bn = torch.nn.BatchNorm1d(conv.out_channels)
+        self.dropout, self.residual = dropout, residual
+
+    def forward(self, x: Tensor, edge_index) -> Tensor:
+        if self.training:
+            y = F.relu(self.bn(self.conv(x, edge_index)))
+            y = F.dropout(y, p=self.dropout, training=True)
+            return y + x if self.residual else y
+        scale, shift = fold_batchnorm(self.bn)
+        return self.conv(x, edge_index, relu=True, scale=scale, shift=shift, residual=x if self.residual else None)

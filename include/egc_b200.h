@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EGC_ABI_VERSION 4
+#define EGC_ABI_VERSION 5
 #define EGC_MAX_AGGR 8          /* len(aggrs) accepted by one layer */
 #define EGC_CHUNK_EDGES 256     /* rows longer than this are split into chunks of this many nnz */
 
@@ -73,6 +73,17 @@ typedef struct egc_layer_desc {
   int32_t relu;                  /* fused epilogue of the stack around the layer (ref mag/models.py:63): out = max(out, 0);
                                     the backward then masks grad_out with out > 0 (egc_aggregate_bwd `out_act`)   */
 } egc_layer_desc;
+
+/* Optional fused epilogue of egc_aggregate_fwd (the stack around the layer), applied per output
+ * element c of row i in this order:   y = out[i, c] (+ bias)  ->  y = y * scale[c] + shift[c]  (BatchNorm in eval mode,
+ * folded: scale = gamma / sqrt(var + eps), shift = beta - mean * scale; ref arxiv/norm_models.py:35)  ->  y = max(y, 0)
+ * when desc->relu (ref :36, mag/models.py:63)  ->  y += add[i, c]  (the residual of ref :38-39, or the running sum of
+ * REGConv's relation terms, rmag/models.py:146; `add` may alias `out`).  Any pointer may be NULL. */
+typedef struct egc_epilogue {
+  const float* scale;            /* [H*D] or NULL (then shift must be NULL too)                  */
+  const float* shift;            /* [H*D] or NULL                                                */
+  const float* add;              /* [n_dst, H*D] or NULL                                         */
+} egc_epilogue;
 
 /* Row plan: how long rows of a CSR (or columns of its CSC) are split into chunks so that no
  * warp walks more than EGC_CHUNK_EDGES nnz.  Built once per graph by egc_plan_build(). */
@@ -213,7 +224,7 @@ int32_t egc_saved_arg_slots(const egc_layer_desc* desc);
 size_t egc_aggregate_fwd_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* plan);
 int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const int32_t* col,
                       const float* val_sym, const float* val_lin, const egc_row_plan* plan,
-                      const float* bases, const float* weightings, const float* bias,
+                      const float* bases, const float* weightings, const float* bias, const egc_epilogue* epilogue,
                       const int32_t* row_subset, int32_t n_subset,
                       float* out, float* agg_out, int32_t* arg_out, float* saved, int32_t* saved_arg,
                       void* workspace, size_t workspace_bytes, void* stream);
@@ -230,7 +241,10 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
  * writes every row of d_bases.  d_bias (may be NULL) = column sums of grad_out; d_lin_colsum (may be NULL) = column sums of
  * d_weightings = gradient of the comb-weight bias (ref :108, :182), produced here because pass 1 has the rows in
  * registers - egc_project_bwd then takes d_b_comb = NULL.  out_act: the forward's `out` (required iff desc->relu, else
- * NULL): pass 1 uses grad_out[i, c] * (out_act[i, c] > 0).  flags: EGC_BWD_* bits. */
+ * NULL): pass 1 uses grad_out[i, c] * (out_act[i, c] > 0) - with an epilogue `add`, pass the post-activation value
+ * BEFORE the add (out - add).  epi_scale (or NULL): the forward epilogue's scale; pass 1 multiplies the masked gradient
+ * by it (scale / shift themselves are constants: no gradient is produced for them); the gradient w.r.t. `add` is
+ * grad_out itself.  d_bias then is the gradient of the bias INSIDE the epilogue (masked and scaled).  flags: EGC_BWD_*. */
 #define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients with a compare-and-add gather over the CSC instead of fp32
                                    atomics: bit-reproducible from run to run (needs csr2csc; two more gathered rows per
                                    entry and min/max slot) */
@@ -247,7 +261,8 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const int32_t* colptr, const int32_t* rowidx, const int32_t* csr2csc, const float* csc_val_sym,
                       const float* csc_val_lin, const egc_row_plan* csc_plan,
                       const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
-                      const float* grad_out, const float* out_act, float* d_weightings, float* d_bases, float* d_bias,
+                      const float* grad_out, const float* out_act, const float* epi_scale, float* d_weightings,
+                      float* d_bases, float* d_bias,
                       float* d_lin_colsum, int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes,
                       void* stream);
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_build_info():
     lib = egc_b200.load()
-    assert lib.egc_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.egc_abi_version() == _lib.ABI_VERSION == 5
     info = lib.egc_build_info().decode()
     assert "sm_100a" in info and "chunk_edges=256" in info
 
@@ -133,7 +133,7 @@ int main(void) {
   d.aggr[0] = EGC_AGGR_SYMNORM; d.aggr[1] = EGC_AGGR_MAX; d.aggr[2] = EGC_AGGR_STD;
   printf("%d %d %d %s\n", egc_abi_version(), (int)egc_saved_slots(&d), (int)egc_saved_arg_slots(&d), egc_build_info());
   /* a call that must fail cleanly without a device: null descriptor */
-  int rc = egc_aggregate_fwd(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL);
+  int rc = egc_aggregate_fwd(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL);
   printf("%d %s\n", rc, egc_last_error_string());
   return 0;
 }

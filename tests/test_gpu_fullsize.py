@@ -157,3 +157,37 @@ def test_tensor_core_projection_vs_fp64(algo, bar, n, f_in, bd, hab, sigmoid):
     print(f"tensor-core projection n={n} f_in={f_in} bd={bd} hab={hab} sigmoid={sigmoid} bar={bar:g}: {errs}")
     for k, e in errs.items():
         assert e < bar, f"{k}: {e:.3e} >= {bar:g}"
+
+
+@pytest.mark.parametrize("n,f_in,bd,hab", [(2001, 128, 64, 224), (5000, 128, 32, 288), (999, 64, 100, 544)])
+def test_wide_parameter_gradient_runs_on_the_tensor_cores(n, f_in, bd, hab):
+    """More than 256 accumulator columns (REGConv's paper type: root + every relation's combination weights in one
+    projection, rmag/models.py:100-146): `k_wgrad_mn` is launched once per <= 256-column range instead of falling back to
+    the fp32 FFMA kernel; results vs fp64 at the 3xTF32 bar."""
+    lib = egc_b200.load()
+    torch.manual_seed(1)
+    x, d_bases, d_lin = torch.randn(n, f_in), torch.randn(n, bd), torch.randn(n, hab)
+    wb, wc = torch.randn(f_in, bd) * 0.1, torch.randn(hab, f_in) * 0.1
+    outs = [torch.empty(s, device=DEV) for s in ((f_in, bd), (hab, f_in), (hab,))]
+    nbytes = lib.egc_project_bwd_workspace_bytes(n, f_in, bd, hab)
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=DEV)
+    P = _lib.ptr
+    dev_in = [t.to(DEV) for t in (x, wb, wc, d_bases, d_lin)]
+    _lib.profile_enable(True)
+    try:
+        rc = lib.egc_project_bwd(*[P(t) for t in dev_in], n, f_in, bd, hab, None, *[P(t) for t in outs], _lib.GEMM_3XTF32,
+                                 P(ws), nbytes, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        prof = _lib.profile_collect()
+    finally:
+        _lib.profile_enable(False)
+    if rc != 0:
+        assert b"does not support" in lib.egc_last_error_string()
+        pytest.skip("shape outside the tensor-core projection")
+    assert prof.get("k_wgrad_tc", (0, 0))[0] == 1 + -(-(hab - (256 - 32 * -(-bd // 32)) // 32 * 32) // 256), prof
+    xd = x.double()
+    errs = {"d_bases_weight": rel_err(outs[0], xd.t() @ d_bases.double()), "d_comb_weight": rel_err(outs[1], d_lin.double().t() @ xd),
+            "d_comb_bias": rel_err(outs[2], d_lin.double().sum(0))}
+    print(f"wide wgrad n={n} f_in={f_in} bd={bd} hab={hab}: {errs} {prof}")
+    for k, e in errs.items():
+        assert e < TOL_3XTF32, f"{k}: {e:.3e}"
