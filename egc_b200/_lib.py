@@ -19,6 +19,7 @@ LOOPS_NONE, LOOPS_ALL_NODES, LOOPS_UP_TO_MAX_ID = 0, 1, 2
 GEMM_AUTO, GEMM_FP32_SIMT, GEMM_3XTF32, GEMM_TF32 = 0, 1, 2, 3
 BWD_DETERMINISTIC, BWD_SKIP_ROUTING, BWD_NO_HUB_PRIVATISATION = 1, 4, 8
 BWD_COLS_HEAD, BWD_COLS_TAIL = 128, 256
+BWD_PASS1_ONLY, BWD_ACCUMULATE = 512, 1024
 
 POOL_CODES = {"sum": 0, "add": 0, "mean": 1, "max": 2}
 AGGR_CODES = {"sum": 0, "mean": 1, "symnorm": 2, "min": 3, "max": 4, "var": 5, "std": 6}
@@ -72,7 +73,9 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "egc_aggregate_bwd_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan), c_int32]),
     "egc_aggregate_bwd": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P,
-                                    _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P, c_size_t, _P]),
+    "egc_aggregate_bwd_cols_workspace_bytes": (c_size_t, [POINTER(LayerDesc), POINTER(RowPlan)]),
+    "egc_aggregate_bwd_cols": (c_int32, [POINTER(LayerDesc), _P, _P, _P, _P, POINTER(RowPlan), _P, _P, _P, c_int32, _P, c_size_t, _P]),
     "egc_gather_rows": (c_int32, [_P, _P, c_int32, c_int32, _P, _P]),
     "egc_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), _P]),
     "egc_peer_free": (c_int32, [_P]),

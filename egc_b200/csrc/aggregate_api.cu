@@ -119,6 +119,60 @@ static BwdLayout bwd_layout(const egc_layer_desc& d, const egc_row_plan* csc_pla
   return L;
 }
 
+// Pass 2 of the backward: per source column over a CSC view, atomic-free.  d_bases[j] (= | +=) the column's sum of
+// val_sym t_sym[i] + val_lin (t_lin[i] + 2 bases[j] t_sq[i]) over its entries; `csc_part` = chunk partials, the long-column
+// counters and the task counter (BwdLayout::csc_part_bytes).
+static int run_pass2(const egc_layer_desc& desc, const BwdLayout& L, const int32_t* colptr, const int32_t* rowidx,
+                     const float* csc_val_sym, const float* csc_val_lin, const egc_row_plan* csc_plan, const float* tstreams,
+                     const float* bases, float* d_bases, int col_begin, int col_end, bool accumulate, float* csc_part, bool vec4,
+                     cudaStream_t st) {
+  const int bd = desc.bases * desc.dim;
+  AggParams geo{};
+  fill_agg_params(geo, desc, vec4);
+  ScatterParams s{};
+  s.colptr = colptr; s.rowidx = rowidx; s.val_sym = csc_val_sym; s.val_lin = csc_val_lin; s.n_cols = desc.n_src;
+  s.col_begin = col_begin;
+  s.col_end = col_end;
+  s.n_long = csc_plan ? csc_plan->n_long : 0;
+  s.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
+  s.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
+  s.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
+  s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
+  s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
+  s.partials = csc_part;
+  const size_t part_bytes = align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256);
+  const size_t counters_bytes = align_up(static_cast<size_t>(s.n_long) * sizeof(int), 256);
+  int* long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) + part_bytes);
+  int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(long_counter) + counters_bytes);
+  // column-block kernel: 128-bit pieces, unweighted entries, one pass, interleaved streams
+  // (EGC_BWD_WARP_PER_COLUMN=1 keeps the warp-per-column kernel)
+  static const bool legacy_cols = getenv("EGC_BWD_WARP_PER_COLUMN") != nullptr;
+  const bool col_blocks = vec4 && csc_val_lin == nullptr && geo.n_pass == 1 && (geo.G == 32 || geo.G == 16) && !legacy_cols;
+  const bool fuse_merge = geo.n_pass == 1 && s.n_long > 0;     // the last chunk warp of a long column merges its partials
+  s.long_counter = (col_blocks || fuse_merge) ? long_counter : nullptr;
+  s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
+  s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
+  s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
+  s.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;
+  s.off_sym = L.ts_sym < 0 ? 0 : static_cast<int64_t>(L.ts_sym) * bd;
+  s.off_lin = L.ts_lin < 0 ? 0 : static_cast<int64_t>(L.ts_lin) * bd;
+  s.off_sq = L.ts_sq < 0 ? 0 : static_cast<int64_t>(L.ts_sq) * bd;
+  s.routed = accumulate ? 1 : 0;
+  s.mode = 0;
+  if (s.col_end <= s.col_begin) return EGC_OK;
+  if (col_blocks) {
+    EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes + sizeof(int), st));
+    return geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st);
+  }
+  if (fuse_merge) EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes, st));
+  if (int rc = launch_scatter(s, L.tsmask, vec4, csc_val_lin != nullptr, st)) return rc;
+  if (s.n_long > 0 && !fuse_merge) {
+    s.mode = 1;
+    if (int rc = launch_scatter(s, L.tsmask, vec4, csc_val_lin != nullptr, st)) return rc;
+  }
+  return EGC_OK;
+}
+
 }  // namespace egc
 
 using namespace egc;
@@ -224,12 +278,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const float* csc_val_lin, const egc_row_plan* csc_plan, const float* bases,
                       const float* weightings, const float* saved, const int32_t* saved_arg, const float* grad_out,
                       const float* out_act, const float* epi_scale, float* d_weightings, float* d_bases, float* d_bias,
-                      float* d_lin_colsum, int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+                      float* d_lin_colsum, float* tstreams_out, int32_t flags, int32_t col_split, void* workspace,
+                      size_t workspace_bytes, void* stream) {
   if (int rc = validate_desc(desc, "egc_aggregate_bwd")) return rc;
   if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd")) return rc;
-  EGC_REQUIRE(rowptr && col && colptr && rowidx && bases && weightings && saved && grad_out && d_weightings && d_bases && workspace,
-              "egc_aggregate_bwd: null pointer");
+  const bool pass1_only = (flags & EGC_BWD_PASS1_ONLY) != 0;
+  EGC_REQUIRE(rowptr && col && bases && weightings && saved && grad_out && d_weightings && workspace &&
+              (pass1_only || (colptr && rowidx && d_bases)), "egc_aggregate_bwd: null pointer");
   EGC_REQUIRE((desc->relu != 0) == (out_act != nullptr), "egc_aggregate_bwd: out_act must be given exactly when desc->relu is set");
   const BwdLayout L = bwd_layout(*desc, csc_plan);
   const bool det_route = (flags & EGC_BWD_DETERMINISTIC) != 0 && L.has_route;
@@ -237,7 +292,7 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const int mask = prim_mask_of(*desc);
   const int n_arg = n_arg_slots(*desc);
   EGC_REQUIRE(n_arg == 0 || saved_arg != nullptr, "egc_aggregate_bwd: saved_arg required for min/max");
-  EGC_REQUIRE(!(mask & P_SYM) || csc_val_sym, "egc_aggregate_bwd: symnorm requested without csc_val_sym");
+  EGC_REQUIRE(!(mask & P_SYM) || csc_val_sym || pass1_only, "egc_aggregate_bwd: symnorm requested without csc_val_sym");
   EGC_REQUIRE((val_lin == nullptr) == (csc_val_lin == nullptr), "egc_aggregate_bwd: val_lin and csc_val_lin must come together");
   EGC_REQUIRE(!((mask & P_SYM) && val_lin), "egc_aggregate_bwd: val_lin cannot be combined with symnorm");
   EGC_REQUIRE(workspace_bytes >= L.total, "egc_aggregate_bwd: workspace too small (%zu < %zu)", workspace_bytes, L.total);
@@ -247,10 +302,13 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   const bool head = (flags & EGC_BWD_COLS_HEAD) != 0, tail = (flags & EGC_BWD_COLS_TAIL) != 0;
   EGC_REQUIRE(!(head && tail), "egc_aggregate_bwd: EGC_BWD_COLS_HEAD and EGC_BWD_COLS_TAIL are separate calls");
   const bool split = head || tail;
+  EGC_REQUIRE(!pass1_only || (!split && !L.has_route && tstreams_out != nullptr),
+              "egc_aggregate_bwd: EGC_BWD_PASS1_ONLY needs tstreams_out, a layer without min / max and no column phase");
+  EGC_REQUIRE(aligned16(tstreams_out), "egc_aggregate_bwd: tstreams_out must be 16-byte aligned");
   EGC_REQUIRE(!split || (col_split >= 0 && col_split <= desc->n_src), "egc_aggregate_bwd: col_split=%d outside [0, %d]", col_split, desc->n_src);
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
-  float* tstreams = reinterpret_cast<float*>(ws);
+  float* tstreams = tstreams_out != nullptr ? tstreams_out : reinterpret_cast<float*>(ws);
   float* csc_part = reinterpret_cast<float*>(ws + L.ts_bytes);
   void* colsum_ws = ws + L.ts_bytes + L.csc_part_bytes;
   float* t_route = reinterpret_cast<float*>(ws + L.ts_bytes + L.csc_part_bytes + L.colsum_bytes);
@@ -387,52 +445,10 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   }
 
   // ---- pass 2: per source column (CSC), atomic-free
-  if (L.tsmask != 0) {
-    AggParams geo{};
-    fill_agg_params(geo, *desc, vec4);
-    ScatterParams s{};
-    s.colptr = colptr; s.rowidx = rowidx; s.val_sym = csc_val_sym; s.val_lin = csc_val_lin; s.n_cols = desc->n_src;
-    s.col_begin = head ? col_split : 0;
-    s.col_end = tail ? col_split : desc->n_src;
-    s.n_long = csc_plan ? csc_plan->n_long : 0;
-    s.n_chunks = csc_plan ? csc_plan->n_chunks : 0;
-    s.long_rows = csc_plan ? csc_plan->long_rows : nullptr;
-    s.long_chunk_ptr = csc_plan ? csc_plan->long_chunk_ptr : nullptr;
-    s.chunk_row = csc_plan ? csc_plan->chunk_row : nullptr;
-    s.chunk_begin = csc_plan ? csc_plan->chunk_begin : nullptr;
-    s.partials = csc_part;
-    const size_t part_bytes = align_up(static_cast<size_t>(s.n_chunks) * std::max(L.n_ts, 1) * bd * 4, 256);
-    const size_t counters_bytes = align_up(static_cast<size_t>(s.n_long) * sizeof(int), 256);
-    int* long_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(csc_part) + part_bytes);
-    int* task_counter = reinterpret_cast<int*>(reinterpret_cast<char*>(long_counter) + counters_bytes);
-    // column-block kernel: 128-bit pieces, unweighted entries, one pass, interleaved streams
-    // (EGC_BWD_WARP_PER_COLUMN=1 keeps the warp-per-column kernel)
-    static const bool legacy_cols = getenv("EGC_BWD_WARP_PER_COLUMN") != nullptr;
-    const bool col_blocks = vec4 && val_lin == nullptr && geo.n_pass == 1 && (geo.G == 32 || geo.G == 16) && !legacy_cols;
-    const bool fuse_merge = geo.n_pass == 1 && s.n_long > 0;     // the last chunk warp of a long column merges its partials
-    s.long_counter = (col_blocks || fuse_merge) ? long_counter : nullptr;
-    s.tstreams = tstreams; s.bases = bases; s.d_bases = d_bases;
-    s.n_ts = L.n_ts; s.ts_sym = L.ts_sym; s.ts_lin = L.ts_lin; s.ts_sq = L.ts_sq;
-    s.BD = bd; s.nvec = geo.nvec; s.G = geo.G; s.n_pass = geo.n_pass;
-    s.ts_row_stride = static_cast<int64_t>(L.n_ts) * bd;
-    s.off_sym = L.ts_sym < 0 ? 0 : static_cast<int64_t>(L.ts_sym) * bd;
-    s.off_lin = L.ts_lin < 0 ? 0 : static_cast<int64_t>(L.ts_lin) * bd;
-    s.off_sq = L.ts_sq < 0 ? 0 : static_cast<int64_t>(L.ts_sq) * bd;
-    s.routed = pass2_accumulates ? 1 : 0;
-    s.mode = 0;
-    if (s.col_end > s.col_begin) {
-      if (col_blocks) {
-        EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes + sizeof(int), st));
-        if (int rc = geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st)) return rc;
-      } else {
-        if (fuse_merge) EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes, st));
-        if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
-        if (s.n_long > 0 && !fuse_merge) {
-          s.mode = 1;
-          if (int rc = launch_scatter(s, L.tsmask, vec4, val_lin != nullptr, st)) return rc;
-        }
-      }
-    }
+  if (L.tsmask != 0 && !pass1_only) {
+    if (int rc = run_pass2(*desc, L, colptr, rowidx, csc_val_sym, csc_val_lin, csc_plan, tstreams, bases, d_bases,
+                           head ? col_split : 0, tail ? col_split : desc->n_src, pass2_accumulates, csc_part, vec4, st))
+      return rc;
   }
 
   if (!tail && !route_first) {
@@ -450,6 +466,32 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     }
   }
   return EGC_OK;
+}
+
+size_t egc_aggregate_bwd_cols_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan) {
+  if (desc == nullptr || prim_mask_of(*desc) <= 0) return 0;
+  return bwd_layout(*desc, csc_plan).csc_part_bytes + 256;
+}
+
+int egc_aggregate_bwd_cols(const egc_layer_desc* desc, const int32_t* colptr, const int32_t* rowidx, const float* csc_val_sym,
+                           const float* csc_val_lin, const egc_row_plan* csc_plan, const float* tstreams, const float* bases,
+                           float* d_bases, int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate_desc(desc, "egc_aggregate_bwd_cols")) return rc;
+  if (int rc = validate_plan(csc_plan, "egc_aggregate_bwd_cols")) return rc;
+  EGC_REQUIRE(colptr && rowidx && tstreams && d_bases && workspace, "egc_aggregate_bwd_cols: null pointer");
+  const BwdLayout L = bwd_layout(*desc, csc_plan);
+  EGC_REQUIRE(!L.has_route, "egc_aggregate_bwd_cols: min / max gradients are routed by egc_aggregate_bwd, not by the column pass");
+  EGC_REQUIRE(L.tsmask != 0, "egc_aggregate_bwd_cols: the layer has no linear stream");
+  const int mask = prim_mask_of(*desc);
+  EGC_REQUIRE(!(mask & P_SYM) || csc_val_sym, "egc_aggregate_bwd_cols: symnorm requested without csc_val_sym");
+  EGC_REQUIRE(!((mask & P_SYM) && csc_val_lin), "egc_aggregate_bwd_cols: val_lin cannot be combined with symnorm");
+  EGC_REQUIRE(L.ts_sq < 0 || bases != nullptr, "egc_aggregate_bwd_cols: var / std need the basis rows of the columns");
+  EGC_REQUIRE(workspace_bytes >= L.csc_part_bytes, "egc_aggregate_bwd_cols: workspace too small (%zu < %zu)", workspace_bytes, L.csc_part_bytes);
+  EGC_REQUIRE(L.ts_bytes / 4 < (size_t{1} << 32), "egc_aggregate_bwd_cols: target-side streams exceed 2^32 floats");
+  const int bd = desc->bases * desc->dim;
+  const bool vec4 = (bd % 4 == 0) && (bases == nullptr || aligned16(bases)) && aligned16(d_bases) && aligned16(tstreams) && aligned16(workspace);
+  return run_pass2(*desc, L, colptr, rowidx, csc_val_sym, csc_val_lin, csc_plan, tstreams, bases, d_bases, 0, desc->n_src,
+                   (flags & EGC_BWD_ACCUMULATE) != 0, static_cast<float*>(workspace), vec4, as_stream(stream));
 }
 
 }  // extern "C"

@@ -11,6 +11,10 @@ Scheme (one process per GPU, torch.distributed; NCCL over NVLink on the B200 box
   * backward: local passes produce d_bases for own AND halo sources; halo partial sums travel back to
               their owners (reverse exchange) and are added in fixed peer order (deterministic);
               parameter gradients are all-reduced.
+              Layers without min / max and with ONE target-side stream (symnorm-only, sum / mean only: EGC-S) instead
+              exchange that stream ("T exchange"): pass 1 -> the stream rows of my boundary targets go to the ranks
+              whose source columns they touch (a forward-style halo exchange on the TRANSPOSED adjacency) -> pass 2
+              over my OWN columns only, complete and in CSC order: no 1-entry halo columns, no partial-sum reduce.
 `PartitionPlan` and `HaloExchange` are pure index / communication plumbing (any device, any backend);
 `PartitionedGraph` + `partitioned_egconv` bind them to the CUDA kernels.  On the B200 box the data path does not
 go through NCCL: `transport="peer"` moves halo rows, halo gradient partial sums and the replicated parameter
@@ -38,6 +42,18 @@ def balanced_row_bounds(rowptr: Tensor, world_size: int) -> List[int]:
         bounds.append(b)
     bounds.append(n)
     return bounds
+
+
+def transpose_csr(rowptr: Tensor, col: Tensor, *values: Optional[Tensor]):
+    """Host-side transpose of a square CSR: (rowptr_t, col_t, *values_t), entries of a row of the transpose ascending by
+    their original row (stable)."""
+    rowptr, col = rowptr.long().cpu(), col.long().cpu()
+    n = rowptr.numel() - 1
+    row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    order = torch.argsort(col, stable=True)
+    rowptr_t = torch.zeros(n + 1, dtype=torch.long)
+    rowptr_t[1:] = torch.cumsum(torch.bincount(col, minlength=n), 0)
+    return (rowptr_t, row[order]) + tuple(v.cpu()[order] if v is not None else None for v in values)
 
 
 @dataclass
@@ -85,6 +101,14 @@ class PartitionPlan:
 
     def owner_of(self, ids: Tensor) -> Tensor:
         return torch.searchsorted(self._bounds_t, ids, right=True) - 1
+
+    def transposed(self) -> "PartitionPlan":
+        """The same node ranges over the TRANSPOSED adjacency: rank p's rows are its own SOURCE columns, its halo the
+        remote TARGETS that aggregate them - what the backward's T exchange needs (see the module docstring)."""
+        if int(self.col.max()) >= self.n if self.col.numel() else False:
+            raise ValueError("the transposed plan needs a square adjacency")
+        rowptr_t, col_t, sym_t, lin_t = transpose_csr(self.rowptr, self.col, self.val_sym, self.val_lin)
+        return PartitionPlan(rowptr_t, col_t, self.world_size, val_sym=sym_t, val_lin=lin_t, bounds=list(self.bounds))
 
     def _needed_remote(self, rank: int) -> List[Tensor]:
         b, e = self.bounds[rank], self.bounds[rank + 1]
@@ -214,11 +238,15 @@ class PartitionedGraph:
     stores into the consumer's memory ordered by epoch flags, graph-capturable, no NCCL on the data path;
     transport = "nccl": point-to-point `batch_isend_irecv` + all-reduce (kept as the library baseline)."""
 
-    def __init__(self, part: LocalPartition, device, group=None, transport: str = "peer"):
+    def __init__(self, part: LocalPartition, device, group=None, transport: str = "peer",
+                 tpart: Optional[LocalPartition] = None):
         from .graph import GraphStructure
         if transport not in ("peer", "nccl"):
             raise ValueError(f"unknown transport {transport!r}")
         self.part = part
+        self.tpart = tpart                         # local block of the TRANSPOSED adjacency (T exchange), or None
+        self._graph_t = None
+        self.exchange_t = CudaHaloExchange(tpart, torch.device(device), group) if tpart is not None else None
         self.device = torch.device(device)
         self.graph = GraphStructure.from_prepared(part.rowptr, part.col, part.n_local + part.n_halo,
                                                   val_sym=part.val_sym, val_lin=part.val_lin, device=self.device)
@@ -236,24 +264,52 @@ class PartitionedGraph:
         # arxiv-shaped EGC-M step) - so "auto" splits only layers without min / max.  EGC_DIST_SPLIT_BWD=0|1 forces it.
         import os
         self.split_backward = os.environ.get("EGC_DIST_SPLIT_BWD", "auto")
+        # backward by T exchange (module docstring): "auto" = layers without min / max whose backward has ONE target-side
+        # stream - the exchanged rows are then as wide as the partial sums they replace; EGC_DIST_T_EXCHANGE=0|1 forces it
+        # (1: every layer without min / max, whatever its stream count)
+        self.t_exchange = os.environ.get("EGC_DIST_T_EXCHANGE", "auto")
         self.group = group
         self._peer_ctx = {}
 
     @staticmethod
-    def from_global(graph, rank: int, world_size: int, device, group=None, transport: str = "peer") -> "PartitionedGraph":
-        """Partition a prepared single-device `GraphStructure` (every rank builds the same plan)."""
+    def from_global(graph, rank: int, world_size: int, device, group=None, transport: str = "peer",
+                    t_exchange: Optional[bool] = None) -> "PartitionedGraph":
+        """Partition a prepared single-device `GraphStructure` (every rank builds the same plan).  `t_exchange`: also
+        partition the transposed adjacency (needed by the T-exchange backward; default: yes for square graphs on more
+        than one rank unless EGC_DIST_T_EXCHANGE=0)."""
+        import os
         plan = PartitionPlan(graph.rowptr.cpu(), graph.col.cpu(), world_size,
                              val_sym=graph.val_sym.cpu() if graph.val_sym is not None else None,
                              val_lin=graph.val_lin.cpu() if graph.val_lin is not None else None)
-        return PartitionedGraph(plan.local(rank), device, group, transport)
+        if t_exchange is None:
+            t_exchange = world_size > 1 and graph.n_dst == graph.n_src and os.environ.get("EGC_DIST_T_EXCHANGE", "auto") != "0"
+        tpart = plan.transposed().local(rank) if t_exchange else None
+        return PartitionedGraph(plan.local(rank), device, group, transport, tpart)
 
-    def peer_context(self, key, bd: int, n_flat: int):
+    @property
+    def graph_t(self):
+        """Device CSR of this rank's rows of the transposed adjacency: rows = own source columns, column ids = rows of
+        the [own | halo] target-stream table."""
+        if self._graph_t is None:
+            from .graph import GraphStructure
+            t = self.tpart
+            self._graph_t = GraphStructure.from_prepared(t.rowptr, t.col, t.n_local + t.n_halo, val_sym=t.val_sym,
+                                                         val_lin=t.val_lin, device=self.device)
+        return self._graph_t
+
+    def uses_t_exchange(self, aggrs) -> bool:
+        if self.tpart is None or self.t_exchange == "0" or any(a in ("max", "min") for a in aggrs):
+            return False
+        return self.t_exchange == "1" or n_target_streams(aggrs) == 1
+
+    def peer_context(self, key, bd: int, n_flat: int, t_width: int = 0):
         """Exchange state of one layer (collective on first use: every rank must reach it in the same order)."""
-        k = (key, int(bd), int(n_flat))
+        k = (key, int(bd), int(n_flat), int(t_width))
         ctx = self._peer_ctx.get(k)
         if ctx is None:
             from .peer import PeerLayerContext
-            ctx = PeerLayerContext(self.part, bd, n_flat, self.device, self.group)
+            ctx = PeerLayerContext(self.part, bd, n_flat, self.device, self.group,
+                                   tpart=self.tpart if t_width else None, t_width=t_width)
             self._peer_ctx[k] = ctx
         return ctx
 
@@ -266,6 +322,12 @@ class PartitionedGraph:
         for ctx in self._peer_ctx.values():
             ctx.close()
         self._peer_ctx = {}
+
+
+def n_target_streams(aggrs) -> int:
+    """Linear target-side streams of the backward: [symnorm] + [sum / mean / var / std] + [var / std]."""
+    return (int("symnorm" in aggrs) + int(any(a in ("sum", "mean", "var", "std") for a in aggrs)) +
+            int(any(a in ("var", "std") for a in aggrs)))
 
 
 class _PartitionedEGConvFunction(torch.autograd.Function):
@@ -283,7 +345,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             if pg.transport == "peer":
                 n_flat = bases_weight.numel() + comb_weight.numel() + comb_weight.size(0) + heads * (bd // num_bases)
-                peer = pg.peer_context(key, bd, n_flat)
+                peer = pg.peer_context(key, bd, n_flat, n_target_streams(aggrs) * bd if pg.uses_t_exchange(aggrs) else 0)
                 # new epoch; every peer is done with the halo rows of my previous step
                 ctx.step_id = peer.begin_step(needs_grad)
                 bases_ext = peer.bases_ext
@@ -332,12 +394,26 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         want_b = bool(need_b and ctx.has_bias)
         want_bc = bool(need_bc and ctx.has_comb_bias)
         with torch.cuda.device(x.device):
-            if peer is None:
+            use_t = pg.uses_t_exchange(ctx.aggrs)
+            if use_t:                                      # descriptor of the column pass over the transposed local block
+                gt = pg.graph_t
+                desc_t = F.make_desc(gt, ctx.desc.heads, ctx.desc.bases, ctx.desc.dim, ctx.aggrs, False)
+                desc_t.n_dst, desc_t.n_src = gt.n_src, gt.n_dst
+                t_width = n_target_streams(ctx.aggrs) * ctx.desc.bases * ctx.desc.dim
+            if peer is None and use_t:
+                t_own = torch.empty((part.n_local, t_width), dtype=torch.float32, device=x.device)
+                d_w, _, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
+                                                            grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
+                                                            out_act=out_act, tstreams_out=t_own)
+                t_ext = torch.cat([t_own, pg.exchange_t.forward(t_own)])      # stream rows of the remote targets
+                d_bases = F.aggregate_backward_cols(desc_t, gt, t_ext, bases_ext[:part.n_local])
+            elif peer is None:
                 d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
                                                                       saved_arg, grad_out, want_b, ctx.bwd_flags,
                                                                       want_lin_colsum=True, out_act=out_act)
                 d_bases = d_bases_ext[:part.n_local]
                 pg.exchange.reverse(d_bases_ext[part.n_local:], d_bases)     # halo partial sums go home
+            if peer is None:
                 d_x, d_wb, d_wc, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases,
                                                         d_w, need_x, need_wb, need_wc, False, ctx.algo)
                 if not want_bc:
@@ -365,7 +441,16 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                     peer.push_backward(d_ext)
 
             routed = any(a in ("max", "min") for a in ctx.aggrs)
-            if pg.split_backward == "1" or (pg.split_backward == "auto" and not routed):
+            if use_t:
+                # pass 1 writes the streams of my targets into the exchange table; the rows my peers' columns touch go
+                # to them (BWD + CONS flags); once theirs are here the column pass over my own columns is complete
+                d_w, _, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg, grad_out,
+                                                    want_b, ctx.bwd_flags, want_lin_colsum=True, out_bias=v_b,
+                                                    out_lin_colsum=v_bc, out_act=out_act, tstreams_out=peer.t_ext)
+                peer.push_t()
+                peer.wait(P.SLOT_BWD)
+                d_bases = F.aggregate_backward_cols(desc_t, gt, peer.t_ext, bases_ext[:part.n_local])
+            elif pg.split_backward == "1" or (pg.split_backward == "auto" and not routed):
                 d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
                                                               out_bias=v_b, out_lin_colsum=v_bc, col_split=part.n_local,
@@ -376,9 +461,10 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
                                                               out_bias=v_b, out_lin_colsum=v_bc, out_act=out_act)
                 peer.push_backward(d_bases_ext)
-            peer.wait(P.SLOT_BWD)
-            d_bases = d_bases_ext[:part.n_local]
-            peer.reduce_into(d_bases)                      # fixed peer order: deterministic
+            if not use_t:
+                peer.wait(P.SLOT_BWD)
+                d_bases = d_bases_ext[:part.n_local]
+                peer.reduce_into(d_bases)                  # fixed peer order: deterministic
             d_x, _, _, _ = F.project_backward(x, bases_weight.contiguous(), comb_weight.contiguous(), d_bases, d_w,
                                               need_x, need_wb, need_wc, False, ctx.algo, out_wb=v_wb, out_wc=v_wc)
             total = peer.allreduce_flat()

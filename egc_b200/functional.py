@@ -111,16 +111,23 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
                        saved_arg: Optional[Tensor], grad_out: Tensor, want_bias: bool, flags: int = 0,
                        want_lin_colsum: bool = False, out_bias: Optional[Tensor] = None,
                        out_lin_colsum: Optional[Tensor] = None, col_split: Optional[int] = None, between_phases=None,
-                       out_act: Optional[Tensor] = None, epi_scale: Optional[Tensor] = None):
+                       out_act: Optional[Tensor] = None, epi_scale: Optional[Tensor] = None,
+                       tstreams_out: Optional[Tensor] = None):
     """Backward of `aggregate_combine`: returns (d_weightings [n_dst, HAB], d_bases [n_src, BD], d_bias|None) and,
     with `want_lin_colsum`, a 4th item: the column sums of d_weightings (= gradient of the comb-weight bias).
     `col_split` (row-partitioned callers): run the source columns >= col_split first (EGC_BWD_COLS_HEAD), call
     `between_phases(d_bases)` - typically the NVLink push of those rows on a side stream - then the rest (COLS_TAIL).
     `out_act`: the forward's post-activation output (before an epilogue `add`) when the layer carries the fused ReLU
-    (desc.relu): grad_out is masked with it; `epi_scale`: the fused affine epilogue's scale (multiplies the gradient)."""
+    (desc.relu): grad_out is masked with it; `epi_scale`: the fused affine epilogue's scale (multiplies the gradient).
+    `tstreams_out` [>= n_dst rows, L * B * D] (row-partitioned callers that exchange the target-side streams): pass 1 only
+    (EGC_BWD_PASS1_ONLY) - the streams of the n_dst targets are written to its first rows, d_bases is returned as None
+    and comes from `aggregate_backward_cols` once the peers' rows have arrived."""
     lib = _lib.load()
     dev = bases.device
     bd, hab = desc.bases * desc.dim, desc.heads * desc.n_aggr * desc.bases
+    pass1_only = tstreams_out is not None
+    if pass1_only:
+        flags |= _lib.BWD_PASS1_ONLY
     if desc.n_dst == 0:                                   # no target rows: every gradient is zero
         d_w = torch.zeros((0, hab), dtype=torch.float32, device=dev)
         d_bases = torch.zeros((desc.n_src, bd), dtype=torch.float32, device=dev)
@@ -130,21 +137,24 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
             return d_w, d_bases, d_bias, (out_lin_colsum.zero_() if out_lin_colsum is not None else
                                           torch.zeros(hab, dtype=torch.float32, device=dev))
         return d_w, d_bases, d_bias
-    graph.ensure_csc()
+    if not pass1_only:
+        graph.ensure_csc()
     d_w = torch.empty((desc.n_dst, hab), dtype=torch.float32, device=dev)
-    d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev)
+    d_bases = torch.empty((desc.n_src, bd), dtype=torch.float32, device=dev) if not pass1_only else None
     d_bias = (out_bias if out_bias is not None else
               torch.empty(desc.heads * desc.dim, dtype=torch.float32, device=dev)) if want_bias else None
     d_lin_sum = (out_lin_colsum if out_lin_colsum is not None else
                  torch.empty(hab, dtype=torch.float32, device=dev)) if want_lin_colsum else None
-    nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, graph.csc_plan.struct, flags)
+    csc_plan = graph.csc_plan.struct if not pass1_only else None
+    nbytes = lib.egc_aggregate_bwd_workspace_bytes(desc, csc_plan, flags)
     ws = _ws(nbytes, dev)
     def call(phase_flags):
-        check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin), ptr(graph.colptr),
-                                    ptr(graph.rowidx), ptr(graph.csr2csc), ptr(graph.csc_val_sym), ptr(graph.csc_val_lin),
-                                    graph.csc_plan.struct, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
+        check(lib.egc_aggregate_bwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_lin),
+                                    *((None,) * 5 if pass1_only else (ptr(graph.colptr), ptr(graph.rowidx), ptr(graph.csr2csc),
+                                                                      ptr(graph.csc_val_sym), ptr(graph.csc_val_lin))),
+                                    csc_plan, ptr(bases), ptr(weightings), ptr(saved), ptr(saved_arg),
                                     ptr(grad_out), ptr(out_act), ptr(epi_scale), ptr(d_w), ptr(d_bases), ptr(d_bias), ptr(d_lin_sum),
-                                    flags | phase_flags,
+                                    ptr(tstreams_out), flags | phase_flags,
                                     int(col_split or 0), ptr(ws), nbytes, _stream()),
               "egc_aggregate_bwd")
 
@@ -159,6 +169,27 @@ def aggregate_backward(desc: LayerDesc, graph: GraphStructure, bases: Tensor, we
         return d_w, d_bases, d_bias, d_lin_sum
     return d_w, d_bases, d_bias
 
+
+
+def aggregate_backward_cols(desc_t: LayerDesc, graph_t: GraphStructure, tstreams: Tensor, bases: Optional[Tensor],
+                            d_bases: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """Pass 2 of the backward alone (`egc_aggregate_bwd_cols`): `graph_t` is the TRANSPOSED local adjacency in CSR form
+    (rows = own source columns, column ids = rows of `tstreams`, values = the entries' weights), `desc_t` its descriptor
+    (n_dst of the descriptor = rows of `tstreams`, n_src = rows of `graph_t`).  Returns d_bases [n_src, B * D]."""
+    lib = _lib.load()
+    dev = tstreams.device
+    bd = desc_t.bases * desc_t.dim
+    if d_bases is None:
+        d_bases = torch.empty((desc_t.n_src, bd), dtype=torch.float32, device=dev)
+    if desc_t.n_src == 0:
+        return d_bases
+    plan = graph_t.plan.struct
+    nbytes = lib.egc_aggregate_bwd_cols_workspace_bytes(desc_t, plan)
+    ws = _ws(nbytes, dev)
+    check(lib.egc_aggregate_bwd_cols(desc_t, ptr(graph_t.rowptr), ptr(graph_t.col), ptr(graph_t.val_sym), ptr(graph_t.val_lin),
+                                     plan, ptr(tstreams), ptr(bases), ptr(d_bases), _lib.BWD_ACCUMULATE if accumulate else 0,
+                                     ptr(ws), nbytes, _stream()), "egc_aggregate_bwd_cols")
+    return d_bases
 
 def project_backward(x: Tensor, bases_weight: Tensor, comb_weight: Tensor, d_bases: Tensor, d_lin: Tensor,
                      need_x: bool, need_wb: bool, need_wc: bool, need_bc: bool, algo: int = _lib.GEMM_AUTO,

@@ -12,6 +12,10 @@ own regions.  `PeerLayerContext` binds a `LocalPartition` to the exchange kernel
             reduce into own rows -> [projection
             gradients] -> push flat parameter gradients into every rank's slot (raises GRAD) -> wait GRAD
             -> sum the slots in rank order (bit-identical on every rank)
+  backward, T exchange (layers without min / max and one target-side stream, `egc_b200.dist`): [pass 1 writes the stream
+            rows of my targets into my `t_ext` table] -> push the rows my peers' source columns touch into THEIR tables
+            (raises BWD + CONS) -> wait BWD -> [pass 2 over my own columns of the transposed local block: complete sums,
+            no staging, no reduce] -> [projection gradients] -> as above
 
 No NCCL call, no host synchronisation and no allocation is on that path, so a whole step can be captured
 in a CUDA graph (`egc_b200.dist.GraphedStep`).  The reference has no multi-GPU counterpart.
@@ -118,17 +122,21 @@ def _ptr_array(values: List[int]):
 class PeerLayerContext:
     """Exchange state of one layer (basis width `bd`, `n_flat` replicated parameter-gradient floats) on one rank."""
 
-    def __init__(self, part, bd: int, n_flat: int, device, group=None, timeout_ns: int = DEFAULT_TIMEOUT_NS):
+    def __init__(self, part, bd: int, n_flat: int, device, group=None, timeout_ns: int = DEFAULT_TIMEOUT_NS,
+                 tpart=None, t_width: int = 0):
         self.part, self.bd, self.device, self.group = part, int(bd), torch.device(device), group
+        self.tpart, self.t_width = (tpart, int(t_width)) if tpart is not None and t_width else (None, 0)
         self.rank, self.world = part.rank, part.world_size
         self.timeout_ns = int(timeout_ns)
         self.n_flat = _align(int(n_flat), 128)                     # rows of 128 floats for the slot pushes
         n_ext = part.n_local + part.n_halo
         send_counts = [int(t.numel()) for t in part.send_rows]
-        n_send = sum(send_counts)
+        n_send = sum(send_counts) if self.tpart is None else 0     # T exchange: no partial sums, no staging
+        n_ext_t = (self.tpart.n_local + self.tpart.n_halo) if self.tpart is not None else 0
         self.seg = PeerSegment([("flags", 4 * N_SLOTS * self.world), ("bases_ext", 4 * n_ext * bd),
-                                ("staging", 4 * max(n_send, 1) * bd), ("slots", 4 * self.world * self.n_flat)],
-                               device, group)
+                                ("staging", 4 * max(n_send, 1) * bd), ("slots", 4 * self.world * self.n_flat),
+                                ("t_ext", 4 * n_ext_t * self.t_width)], device, group)
+        self.t_ext = self.seg.view("t_ext", (n_ext_t, self.t_width)) if self.tpart is not None else None
         self.flags = self.seg.view("flags", (N_SLOTS * self.world,), torch.int32)
         self.bases_ext = self.seg.view("bases_ext", (n_ext, bd))
         self.staging = self.seg.view("staging", (max(n_send, 1), bd))
@@ -153,7 +161,11 @@ class PeerLayerContext:
             send_off.append(send_off[-1] + c)
         self.recv_off, self.send_off = recv_off, send_off
         infos = [None] * self.world
-        dist.all_gather_object(infos, {"n_local": part.n_local, "recv_off": recv_off, "send_off": send_off}, group=group)
+        t_recv_off = [0]
+        for c in (self.tpart.recv_counts if self.tpart is not None else []):
+            t_recv_off.append(t_recv_off[-1] + c)
+        dist.all_gather_object(infos, {"n_local": part.n_local, "recv_off": recv_off, "send_off": send_off,
+                                       "t_recv_off": t_recv_off}, group=group)
         self.peers = [q for q in range(self.world) if q != self.rank]
         row_bytes = 4 * bd
 
@@ -175,6 +187,19 @@ class PeerLayerContext:
             self.bwd_seg_ptr[s + 1] = self.bwd_seg_ptr[s] + part.recv_counts[q]
             bwd_dst.append(self.seg.peer_ptr(q, "staging", infos[q]["send_off"][self.rank] * row_bytes))
         self.bwd_dst = _ptr_array(bwd_dst)
+
+        # T exchange: rows tpart.send_rows[q] of my stream table -> q's table, at q's offset for owner = me
+        if self.tpart is not None:
+            t_counts = [int(t.numel()) for t in self.tpart.send_rows]
+            self.t_index = (torch.cat([self.tpart.send_rows[q] for q in self.peers]) if self.peers else
+                            torch.zeros(0, dtype=torch.long)).to(self.device, torch.int32)
+            self.t_seg_ptr = (ctypes.c_int32 * (len(self.peers) + 1))()
+            t_dst = []
+            for s, q in enumerate(self.peers):
+                self.t_seg_ptr[s + 1] = self.t_seg_ptr[s] + t_counts[q]
+                t_dst.append(self.seg.peer_ptr(q, "t_ext", (infos[q]["n_local"] + infos[q]["t_recv_off"][self.rank]) * 4 * self.t_width))
+            self.t_dst = _ptr_array(t_dst)
+            self.t_src = _ptr_array([self.t_ext.data_ptr()] * len(self.peers))
 
         # deterministic reduce plan: local row -> its staging entries in ascending peer order
         if n_send:
@@ -261,6 +286,12 @@ class PeerLayerContext:
         base = d_bases_ext.data_ptr() + self.part.n_local * self.bd * 4
         src = _ptr_array([base + self.recv_off[q] * self.bd * 4 for q in self.peers])
         self._push(len(self.peers), src, self.bwd_dst, self.bwd_seg_ptr, None, self.bd, (SLOT_BWD, SLOT_CONS))
+
+    def push_t(self):
+        """T exchange: the target-side stream rows my peers' source columns touch -> their stream tables; raises BWD and
+        CONS (pass 1 is done: neither it nor the column pass reads my halo copy of the peers' basis rows)."""
+        self._push(len(self.peers), self.t_src, self.t_dst, self.t_seg_ptr, self.t_index.data_ptr(), self.t_width,
+                   (SLOT_BWD, SLOT_CONS))
 
     def reduce_into(self, d_bases_local: torch.Tensor):
         if self.red_rows is None:

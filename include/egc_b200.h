@@ -244,7 +244,9 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
  * NULL): pass 1 uses grad_out[i, c] * (out_act[i, c] > 0) - with an epilogue `add`, pass the post-activation value
  * BEFORE the add (out - add).  epi_scale (or NULL): the forward epilogue's scale; pass 1 multiplies the masked gradient
  * by it (scale / shift themselves are constants: no gradient is produced for them); the gradient w.r.t. `add` is
- * grad_out itself.  d_bias then is the gradient of the bias INSIDE the epilogue (masked and scaled).  flags: EGC_BWD_*. */
+ * grad_out itself.  d_bias then is the gradient of the bias INSIDE the epilogue (masked and scaled).  tstreams_out (or NULL):
+ * where pass 1 writes the target-side streams [n_dst, L, B*D] instead of the workspace (see egc_aggregate_bwd_cols).
+ * flags: EGC_BWD_*. */
 #define EGC_BWD_DETERMINISTIC 1 /* route min/max gradients with a compare-and-add gather over the CSC instead of fp32
                                    atomics: bit-reproducible from run to run (needs csr2csc; two more gathered rows per
                                    entry and min/max slot) */
@@ -262,9 +264,25 @@ int egc_aggregate_bwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
                       const float* csc_val_lin, const egc_row_plan* csc_plan,
                       const float* bases, const float* weightings, const float* saved, const int32_t* saved_arg,
                       const float* grad_out, const float* out_act, const float* epi_scale, float* d_weightings,
-                      float* d_bases, float* d_bias,
-                      float* d_lin_colsum, int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      float* d_bases, float* d_bias, float* d_lin_colsum, float* tstreams_out,
+                      int32_t flags, int32_t col_split, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pass 2 alone, for row-partitioned callers that exchange the TARGET-SIDE STREAMS instead of partial sums (layers without
+ * min / max; no reference counterpart, DESIGN.md "multi-GPU"): pass 1 runs through egc_aggregate_bwd with
+ * EGC_BWD_PASS1_ONLY and tstreams_out = the first n_dst rows of a table [n_rows_ext, L, B*D] (L = number of linear streams:
+ * [symnorm] + [sum / mean / var / std] + [var / std], interleaved per row) whose remaining rows the peers fill with the
+ * streams of their targets; this call then sums, for every OWN source column j of the TRANSPOSED local adjacency
+ * (colptr / rowidx / csc_val_* = that adjacency, rowidx indexing the rows of `tstreams`; desc->n_src = number of columns,
+ * desc->n_dst = rows of `tstreams`), d_bases[j] = sum_e val_sym[e] t_sym[i_e] + val_lin[e] (t_lin[i_e] + 2 bases[j] t_sq[i_e])
+ * - complete, atomic-free, and over full-degree columns only.  EGC_BWD_ACCUMULATE: d_bases[j] += instead of = (a second
+ * launch over another entry subset, e.g. the halo targets after the local ones).  bases may be NULL without var / std. */
+#define EGC_BWD_PASS1_ONLY 512  /* egc_aggregate_bwd: stop after pass 1 (needs tstreams_out, no min / max aggregator)          */
+#define EGC_BWD_ACCUMULATE 1024 /* egc_aggregate_bwd_cols: add to d_bases instead of overwriting it                            */
+size_t egc_aggregate_bwd_cols_workspace_bytes(const egc_layer_desc* desc, const egc_row_plan* csc_plan);
+int egc_aggregate_bwd_cols(const egc_layer_desc* desc, const int32_t* colptr, const int32_t* rowidx,
+                           const float* csc_val_sym, const float* csc_val_lin, const egc_row_plan* csc_plan,
+                           const float* tstreams, const float* bases, float* d_bases, int32_t flags,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row exchange for row-partitioned graphs (no reference counterpart; see DESIGN.md "multi-GPU")

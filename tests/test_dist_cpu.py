@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from egc_b200.dist import HaloExchange, PartitionPlan, balanced_row_bounds
+from egc_b200.dist import HaloExchange, PartitionPlan, balanced_row_bounds, n_target_streams, transpose_csr
 from oracle import restatement as R
 from tests.util import random_graph, rel_err
 
@@ -115,6 +115,93 @@ def test_partition_plan_invariants(world):
             assert torch.equal(plan.local(q).send_rows[r] + plan.bounds[q], plan._needs[r][q])
     assert total_rows == n
     assert balanced_row_bounds(g.rowptr, 1) == [0, n]
+
+
+# ------------------------------------------------------------------------------------------------
+# T exchange: the backward of layers without min / max exchanges the target-side stream rows over the TRANSPOSED plan
+# ------------------------------------------------------------------------------------------------
+def _directed_graph(n, seed):
+    """NOT symmetric: the transposed plan's halo differs from the forward one."""
+    ei = random_graph(n, 1400, seed=seed, hub=80)
+    gen = torch.Generator().manual_seed(seed + 1)
+    extra = torch.stack([torch.randint(0, n // 3, (500,), generator=gen), torch.randint(n // 2, n, (500,), generator=gen)])
+    return torch.cat([ei, extra], 1)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_transposed_plan_invariants(world):
+    n = 400
+    g = R.graph_from_edge_index(_directed_graph(n, 21), n, True, True)
+    plan = PartitionPlan(g.rowptr, g.col, world, val_sym=g.val_sym)
+    plan_t = plan.transposed()
+    assert plan_t.bounds == plan.bounds
+    rowptr_t, col_t, val_t = transpose_csr(g.rowptr, g.col, g.val_sym)
+    dense = torch.zeros(n, n, dtype=torch.float64)
+    rows = torch.repeat_interleave(torch.arange(n), g.rowptr[1:] - g.rowptr[:-1])
+    dense.index_put_((rows, g.col), g.val_sym.double(), accumulate=True)
+    rows_t = torch.repeat_interleave(torch.arange(n), rowptr_t[1:] - rowptr_t[:-1])
+    dense_t = torch.zeros(n, n, dtype=torch.float64)
+    dense_t.index_put_((rows_t, col_t), val_t.double(), accumulate=True)
+    assert torch.equal(dense_t, dense.t())
+    for r in range(world):
+        tp, p = plan_t.local(r), plan.local(r)
+        assert (tp.row_begin, tp.row_end) == (p.row_begin, p.row_end)
+        ext = torch.cat([torch.arange(tp.row_begin, tp.row_end), tp.halo_ids])
+        lo, hi = int(rowptr_t[tp.row_begin]), int(rowptr_t[tp.row_end])
+        assert torch.equal(ext[tp.col], col_t[lo:hi]) and torch.equal(tp.val_sym, val_t[lo:hi])
+        # my transposed halo = the remote TARGETS of my source columns = the ranks whose forward halo contains my rows
+        for q in range(world):
+            assert torch.equal(plan_t.local(q).send_rows[r] + plan.bounds[q], plan_t._needs[r][q])
+    assert n_target_streams(["symnorm"]) == 1 and n_target_streams(["sum", "mean"]) == 1
+    assert n_target_streams(["symnorm", "mean"]) == 2 and n_target_streams(["symnorm", "max", "std"]) == 3
+
+
+def _t_worker(rank, world, port, n, ei, x, go, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        aggrs = ["symnorm"]
+        torch.manual_seed(7)
+        layer = R.EGConvOracle(12, 32, aggrs=aggrs, num_heads=4, num_bases=4).double()
+        g = layer.prepare(x, ei)
+        # single-process truth: gradient of the loss with respect to the projected bases
+        bases_full, w_full = R.project(x, layer.bases_weight, layer.comb_weight.weight, layer.comb_weight.bias)
+        bases_full = bases_full.detach().requires_grad_(True)
+        agg_full, _ = R.aggregate(g, bases_full, aggrs)
+        out_full = R.combine(w_full, agg_full, layer.bias, 4)
+        (d_bases_ref,) = torch.autograd.grad(out_full, [bases_full], go)
+        plan = PartitionPlan(g.rowptr, g.col, world, val_sym=g.val_sym)
+        part, tpart = plan.local(rank), plan.transposed().local(rank)
+        b, e = part.row_begin, part.row_end
+        # pass 1 on this rank: the target-side stream of my rows (symnorm: t_sym = d(loss) / d(agg), [n_local, B*D])
+        halo = HaloExchange(part, "cpu").forward(bases_full.detach()[b:e])
+        local_graph = R.OracleGraph(part.rowptr, part.col, part.n_local, part.n_local + part.n_halo, val_sym=part.val_sym)
+        bases_ext = torch.cat([bases_full.detach()[b:e], halo])
+        agg = R.aggregate(local_graph, bases_ext, aggrs)[0].detach().requires_grad_(True)
+        out_loc = R.combine(w_full[b:e], agg, layer.bias, 4)
+        (t_own,) = torch.autograd.grad(out_loc, [agg], go[b:e])
+        t_own = t_own.reshape(part.n_local, -1)
+        # T exchange over the transposed plan, then the column pass over my own columns
+        t_ext = torch.cat([t_own, HaloExchange(tpart, "cpu").forward(t_own)])
+        rows = torch.repeat_interleave(torch.arange(tpart.n_local), tpart.rowptr[1:] - tpart.rowptr[:-1])
+        d_bases = torch.zeros(tpart.n_local, t_own.size(1), dtype=torch.float64)
+        d_bases.index_add_(0, rows, tpart.val_sym.double().unsqueeze(1) * t_ext[tpart.col])
+        assert rel_err(d_bases, d_bases_ref[b:e]) < 1e-12
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_t_exchange_backward_matches_single_process_gloo_world2():
+    n = 300
+    ei = _directed_graph(n, 31)
+    torch.manual_seed(1)
+    x = torch.randn(n, 12, dtype=torch.float64)
+    go = torch.randn(n, 32, dtype=torch.float64)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_t_worker, args=(2, _free_port(), n, ei, x, go, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
 
 
 # ------------------------------------------------------------------------------------------------

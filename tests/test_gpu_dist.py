@@ -36,7 +36,8 @@ def check_two_layers(conv, conv2, params2, pg, x, go, eid, b, e, dev):
         assert rel_err(a, r) < 2e-5
 
 
-def _worker(rank, world, port, n, ei, x, go, transport, ret):
+def _worker(rank, world, port, n, ei, x, go, transport, ret, aggrs=None, expect_t=False):
+    AGGRS = aggrs or globals()["AGGRS"]
     import egc_b200
     from egc_b200.dist import GraphedStep, PartitionedGraph, partitioned_egconv
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -54,6 +55,7 @@ def _worker(rank, world, port, n, ei, x, go, transport, ret):
         g = egc_b200.GraphStructure.from_edge_index(eid, n, True, True)
         pg = PartitionedGraph.from_global(g, rank, world, dev, transport=transport)
         assert pg.transport == transport
+        assert pg.uses_t_exchange(AGGRS) == expect_t
         b, e = pg.part.row_begin, pg.part.row_end
         assert pg.part.interior_rows.numel() > 0 and pg.part.n_halo > 0
 
@@ -141,6 +143,26 @@ def test_partitioned_layer_matches_single_gpu_world2(transport):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("aggrs", [["symnorm"], ["sum"], ["mean"]], ids=lambda a: "+".join(a))
+def test_partitioned_layer_with_t_exchange_matches_single_gpu_world2(transport, aggrs):
+    """Layers without min / max and one target-side stream (EGC-S) exchange the stream rows over the TRANSPOSED plan and
+    run the column pass over their own columns only.  The graph is NOT symmetric (extra one-way edges from the low to the
+    high node range), so the transposed halo differs from the forward one."""
+    n = 4000
+    ei = random_graph(n, 30000, seed=6, hub=900)
+    blk = torch.randint(0, n // 2, (2, 15000))
+    one_way = torch.stack([torch.randint(0, n // 3, (4000,)), torch.randint(n // 2, n, (4000,))])
+    ei = torch.cat([ei, blk, blk + n // 2, one_way], 1)
+    torch.manual_seed(2)
+    x, go = torch.randn(n, 64), torch.randn(n, 128)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret, aggrs, True), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
 
 

@@ -237,3 +237,50 @@ def test_fused_relu_equals_relu_after_the_layer(cfg):
         assert torch.equal(u, v)
     with torch.no_grad():
         assert torch.equal(c(x, ei, relu=True), torch.relu(c(x, ei)))
+
+
+# ------------------------------------------------------------------------------------------------
+# pass 1 / column pass as separate entry points (the T-exchange backward of row-partitioned layers)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(["symnorm"], 8, 4, 16), (["sum", "mean"], 4, 4, 32), (["symnorm", "std"], 4, 4, 32),
+                                 (["mean", "var"], 4, 3, 10)], ids=lambda c: "+".join(c[0]) + f"-h{c[1]}b{c[2]}d{c[3]}")
+def test_pass1_only_plus_column_pass_equals_the_one_call_backward(cfg):
+    """egc_aggregate_bwd(EGC_BWD_PASS1_ONLY, tstreams_out) followed by egc_aggregate_bwd_cols over the TRANSPOSED adjacency
+    (a CSR whose rows are the source columns) gives the d_bases of the single call (same entries per column; agreement to
+    fp32 rounding is what is asserted); so does a split into two entry subsets with EGC_BWD_ACCUMULATE."""
+    from egc_b200.dist import n_target_streams, transpose_csr
+    from egc_b200.functional import aggregate_backward, aggregate_backward_cols, aggregate_combine
+    aggrs, h, b, d = cfg
+    n = 3000
+    ei = random_graph(n, 30000, seed=95, hub=700).to(DEV)
+    g = egc_b200.GraphStructure.from_edge_index(ei, n, True, True)
+    desc = egc_b200.make_desc(g, h, b, d, aggrs, False)
+    torch.manual_seed(16)
+    bases, w = torch.randn(n, b * d, device=DEV), torch.randn(n, h * len(aggrs) * b, device=DEV)
+    go = torch.randn(n, h * d, device=DEV)
+    _, _, _, saved, saved_arg = aggregate_combine(desc, g, bases, w, None, want_saved=True)
+    ref = aggregate_backward(desc, g, bases, w, saved, saved_arg, go, True, want_lin_colsum=True)
+    L = n_target_streams(aggrs)
+    pad = 5                                                     # extra table rows (a partitioned caller's halo rows)
+    t_ext = torch.full((n + pad, L * b * d), float("nan"), device=DEV)
+    got = aggregate_backward(desc, g, bases, w, saved, saved_arg, go, True, want_lin_colsum=True, tstreams_out=t_ext)
+    assert got[1] is None and torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+    assert bool(torch.isfinite(t_ext[:n]).all()) and bool(torch.isnan(t_ext[n:]).all())
+    rowptr_t, col_t, sym_t = transpose_csr(g.rowptr.cpu(), g.col.cpu(), g.val_sym.cpu())
+    gt = egc_b200.GraphStructure.from_prepared(rowptr_t, col_t, n + pad, val_sym=sym_t, device=DEV)
+    desc_t = egc_b200.make_desc(gt, h, b, d, aggrs, False)
+    desc_t.n_dst, desc_t.n_src = gt.n_src, gt.n_dst
+    d_bases = aggregate_backward_cols(desc_t, gt, t_ext, bases)
+    print("column pass bit-equal to the one-call backward:", torch.equal(d_bases, ref[1]))
+    assert rel_err(d_bases, ref[1]) < 2e-6
+    # two entry subsets (targets below / above n // 2), the second launch accumulating
+    keep = col_t < n // 2
+    rows = torch.repeat_interleave(torch.arange(n), rowptr_t[1:] - rowptr_t[:-1])
+    halves = []
+    for m in (keep, ~keep):
+        rp = torch.zeros(n + 1, dtype=torch.long)
+        rp[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n), 0)
+        halves.append(egc_b200.GraphStructure.from_prepared(rp, col_t[m], n + pad, val_sym=sym_t[m], device=DEV))
+    two = aggregate_backward_cols(desc_t, halves[0], t_ext, bases)
+    two = aggregate_backward_cols(desc_t, halves[1], t_ext, bases, d_bases=two, accumulate=True)
+    assert rel_err(two, ref[1]) < 2e-6
