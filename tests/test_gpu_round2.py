@@ -87,7 +87,7 @@ def test_deterministic_flag_needs_csr2csc_at_the_c_abi():
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     P = _lib.ptr
     rc = lib.egc_aggregate_bwd(desc, P(g.rowptr), P(g.col), None, P(g.colptr), P(g.rowidx), None, None, None,
-                               g.csc_plan.struct, P(bases), P(w), P(saved), P(saved_arg), P(go), None, None, P(d_w), P(d_b), None, None,
+                               g.csc_plan.struct, P(bases), P(w), P(saved), P(saved_arg), P(go), None, None, P(d_w), P(d_b), None, None, None,
                                _lib.BWD_DETERMINISTIC, 0, P(ws), nbytes, torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"csr2csc" in lib.egc_last_error_string()
 
