@@ -34,7 +34,7 @@ class LayerDesc(Structure):
 
 class Epilogue(Structure):
     """mirrors `egc_epilogue`"""
-    _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("add", c_void_p)]
+    _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("add", c_void_p), ("agg_init", c_void_p)]
 
 
 class RowPlan(Structure):
@@ -82,6 +82,7 @@ SIGNATURES = {
     "egc_peer_open": (c_int32, [_P, POINTER(c_void_p)]),
     "egc_peer_close": (c_int32, [_P]),
     "egc_peer_push_rows": (c_int32, [c_int32, _P, _P, _P, _P, c_int32, _P, c_int32, c_int32, ctypes.c_uint32, _P, _P, _P]),
+    "egc_peer_copy": (c_int32, [_P, _P, c_size_t, _P]),
     "egc_peer_epoch_advance": (c_int32, [_P, _P]),
     "egc_peer_signal": (c_int32, [_P, c_int32, c_int32, ctypes.c_uint32, _P, _P]),
     "egc_peer_wait": (c_int32, [_P, c_int32, c_int32, c_int32, _P, ctypes.c_uint32, c_int32, ctypes.c_uint64, _P, _P]),

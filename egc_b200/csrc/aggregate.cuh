@@ -50,6 +50,8 @@ struct AggParams {
   const float* epi_scale;    // fused epilogue (egc_epilogue): y = y * scale + shift, [HD] each, or null
   const float* epi_shift;
   const float* epi_add;      // [n_rows, HD] added after the activation, or null (may alias out)
+  const float* agg_init;     // [n_rows, A, BD] partial aggregates of an earlier call over another entry subset (sum / symnorm
+                             // only), added to this call's before saving / combining; or null (may alias agg_out / saved)
   float* out;                // [n_rows, HD] or null
   float* agg_out;            // [n_rows, A, BD] or null   (reference `aggregated`)
   int32_t* arg_out;          // [n_rows, A, BD] or null

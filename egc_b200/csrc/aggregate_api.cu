@@ -228,6 +228,13 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
     EGC_REQUIRE((epilogue->scale == nullptr) == (epilogue->shift == nullptr), "egc_aggregate_fwd: epilogue scale and shift come together");
     EGC_REQUIRE(out != nullptr || (!epilogue->scale && !epilogue->add), "egc_aggregate_fwd: an epilogue needs the `out` output");
     p.epi_scale = epilogue->scale; p.epi_shift = epilogue->shift; p.epi_add = epilogue->add;
+    if (epilogue->agg_init != nullptr) {
+      for (int a = 0; a < desc->n_aggr; ++a)
+        EGC_REQUIRE(desc->aggr[a] == EGC_AGGR_SUM || desc->aggr[a] == EGC_AGGR_SYMNORM,
+                    "egc_aggregate_fwd: agg_init continues sums - every aggregator must be sum or symnorm");
+      EGC_REQUIRE(aligned16(epilogue->agg_init), "egc_aggregate_fwd: agg_init must be 16-byte aligned");
+      p.agg_init = epilogue->agg_init;
+    }
   }
   p.out = out; p.agg_out = agg_out; p.arg_out = arg_out; p.saved = saved; p.saved_arg = saved_arg;
   cudaStream_t st = as_stream(stream);

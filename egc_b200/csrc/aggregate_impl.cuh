@@ -122,6 +122,13 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_aggregate(const __grid_const
           if (code == EGC_AGGR_STD && !(var > 0.f)) sv[k] = -v[k];   // sign bit = relu gate closed (std > 0 always)
         }
       }
+      if (p.agg_init != nullptr) {                  // continue the sums of an earlier call (host: sum / symnorm only)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          v[k] += p.agg_init[(static_cast<int64_t>(row) * p.A + a) * p.BD + foff + k];
+          sv[k] = v[k];
+        }
+      }
       if (p.out != nullptr) st_row<VEC>(sm + p.sm_agg + a * p.BD + foff, v);
       if (p.agg_out != nullptr) st_stream<VEC>(p.agg_out + (static_cast<int64_t>(row) * p.A + a) * p.BD + foff, v);
       if (p.saved != nullptr) st_stream<VEC>(p.saved + (static_cast<int64_t>(row) * p.n_saved + a) * p.BD + foff, sv);

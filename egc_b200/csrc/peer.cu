@@ -346,6 +346,13 @@ int egc_peer_push_rows(int32_t n_seg, const float* const* src, float* const* dst
   return EGC_OK;
 }
 
+int egc_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return EGC_OK;
+  EGC_REQUIRE(dst && src, "egc_peer_copy: null pointer");
+  EGC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));   // copy engine: no SM is involved
+  return EGC_OK;
+}
+
 int egc_peer_epoch_advance(uint32_t* epoch, void* stream) {
   EGC_REQUIRE(epoch, "egc_peer_epoch_advance: null pointer");
   cudaStream_t st = as_stream(stream);

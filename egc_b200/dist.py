@@ -77,6 +77,21 @@ class LocalPartition:
     def n_local(self) -> int:
         return self.row_end - self.row_begin
 
+    def split_by_column(self):
+        """The local CSR cut by column locality: (entries whose column is an OWN row, entries whose column is a HALO row),
+        each as (rowptr, col, val_sym, val_lin) over the same rows and the same [own | halo] column space.  A sum over a
+        row = the sum over the first part (computable while the halo rows are still in flight) + the sum over the second."""
+        n = self.n_local
+        rows = torch.repeat_interleave(torch.arange(n), self.rowptr[1:] - self.rowptr[:-1])
+        is_own = self.col < n
+        parts = []
+        for m in (is_own, ~is_own):
+            rowptr = torch.zeros(n + 1, dtype=torch.long)
+            rowptr[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n), 0)
+            parts.append((rowptr, self.col[m], self.val_sym[m] if self.val_sym is not None else None,
+                          self.val_lin[m] if self.val_lin is not None else None))
+        return parts
+
     @property
     def n_halo(self) -> int:
         return int(self.halo_ids.numel())
@@ -268,6 +283,11 @@ class PartitionedGraph:
         # stream - the exchanged rows are then as wide as the partial sums they replace; EGC_DIST_T_EXCHANGE=0|1 forces it
         # (1: every layer without min / max, whatever its stream count)
         self.t_exchange = os.environ.get("EGC_DIST_T_EXCHANGE", "auto")
+        # Overlapped exchanges for sum / symnorm-only layers on the peer transport (EGC_DIST_OVERLAP=0|1, default 1): the
+        # halo rows travel by the copy engine on a side stream while the entries with OWN columns are aggregated; a second
+        # launch over the halo entries continues those sums (forward: `agg_init`; backward: EGC_BWD_ACCUMULATE)
+        self.overlap = os.environ.get("EGC_DIST_OVERLAP", "1")
+        self._split = {}
         self.group = group
         self._peer_ctx = {}
 
@@ -296,6 +316,22 @@ class PartitionedGraph:
             self._graph_t = GraphStructure.from_prepared(t.rowptr, t.col, t.n_local + t.n_halo, val_sym=t.val_sym,
                                                          val_lin=t.val_lin, device=self.device)
         return self._graph_t
+
+    def split_graphs(self, transposed: bool):
+        """(own-column part, halo-column part) of the local block (or of its transposed twin) as device graphs."""
+        if transposed not in self._split:
+            from .graph import GraphStructure
+            part = self.tpart if transposed else self.part
+            self._split[transposed] = tuple(
+                GraphStructure.from_prepared(rp, col, part.n_local + part.n_halo, val_sym=vs, val_lin=vl, device=self.device)
+                for rp, col, vs, vl in part.split_by_column())
+        return self._split[transposed]
+
+    def uses_overlap(self, aggrs) -> bool:
+        """Split launches around a copy-engine exchange: layers whose aggregators are all sum / symnorm (continuable sums
+        that do not depend on the row's entry count), peer transport, T-exchange backward."""
+        return (self.transport == "peer" and self.overlap != "0" and self.part.n_halo > 0 and
+                all(a in ("sum", "symnorm") for a in aggrs) and self.uses_t_exchange(aggrs))
 
     def uses_t_exchange(self, aggrs) -> bool:
         if self.tpart is None or self.t_exchange == "0" or any(a in ("max", "min") for a in aggrs):
@@ -359,7 +395,21 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                     F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.interior, use_plan=False,
                                         outputs=outs)
 
-            if peer is not None:
+            overlap = peer is not None and pg.uses_overlap(aggrs)
+            if overlap:
+                # copy-engine push on the side stream while the entries with own columns are aggregated here; the halo
+                # entries then continue those sums (agg_init) and the same launch combines and writes out / saved
+                main = torch.cuda.current_stream()
+                peer.side_stream.wait_stream(main)
+                with torch.cuda.stream(peer.side_stream):
+                    peer.push_forward(dma=True)
+                g_own, g_halo = pg.split_graphs(False)
+                partial = F.aggregate_combine(desc, g_own, bases_ext, None, None, want_out=False, want_agg=True)[1]
+                main.wait_stream(peer.side_stream)
+                peer.wait(P.SLOT_FWD)
+                F.aggregate_combine(desc, g_halo, bases_ext, weightings, bias, outputs=outs,
+                                    epilogue=(None, None, None, partial))
+            elif peer is not None:
                 peer.push_forward()                        # posted stores into the peers' halo regions, then FWD flag
                 interior()
                 peer.wait(P.SLOT_FWD)
@@ -369,7 +419,9 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 interior()
                 pg.exchange.finish(handle)
                 bases_ext[part.n_local:].copy_(halo)
-            if pg.overlap_interior:
+            if overlap:
+                pass
+            elif pg.overlap_interior:
                 F.aggregate_combine(desc, g, bases_ext, weightings, bias, row_subset=pg.boundary, use_plan=True,
                                     outputs=outs)
             else:                                          # one contiguous launch over every local row
@@ -396,9 +448,8 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             use_t = pg.uses_t_exchange(ctx.aggrs)
             if use_t:                                      # descriptor of the column pass over the transposed local block
-                gt = pg.graph_t
-                desc_t = F.make_desc(gt, ctx.desc.heads, ctx.desc.bases, ctx.desc.dim, ctx.aggrs, False)
-                desc_t.n_dst, desc_t.n_src = gt.n_src, gt.n_dst
+                desc_t = F.make_desc(pg.graph, ctx.desc.heads, ctx.desc.bases, ctx.desc.dim, ctx.aggrs, False)
+                desc_t.n_dst, desc_t.n_src = pg.tpart.n_local + pg.tpart.n_halo, pg.tpart.n_local   # stream rows, own columns
                 t_width = n_target_streams(ctx.aggrs) * ctx.desc.bases * ctx.desc.dim
             if peer is None and use_t:
                 t_own = torch.empty((part.n_local, t_width), dtype=torch.float32, device=x.device)
@@ -406,7 +457,7 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                                                             grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,
                                                             out_act=out_act, tstreams_out=t_own)
                 t_ext = torch.cat([t_own, pg.exchange_t.forward(t_own)])      # stream rows of the remote targets
-                d_bases = F.aggregate_backward_cols(desc_t, gt, t_ext, bases_ext[:part.n_local])
+                d_bases = F.aggregate_backward_cols(desc_t, pg.graph_t, t_ext, bases_ext[:part.n_local])
             elif peer is None:
                 d_w, d_bases_ext, d_bias, d_bc = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved,
                                                                       saved_arg, grad_out, want_b, ctx.bwd_flags,
@@ -447,9 +498,20 @@ class _PartitionedEGConvFunction(torch.autograd.Function):
                 d_w, _, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg, grad_out,
                                                     want_b, ctx.bwd_flags, want_lin_colsum=True, out_bias=v_b,
                                                     out_lin_colsum=v_bc, out_act=out_act, tstreams_out=peer.t_ext)
-                peer.push_t()
-                peer.wait(P.SLOT_BWD)
-                d_bases = F.aggregate_backward_cols(desc_t, gt, peer.t_ext, bases_ext[:part.n_local])
+                if pg.uses_overlap(ctx.aggrs):
+                    peer.side_stream.wait_stream(main)
+                    with torch.cuda.stream(peer.side_stream):
+                        peer.push_t(dma=True)
+                    gt_own, gt_halo = pg.split_graphs(True)
+                    d_bases = F.aggregate_backward_cols(desc_t, gt_own, peer.t_ext, bases_ext[:part.n_local])
+                    main.wait_stream(peer.side_stream)
+                    peer.wait(P.SLOT_BWD)
+                    d_bases = F.aggregate_backward_cols(desc_t, gt_halo, peer.t_ext, bases_ext[:part.n_local],
+                                                        d_bases=d_bases, accumulate=True)
+                else:
+                    peer.push_t()
+                    peer.wait(P.SLOT_BWD)
+                    d_bases = F.aggregate_backward_cols(desc_t, pg.graph_t, peer.t_ext, bases_ext[:part.n_local])
             elif pg.split_backward == "1" or (pg.split_backward == "auto" and not routed):
                 d_w, d_bases_ext, _, _ = F.aggregate_backward(ctx.desc, pg.graph, bases_ext, weightings, saved, saved_arg,
                                                               grad_out, want_b, ctx.bwd_flags, want_lin_colsum=True,

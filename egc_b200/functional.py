@@ -79,7 +79,8 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
     """Fused SpMM + combination (ref :191-208).  Returns (out, agg, arg, saved, saved_arg); unrequested ones
     are None.  `saved` / `saved_arg` are what the backward pass consumes (see include/egc_b200.h).
     `row_subset` (int32 device tensor) restricts the row tasks; `outputs` reuses buffers of a previous call.
-    `epilogue` = (scale, shift, add) tensors or None each: the fused tail  y*scale+shift -> relu (desc.relu) -> +add."""
+    `epilogue` = (scale, shift, add[, agg_init]) tensors or None each: the fused tail  y*scale+shift -> relu (desc.relu) ->
+    +add; agg_init [n_dst, A, B*D] = partial aggregates of an earlier call over another entry subset (sum / symnorm only)."""
     lib = _lib.load()
     dev = bases.device
     if outputs is None:
@@ -97,9 +98,8 @@ def aggregate_combine(desc: LayerDesc, graph: GraphStructure, bases: Tensor, wei
         return outputs
     epi = None
     if epilogue is not None and any(t is not None for t in epilogue):
-        scale, shift, add = epilogue
-        epi = _lib.Epilogue(scale.data_ptr() if scale is not None else None, shift.data_ptr() if shift is not None else None,
-                            add.data_ptr() if add is not None else None)
+        scale, shift, add, agg_init = tuple(epilogue) + (None,) * (4 - len(epilogue))
+        epi = _lib.Epilogue(*(t.data_ptr() if t is not None else None for t in (scale, shift, add, agg_init)))
     check(lib.egc_aggregate_fwd(desc, ptr(graph.rowptr), ptr(graph.col), ptr(graph.val_sym), ptr(graph.val_lin), plan,
                                 ptr(bases), ptr(weightings), ptr(bias), epi, ptr(row_subset) if n_subset else None, n_subset,
                                 ptr(out), ptr(agg), ptr(arg), ptr(saved), ptr(saved_arg), ptr(ws), nbytes, _stream()),

@@ -166,7 +166,13 @@ class PeerLayerContext:
             t_recv_off.append(t_recv_off[-1] + c)
         dist.all_gather_object(infos, {"n_local": part.n_local, "recv_off": recv_off, "send_off": send_off,
                                        "t_recv_off": t_recv_off}, group=group)
-        self.peers = [q for q in range(self.world) if q != self.rank]
+        # Destination order of every push: rank + 1, rank + 2, ... (mod world).  The push kernel walks its segments in
+        # this order, so at any moment the ranks write to DIFFERENT destinations; with the ascending order every rank
+        # started on rank 0 (7 senders into one ingress port), then rank 1, ...  (EGC_PEER_ORDER=ascending: A/B)
+        if os.environ.get("EGC_PEER_ORDER", "rotated") == "ascending":
+            self.peers = [q for q in range(self.world) if q != self.rank]
+        else:
+            self.peers = [(self.rank + k) % self.world for k in range(1, self.world)]
         row_bytes = 4 * bd
 
         # forward push: rows send_rows[q] of my basis table -> q's halo region, at q's offset for owner = me
@@ -178,6 +184,7 @@ class PeerLayerContext:
             self.fwd_seg_ptr[s + 1] = self.fwd_seg_ptr[s] + send_counts[q]
             fwd_dst.append(self.seg.peer_ptr(q, "bases_ext", (infos[q]["n_local"] + infos[q]["recv_off"][self.rank]) * row_bytes))
         self.fwd_dst = _ptr_array(fwd_dst)
+        self.fwd_dst_list, self.fwd_counts = fwd_dst, [send_counts[q] for q in self.peers]
         self.fwd_src = _ptr_array([self.bases_ext.data_ptr()] * len(self.peers))
 
         # backward push: my halo segment owned by q (contiguous) -> q's staging, at q's offset for sender = me
@@ -199,7 +206,12 @@ class PeerLayerContext:
                 self.t_seg_ptr[s + 1] = self.t_seg_ptr[s] + t_counts[q]
                 t_dst.append(self.seg.peer_ptr(q, "t_ext", (infos[q]["n_local"] + infos[q]["t_recv_off"][self.rank]) * 4 * self.t_width))
             self.t_dst = _ptr_array(t_dst)
+            self.t_dst_list, self.t_counts = t_dst, [t_counts[q] for q in self.peers]
             self.t_src = _ptr_array([self.t_ext.data_ptr()] * len(self.peers))
+
+        # copy-engine pushes (overlapped exchanges): the rows are packed here first, then one contiguous copy per peer
+        pack = max(sum(send_counts) * bd, sum(self.t_counts) * self.t_width if self.tpart is not None else 0, 4)
+        self.send_buf = torch.empty(pack, dtype=torch.float32, device=self.device)
 
         # deterministic reduce plan: local row -> its staging entries in ascending peer order
         if n_send:
@@ -275,8 +287,26 @@ class PeerLayerContext:
         if not fused:
             self.signal(*slots)
 
-    def push_forward(self):
+    def _push_dma(self, table: torch.Tensor, index: torch.Tensor, counts, dst_ptrs, width: int, slots):
+        """The same transfer by the copy engine: pack the rows (egc_gather_rows, local), one contiguous copy per peer in
+        the rotated order, then the flags.  No SM is busy while the bytes travel, so a compute kernel on another stream
+        runs at full occupancy meanwhile (the posted-store kernel keeps 8 CTAs per SM resident for the whole transfer)."""
+        lib = _lib.load()
+        n = int(index.numel())
+        if n:
+            check(lib.egc_gather_rows(table.data_ptr(), index.data_ptr(), n, width, self.send_buf.data_ptr(), self._stream()),
+                  "egc_gather_rows")
+        off = 0
+        for s_, nrows in enumerate(counts):
+            nbytes = nrows * width * 4
+            check(lib.egc_peer_copy(dst_ptrs[s_], self.send_buf.data_ptr() + off, nbytes, self._stream()), "egc_peer_copy")
+            off += nbytes
+        self.signal(*slots)
+
+    def push_forward(self, dma: bool = False):
         """My basis rows -> the halo regions of the peers that need them; the kernel's last CTA raises FWD."""
+        if dma:
+            return self._push_dma(self.bases_ext, self.fwd_index, self.fwd_counts, self.fwd_dst_list, self.bd, (SLOT_FWD,))
         self._push(len(self.peers), self.fwd_src, self.fwd_dst, self.fwd_seg_ptr, self.fwd_index.data_ptr(), self.bd,
                    (SLOT_FWD,))
 
@@ -287,9 +317,11 @@ class PeerLayerContext:
         src = _ptr_array([base + self.recv_off[q] * self.bd * 4 for q in self.peers])
         self._push(len(self.peers), src, self.bwd_dst, self.bwd_seg_ptr, None, self.bd, (SLOT_BWD, SLOT_CONS))
 
-    def push_t(self):
+    def push_t(self, dma: bool = False):
         """T exchange: the target-side stream rows my peers' source columns touch -> their stream tables; raises BWD and
         CONS (pass 1 is done: neither it nor the column pass reads my halo copy of the peers' basis rows)."""
+        if dma:
+            return self._push_dma(self.t_ext, self.t_index, self.t_counts, self.t_dst_list, self.t_width, (SLOT_BWD, SLOT_CONS))
         self._push(len(self.peers), self.t_src, self.t_dst, self.t_seg_ptr, self.t_index.data_ptr(), self.t_width,
                    (SLOT_BWD, SLOT_CONS))
 

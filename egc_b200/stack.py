@@ -102,11 +102,16 @@ class EGCBlock(torch.nn.Module):
         self.conv = conv
         self.bn = torch.nn.BatchNorm1d(conv.out_channels)
         self.dropout, self.residual = dropout, residual
+        self._folded = None                        # (versions of the BatchNorm tensors, scale, shift)
 
     def forward(self, x: Tensor, edge_index) -> Tensor:
         if self.training:
             y = F.relu(self.bn(self.conv(x, edge_index)))
             y = F.dropout(y, p=self.dropout, training=True)
             return y + x if self.residual else y
-        scale, shift = fold_batchnorm(self.bn)
+        bn = self.bn
+        key = tuple((t.data_ptr(), t._version) for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias) if t is not None)
+        if self._folded is None or self._folded[0] != key:      # refolded only when the statistics / affine parameters change
+            self._folded = (key,) + fold_batchnorm(bn)
+        _, scale, shift = self._folded
         return self.conv(x, edge_index, relu=True, scale=scale, shift=shift, residual=x if self.residual else None)

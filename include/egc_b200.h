@@ -83,6 +83,10 @@ typedef struct egc_epilogue {
   const float* scale;            /* [H*D] or NULL (then shift must be NULL too)                  */
   const float* shift;            /* [H*D] or NULL                                                */
   const float* add;              /* [n_dst, H*D] or NULL                                         */
+  const float* agg_init;         /* [n_dst, A, B*D] or NULL: partial aggregates of an earlier call over ANOTHER entry subset
+                                    of the same rows (agg_out of that call; sum / symnorm aggregators only): added to this
+                                    call's sums before they are saved and combined, so  call(local sources) -> call(halo
+                                    sources, agg_init) = one call over all of them.  May alias agg_out / saved.          */
 } egc_epilogue;
 
 /* Row plan: how long rows of a CSR (or columns of its CSC) are split into chunks so that no
@@ -317,6 +321,12 @@ int egc_peer_close(void* ptr);
 int egc_peer_push_rows(int32_t n_seg, const float* const* src, float* const* dst, const int32_t* seg_ptr,
                        const int32_t* index, int32_t width, uint32_t* const* flags, int32_t world, int32_t rank,
                        uint32_t slot_mask, const uint32_t* epoch, uint32_t* counter, void* stream);
+
+/* Stream-ordered copy of `bytes` from local memory into (or out of) a mapped peer segment by the COPY ENGINE
+ * (cudaMemcpyAsync): unlike egc_peer_push_rows it occupies no SM, so it overlaps a compute kernel on another stream
+ * whatever that kernel's occupancy - the rows are packed first (egc_gather_rows) and sent as one contiguous block per
+ * peer.  Capturable in a CUDA graph (a memcpy node). */
+int egc_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 
 /* *epoch += 1 (device counter) */
 int egc_peer_epoch_advance(uint32_t* epoch, void* stream);

@@ -152,6 +152,14 @@ def test_transposed_plan_invariants(world):
         # my transposed halo = the remote TARGETS of my source columns = the ranks whose forward halo contains my rows
         for q in range(world):
             assert torch.equal(plan_t.local(q).send_rows[r] + plan.bounds[q], plan_t._needs[r][q])
+    for r in range(world):                                      # own-column / halo-column parts of a local block
+        for part in (plan.local(r), plan_t.local(r)):
+            (rp_a, col_a, sym_a, _), (rp_b, col_b, sym_b, _) = part.split_by_column()
+            assert bool((col_a < part.n_local).all()) and bool((col_b >= part.n_local).all())
+            assert torch.equal(rp_a + rp_b, part.rowptr) and col_a.numel() + col_b.numel() == part.col.numel()
+            dense = lambda rp, c, v: torch.zeros(part.n_local, part.n_local + part.n_halo, dtype=torch.float64).index_put_(  # noqa: E731
+                (torch.repeat_interleave(torch.arange(part.n_local), rp[1:] - rp[:-1]), c), v.double(), accumulate=True)
+            assert torch.equal(dense(rp_a, col_a, sym_a) + dense(rp_b, col_b, sym_b), dense(part.rowptr, part.col, part.val_sym))
     assert n_target_streams(["symnorm"]) == 1 and n_target_streams(["sum", "mean"]) == 1
     assert n_target_streams(["symnorm", "mean"]) == 2 and n_target_streams(["symnorm", "max", "std"]) == 3
 

@@ -36,8 +36,9 @@ def check_two_layers(conv, conv2, params2, pg, x, go, eid, b, e, dev):
         assert rel_err(a, r) < 2e-5
 
 
-def _worker(rank, world, port, n, ei, x, go, transport, ret, aggrs=None, expect_t=False):
+def _worker(rank, world, port, n, ei, x, go, transport, ret, aggrs=None, expect_t=False, env=None):
     AGGRS = aggrs or globals()["AGGRS"]
+    os.environ.update(env or {})
     import egc_b200
     from egc_b200.dist import GraphedStep, PartitionedGraph, partitioned_egconv
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -56,6 +57,10 @@ def _worker(rank, world, port, n, ei, x, go, transport, ret, aggrs=None, expect_
         pg = PartitionedGraph.from_global(g, rank, world, dev, transport=transport)
         assert pg.transport == transport
         assert pg.uses_t_exchange(AGGRS) == expect_t
+        if env and "EGC_DIST_OVERLAP" in env:
+            want = (env["EGC_DIST_OVERLAP"] == "1" and transport == "peer" and expect_t and
+                    all(a in ("sum", "symnorm") for a in AGGRS))
+            assert pg.uses_overlap(AGGRS) == want
         b, e = pg.part.row_begin, pg.part.row_end
         assert pg.part.interior_rows.numel() > 0 and pg.part.n_halo > 0
 
@@ -148,11 +153,13 @@ def test_partitioned_layer_matches_single_gpu_world2(transport):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
-@pytest.mark.parametrize("aggrs", [["symnorm"], ["sum"], ["mean"]], ids=lambda a: "+".join(a))
-def test_partitioned_layer_with_t_exchange_matches_single_gpu_world2(transport, aggrs):
+@pytest.mark.parametrize("aggrs,overlap", [(["symnorm"], "1"), (["symnorm"], "0"), (["sum"], "1"), (["mean"], "1"),
+                                           (["sum", "symnorm"], "1")], ids=lambda a: "+".join(a) if isinstance(a, list) else f"overlap{a}")
+def test_partitioned_layer_with_t_exchange_matches_single_gpu_world2(transport, aggrs, overlap):
     """Layers without min / max and one target-side stream (EGC-S) exchange the stream rows over the TRANSPOSED plan and
     run the column pass over their own columns only.  The graph is NOT symmetric (extra one-way edges from the low to the
-    high node range), so the transposed halo differs from the forward one."""
+    high node range), so the transposed halo differs from the forward one.  overlap = 1 (peer transport, sum / symnorm): the
+    exchanges run on the copy engine next to the launch over the own-column entries, a second launch continues the sums."""
     n = 4000
     ei = random_graph(n, 30000, seed=6, hub=900)
     blk = torch.randint(0, n // 2, (2, 15000))
@@ -162,7 +169,9 @@ def test_partitioned_layer_with_t_exchange_matches_single_gpu_world2(transport, 
     x, go = torch.randn(n, 64), torch.randn(n, 128)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret, aggrs, True), nprocs=2, join=True)
+    expect_t = len(aggrs) == 1                                  # sum + symnorm: two streams, partial-sum exchange
+    mp.spawn(_worker, args=(2, _free_port(), n, ei, x, go, transport, ret, aggrs, expect_t, {"EGC_DIST_OVERLAP": overlap}),
+             nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
 
 

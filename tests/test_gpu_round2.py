@@ -284,3 +284,34 @@ def test_pass1_only_plus_column_pass_equals_the_one_call_backward(cfg):
     two = aggregate_backward_cols(desc_t, halves[0], t_ext, bases)
     two = aggregate_backward_cols(desc_t, halves[1], t_ext, bases, d_bases=two, accumulate=True)
     assert rel_err(two, ref[1]) < 2e-6
+
+
+@pytest.mark.parametrize("cfg", [(["symnorm"], 8, 4, 16), (["sum", "symnorm"], 4, 4, 32), (["sum"], 4, 3, 10)],
+                         ids=lambda c: "+".join(c[0]) + f"-h{c[1]}b{c[2]}d{c[3]}")
+def test_forward_over_two_entry_subsets_with_agg_init_equals_one_call(cfg):
+    """egc_epilogue.agg_init: a launch over the entries with columns < n / 2 (aggregates only), then one over the rest that
+    continues those sums, combines and saves = the single launch over every entry (out, saved; fp32 rounding apart)."""
+    from egc_b200.functional import aggregate_combine
+    aggrs, h, b, d = cfg
+    n = 3000
+    ei = random_graph(n, 30000, seed=96, hub=700).to(DEV)
+    g = egc_b200.GraphStructure.from_edge_index(ei, n, True, True)
+    desc = egc_b200.make_desc(g, h, b, d, aggrs, False)
+    torch.manual_seed(17)
+    bases, w = torch.randn(n, b * d, device=DEV), torch.randn(n, h * len(aggrs) * b, device=DEV)
+    bias = torch.randn(h * d, device=DEV)
+    out, _, _, saved, _ = aggregate_combine(desc, g, bases, w, bias, want_saved=True)
+    rowptr, col, sym = g.rowptr.cpu().long(), g.col.cpu().long(), g.val_sym.cpu()
+    rows = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    halves = []
+    for m in (col < n // 2, col >= n // 2):
+        rp = torch.zeros(n + 1, dtype=torch.long)
+        rp[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n), 0)
+        halves.append(egc_b200.GraphStructure.from_prepared(rp, col[m], n, val_sym=sym[m], device=DEV))
+    partial = aggregate_combine(desc, halves[0], bases, None, None, want_out=False, want_agg=True)[1]
+    out2, _, _, saved2, _ = aggregate_combine(desc, halves[1], bases, w, bias, want_saved=True,
+                                              epilogue=(None, None, None, partial))
+    assert rel_err(out2, out) < 2e-6 and rel_err(saved2, saved) < 2e-6
+    desc_mean = egc_b200.make_desc(g, h, b, d, ["mean"] * len(aggrs), False)
+    with pytest.raises(egc_b200.EGCError):                      # a mean divides by the row's entry count: not continuable
+        aggregate_combine(desc_mean, halves[1], bases, w, bias, epilogue=(None, None, None, partial))
