@@ -283,10 +283,13 @@ class PartitionedGraph:
         # stream - the exchanged rows are then as wide as the partial sums they replace; EGC_DIST_T_EXCHANGE=0|1 forces it
         # (1: every layer without min / max, whatever its stream count)
         self.t_exchange = os.environ.get("EGC_DIST_T_EXCHANGE", "auto")
-        # Overlapped exchanges for sum / symnorm-only layers on the peer transport (EGC_DIST_OVERLAP=0|1, default 1): the
-        # halo rows travel by the copy engine on a side stream while the entries with OWN columns are aggregated; a second
-        # launch over the halo entries continues those sums (forward: `agg_init`; backward: EGC_BWD_ACCUMULATE)
-        self.overlap = os.environ.get("EGC_DIST_OVERLAP", "1")
+        # Overlapped exchanges for sum / symnorm-only layers on the peer transport (EGC_DIST_OVERLAP=1, opt-in): the halo
+        # rows travel by the copy engine on a side stream while the entries with OWN columns are aggregated; a second
+        # launch over the halo entries continues those sums (forward: `agg_init`; backward: EGC_BWD_ACCUMULATE).  Measured
+        # on 2 x B200, mag shape (profiles/r02m_bench_2gpu_mag_ov{0,1}.json): 1.105 ms against 1.025 ms without - the second
+        # launches pay the per-row work again (forward 0.23 -> 0.36 ms, column pass 0.16 -> 0.28 ms), more than the two
+        # hidden pushes (0.22 ms) return - so it stays off by default.
+        self.overlap = os.environ.get("EGC_DIST_OVERLAP", "0")
         self._split = {}
         self.group = group
         self._peer_ctx = {}
