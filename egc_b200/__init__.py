@@ -9,6 +9,7 @@ Public surface (mirrors the reference operator API, /root/reference/experiments/
     GraphedStep       capture a (multi-layer) forward + backward step into one CUDA graph and replay it
     EGC               the reference's full-graph layer stack (mag/models.py) on the same kernels
     EGCBlock          conv -> BatchNorm -> ReLU -> dropout -> (+ identity) block (arxiv/norm_models.py); fused epilogue in eval mode
+    EgcArxivNet       the reference's normalised full-graph model (arxiv/norm_models.py) on the same kernels
     REGConv           heterogeneous layer of the reference's rmag experiments on the same kernels
     collate / Batch / global_{add,mean,max}_pool   device-side mini-batch collation and graph readout
     build / load      compile / load libegc_b200.so (C ABI in include/egc_b200.h)
@@ -22,7 +23,7 @@ from .conv import EGConv  # noqa: F401
 from .dist import GradientAllReduce, GraphedStep, OverlappedGradientAllReduce  # noqa: F401
 from .functional import aggregate_combine, egconv, make_desc, project  # noqa: F401
 from .hetero import REGConv  # noqa: F401
-from .stack import EGC, EGCBlock, fold_batchnorm  # noqa: F401
+from .stack import EGC, EGCBlock, EgcArxivNet, fold_batchnorm  # noqa: F401
 from .graph import GraphStructure, SparseTensor, to_sparse_tensor  # noqa: F401
 
 __version__ = "0.1.0"

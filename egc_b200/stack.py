@@ -115,3 +115,55 @@ class EGCBlock(torch.nn.Module):
             self._folded = (key,) + fold_batchnorm(bn)
         _, scale, shift = self._folded
         return self.conv(x, edge_index, relu=True, scale=scale, shift=shift, residual=x if self.residual else None)
+
+
+class EgcArxivNet(torch.nn.Module):
+    """The reference's normalised full-graph model (/root/reference/experiments/arxiv/norm_models.py:14-46 `ArxivNet` +
+    :96-127 `EgcArxivNet`): Linear embed -> num_graph_layers x [EfficientGraphConv -> BatchNorm1d -> ReLU -> dropout ->
+    (+ identity)] -> Linear -> log_softmax.  Same constructor arguments, submodule names and `state_dict` keys
+    (`embed.0.*`, `convs.{i}.comb_weights.*`, `convs.{i}.bases_weight.{b}`, `convs.{i}.bias`, `bns.{i}.*`, `out.*`), so
+    the reference's checkpoints load.
+
+    Execution: the prepared graph is built once per forward and shared by the layers.  In eval mode, for the EGC-S
+    configuration (`aggrs=["symadd"]`, the reference's arxiv / egc_s setting, no softmax weights) every block is ONE
+    aggregation kernel: the folded BatchNorm, the ReLU and the residual add are its epilogue (the BatchNorm's own affine
+    parameters are constants there: no gradient for them).  Everything else - training mode (batch statistics), mixed
+    aggregators (the paper variant adds self-loops for `symadd` only: two graphs) - runs the layer followed by torch ops."""
+
+    def __init__(self, hidden_dim: int, num_graph_layers: int, dropout: float, residual: bool, heads: int = 8, bases: int = 8,
+                 softmax: bool = False, aggrs=None, num_features: int = 128, num_classes: int = 40):
+        super().__init__()
+        from .compat import EfficientGraphConv
+        assert aggrs is not None                                                       # ref :108
+        self.num_graph_layers = num_graph_layers
+        self.embed = torch.nn.Sequential(torch.nn.Linear(num_features, hidden_dim))    # mlp([F, hidden]) (utils.py:33-43)
+        self.convs = torch.nn.ModuleList(
+            EfficientGraphConv(hidden_dim, hidden_dim, num_heads=heads, num_bases=bases, softmax_weights=softmax,
+                               aggrs=list(aggrs)) for _ in range(num_graph_layers))
+        self.bns = torch.nn.ModuleList(torch.nn.BatchNorm1d(hidden_dim) for _ in range(num_graph_layers))
+        self.out = torch.nn.Linear(hidden_dim, num_classes)
+        self.dropout, self.residual = dropout, residual
+        self.heads, self.bases, self.softmax, self.aggrs = heads, bases, softmax, list(aggrs)
+
+    def _fusable(self) -> bool:
+        return not self.training and self.aggrs == ["symadd"] and not self.softmax
+
+    def forward(self, x: Tensor, edge_index) -> Tensor:
+        from .functional import egconv
+        x = self.embed(x)
+        if self._fusable():
+            graph = self.convs[0]._graph(edge_index, x.size(0), True)                  # gcn_norm + self-loops, once
+            for conv, bn in zip(self.convs, self.bns):
+                scale, shift = fold_batchnorm(bn)
+                # one aggregator: the paper's comb-weight order h * (B * A) + b * A + a is EGConv's h * (A * B) + a * B + b
+                x = egconv(x, graph, torch.cat(list(conv.bases_weight), dim=1), conv.comb_weights.weight,
+                           conv.comb_weights.bias, conv.bias, conv.num_heads, conv.num_bases, ["symnorm"], False,
+                           conv.gemm_algo, 0, True, scale, shift, x if self.residual else None)
+        else:
+            for conv, bn in zip(self.convs, self.bns):                                 # ref :31-40
+                identity = x
+                x = F.relu(bn(conv(x, edge_index)))
+                x = F.dropout(x, p=self.dropout, training=self.training)
+                if self.residual:
+                    x = x + identity
+        return self.out(x).log_softmax(dim=-1)                                         # ref :42-43
