@@ -158,6 +158,11 @@ static int run_pass2(const egc_layer_desc& desc, const BwdLayout& L, const int32
   s.off_lin = L.ts_lin < 0 ? 0 : static_cast<int64_t>(L.ts_lin) * bd;
   s.off_sq = L.ts_sq < 0 ? 0 : static_cast<int64_t>(L.ts_sq) * bd;
   s.routed = accumulate ? 1 : 0;
+  // L2 locality hints of the column-block kernel: rows whose streams span ~48 MB around the column stay (evict_last), the
+  // rest is fetched evict_first.  EGC_BWD_NEAR_MB overrides the span (0 = no hints).
+  static const int near_mb = [] { const char* e = getenv("EGC_BWD_NEAR_MB"); return e ? std::max(0, atoi(e)) : 0; }();
+  s.near_rows = static_cast<int>(std::min<int64_t>(int64_t{1} << 30, (static_cast<int64_t>(near_mb) << 20) /
+                                                       std::max<int64_t>(1, static_cast<int64_t>(std::max(L.n_ts, 1)) * bd * 4 * 2)));
   s.mode = 0;
   if (s.col_end <= s.col_begin) return EGC_OK;
   if (col_blocks) {

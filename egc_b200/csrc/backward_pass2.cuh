@@ -31,6 +31,9 @@ struct ScatterParams {
   int64_t off_sym, off_lin, off_sq;   // float offset of each stream inside a target's row of interleaved streams
   int BD, nvec, G, n_pass;
   int routed;               // d_bases already holds a partial result (routed min/max gradients, earlier sweeps): accumulate
+  int near_rows;            // column-block kernel: a gathered target row within this many rows of the column id is fetched
+                            // with an L2 evict_last hint, the others evict_first (0: no hints).  Neighbouring columns of a
+                            // locality-ordered graph gather the same near-diagonal rows again; far rows are one-off.
   int mode;
   int* long_counter;        // [n_long] zero on entry, or null: long columns are merged by a second launch (mode 1)
 };
@@ -251,7 +254,7 @@ constexpr int kColsPerTask = 8;
 constexpr int kColWindow = 384;
 static_assert(kColWindow >= EGC_CHUNK_EDGES, "a normal column must fit the staging window");
 
-template <int TSMASK, int G>
+template <int TSMASK, int G, bool HINT = false>
 __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 : 3) k_scatter_cols(const __grid_constant__ ScatterParams p, int* __restrict__ task_counter) {
   __shared__ int s_idx_all[kAggWarps][kColWindow];
   __shared__ float s_val_all[kAggWarps][(TSMASK & 1) ? kColWindow : 1];
@@ -279,12 +282,27 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
     __syncwarp();
   };
   // sums over the staged entries [b, e) of one column (window base wb), then the xor-merge of the lane groups
-  auto accumulate = [&](int b, int e, int wb) {
+  const uint64_t pol_near = HINT ? l2_policy_keep() : 0, pol_far = HINT ? l2_policy_stream() : 0;
+  auto accumulate = [&](int b, int e, int wb, int colj) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { a_sym[k] = 0.f; a_lin[k] = 0.f; a_sq[k] = 0.f; }
     for (int pos = b; pos < e; pos += STEP) {
       float m[U], vs[U];
       float4 xs[U], xl[U], xq[U];
+      if constexpr (HINT) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int q = pos + u * NG + g, qc = min(q, e - 1);
+          const int ti = s_idx[qc - wb];
+          const size_t r = static_cast<size_t>(static_cast<uint32_t>(ti) * row_stride);
+          const uint64_t pol = abs(ti - colj) <= p.near_rows ? pol_near : pol_far;
+          m[u] = q < e ? 1.f : 0.f;
+          vs[u] = 0.f;
+          if constexpr ((TSMASK & 1) != 0) { vs[u] = q < e ? s_val[qc - wb] : 0.f; xs[u] = ldg_f4_hint(src_sym + r, pol); }
+          if constexpr ((TSMASK & 2) != 0) xl[u] = ldg_f4_hint(src_lin + r, pol);
+          if constexpr ((TSMASK & 4) != 0) xq[u] = ldg_f4_hint(src_sq + r, pol);
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int q = pos + u * NG + g, qc = min(q, e - 1);
@@ -294,6 +312,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
         if constexpr ((TSMASK & 1) != 0) { vs[u] = q < e ? s_val[qc - wb] : 0.f; xs[u] = __ldg(reinterpret_cast<const float4*>(src_sym + r)); }
         if constexpr ((TSMASK & 2) != 0) xl[u] = __ldg(reinterpret_cast<const float4*>(src_lin + r));
         if constexpr ((TSMASK & 4) != 0) xq[u] = __ldg(reinterpret_cast<const float4*>(src_sq + r));
+      }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
       const int begin = __ldg(p.chunk_begin + chunk_id);
       const int end = min(begin + EGC_CHUNK_EDGES, __ldg(p.colptr + colj + 1));
       stage(begin, end);
-      accumulate(begin, end, begin);
+      accumulate(begin, end, begin, colj);
       if (writer) {
         float* q = p.partials + static_cast<int64_t>(chunk_id) * part_stride + foff;
         if constexpr ((TSMASK & 1) != 0) st_row<4>(q + p.ts_sym * p.BD, a_sym);
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(kAggThreads, (TSMASK & (TSMASK - 1)) == 0 ? 4 
       stage(wb, we);
       for (int c = ci; c < ci + n_fit; ++c) {
         const int b = __shfl_sync(kFull, cp, c), e = __shfl_sync(kFull, cpn, c);
-        accumulate(b, e, wb);
+        accumulate(b, e, wb, c0 + c);
         write_col(c0 + c);
       }
       ci += n_fit;
@@ -446,16 +465,17 @@ static int launch_scatter_cols(const ScatterParams& p_in, int tsmask, int* task_
   const int grid = std::max(1, std::min(ceil_div(std::max(n_blocks, p.n_chunks), kAggWarps), sm_count() * resident));
   {
     LaunchScope egc_ls_("k_scatter_bwd", st);
+#define EGC_SCATTER_COLS_CASE(M)                                                                           \
+      case M:                                                                                              \
+        if (p.near_rows > 0) k_scatter_cols<M, G, true><<<grid, kAggThreads, 0, st>>>(p, task_counter);    \
+        else k_scatter_cols<M, G, false><<<grid, kAggThreads, 0, st>>>(p, task_counter);                   \
+        break;
     switch (tsmask) {
-      case 1: k_scatter_cols<1, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 2: k_scatter_cols<2, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 3: k_scatter_cols<3, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 4: k_scatter_cols<4, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 5: k_scatter_cols<5, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 6: k_scatter_cols<6, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
-      case 7: k_scatter_cols<7, G><<<grid, kAggThreads, 0, st>>>(p, task_counter); break;
+      EGC_SCATTER_COLS_CASE(1) EGC_SCATTER_COLS_CASE(2) EGC_SCATTER_COLS_CASE(3) EGC_SCATTER_COLS_CASE(4)
+      EGC_SCATTER_COLS_CASE(5) EGC_SCATTER_COLS_CASE(6) EGC_SCATTER_COLS_CASE(7)
       default: set_error("scatter_cols: bad stream mask %d", tsmask); return EGC_ERR_UNSUPPORTED;
     }
+#undef EGC_SCATTER_COLS_CASE
   }
   EGC_LAUNCH_CHECK("k_scatter_cols");
   return EGC_OK;
