@@ -158,9 +158,13 @@ static int run_pass2(const egc_layer_desc& desc, const BwdLayout& L, const int32
   s.off_lin = L.ts_lin < 0 ? 0 : static_cast<int64_t>(L.ts_lin) * bd;
   s.off_sq = L.ts_sq < 0 ? 0 : static_cast<int64_t>(L.ts_sq) * bd;
   s.routed = accumulate ? 1 : 0;
-  // L2 locality hints of the column-block kernel: rows whose streams span ~48 MB around the column stay (evict_last), the
-  // rest is fetched evict_first.  EGC_BWD_NEAR_MB overrides the span (0 = no hints).
-  static const int near_mb = [] { const char* e = getenv("EGC_BWD_NEAR_MB"); return e ? std::max(0, atoi(e)) : 0; }();
+  // L2 locality hints of the column-block kernel: target rows whose streams lie within a 64 MB span around the column id
+  // are fetched evict_last, the rest evict_first.  Measured on B200 (profiles/r02o_l2_hints.txt): arxiv-shaped EGC-M
+  // (three streams, 1536 B per target) 0.376 -> 0.332 ms, no change on the uniform graph; mag-shaped EGC-S (one stream,
+  // 256 B per target) 0.289 -> 0.362 ms - so the default is on for layers with two or more streams only.
+  // EGC_BWD_NEAR_MB overrides the span for every layer (0 = no hints).
+  static const int near_env = [] { const char* e = getenv("EGC_BWD_NEAR_MB"); return e ? std::max(0, atoi(e)) : -1; }();
+  const int near_mb = near_env >= 0 ? near_env : (L.n_ts >= 2 ? 64 : 0);
   s.near_rows = static_cast<int>(std::min<int64_t>(int64_t{1} << 30, (static_cast<int64_t>(near_mb) << 20) /
                                                        std::max<int64_t>(1, static_cast<int64_t>(std::max(L.n_ts, 1)) * bd * 4 * 2)));
   s.mode = 0;
