@@ -253,7 +253,8 @@ int egc_aggregate_fwd(const egc_layer_desc* desc, const int32_t* rowptr, const i
   auto launch = vec4 ? launch_aggregate_v4 : launch_aggregate_v1;
   p.mode = 0;
   const int hd = desc->heads * desc->dim;
-  const bool fast = vec4 && val_lin == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
+  // (agg_init - the opt-in split launches of a row-partitioned caller - is served by the general kernel only)
+  const bool fast = vec4 && val_lin == nullptr && p.agg_init == nullptr && p.n_pass == 1 && (p.G == 32 || p.G == 16) &&
                     hd <= ((desc->dim % 4 == 0) ? 512 : 128) && static_cast<int64_t>(desc->n_src) * bd < (int64_t{1} << 32) &&
                     (desc->dim % 4 != 0 || (aligned16(bias) && aligned16(p.epi_scale) && aligned16(p.epi_shift) && aligned16(p.epi_add)));
   const int static_idx = fast ? static_cfg_index(*desc) : -1;

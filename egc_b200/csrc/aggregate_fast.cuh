@@ -384,10 +384,6 @@ __global__ void __launch_bounds__(kAggThreads, 4) k_aggregate_fast(const __grid_
             }
             break;
         }
-        if (p.agg_init != nullptr) {                 // continue the sums of an earlier call (host: sum / symnorm only)
-          const float4 ii = *reinterpret_cast<const float4*>(p.agg_init + (row_s * GC::A(p) + a) * BD + foff);
-          v[0] += ii.x; v[1] += ii.y; v[2] += ii.z; v[3] += ii.w;
-        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) sv[k] = (gate_sign && !(var[k] > 0.f)) ? -v[k] : v[k];   // sign bit = relu gate closed
         if (p.out != nullptr) st_row<4>(sm + GC::sm_agg(p) + a * BD + foff, v);

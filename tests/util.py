@@ -11,7 +11,7 @@ def golden_cases(prefix=None):
     """EGConv fixtures by default; `prefix="paper_"` selects the EfficientGraphConv (paper variant) fixtures."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
     if prefix is None:
-        return [n for n in names if not n.startswith(("paper_", "regconv_", "egc_stack_"))]
+        return [n for n in names if not n.startswith(("paper_", "regconv_", "egc_stack_", "arxivnet_"))]
     return [n for n in names if n.startswith(prefix)]
 
 
