@@ -69,6 +69,7 @@ static int validate_plan(const egc_row_plan* plan, const char* who) {
 
 #include "backward_pass1.cuh"
 #include "backward_pass2.cuh"
+#include "backward_pass2_ring.cuh"
 #include "backward_route.cuh"
 
 namespace egc {
@@ -171,6 +172,11 @@ static int run_pass2(const egc_layer_desc& desc, const BwdLayout& L, const int32
   if (s.col_end <= s.col_begin) return EGC_OK;
   if (col_blocks) {
     EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes + sizeof(int), st));
+    // ring variant (rows land in a per-warp shared-memory ring, R entries ahead across columns): 128-float rows, two or more
+    // streams.  EGC_BWD_RING = ring depth (4: three CTAs per SM, 7: two), 0 = the register-gather kernel.
+    static const int ring = [] { const char* e = getenv("EGC_BWD_RING"); return e ? atoi(e) : 0; }();
+    if (ring > 0 && geo.G == 32 && L.n_ts >= 2)
+      return ring >= 7 ? launch_scatter_ring<7>(s, L.tsmask, task_counter, st) : launch_scatter_ring<4>(s, L.tsmask, task_counter, st);
     return geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st);
   }
   if (fuse_merge) EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes, st));
