@@ -173,8 +173,9 @@ static int run_pass2(const egc_layer_desc& desc, const BwdLayout& L, const int32
   if (col_blocks) {
     EGC_CUDA(cudaMemsetAsync(long_counter, 0, counters_bytes + sizeof(int), st));
     // ring variant (rows land in a per-warp shared-memory ring, R entries ahead across columns): 128-float rows, two or more
-    // streams.  EGC_BWD_RING = ring depth (4: three CTAs per SM, 7: two), 0 = the register-gather kernel.
-    static const int ring = [] { const char* e = getenv("EGC_BWD_RING"); return e ? atoi(e) : 0; }();
+    // streams.  Measured on B200, arxiv-shaped EGC-M (profiles/r02r_ring.txt): 0.334 -> 0.282 ms (depth 4 = depth 7), uniform
+    // graph 0.480 -> 0.439 ms.  EGC_BWD_RING = ring depth (4: three CTAs per SM, 7: two), 0 = the register-gather kernel.
+    static const int ring = [] { const char* e = getenv("EGC_BWD_RING"); return e ? atoi(e) : 4; }();
     if (ring > 0 && geo.G == 32 && L.n_ts >= 2)
       return ring >= 7 ? launch_scatter_ring<7>(s, L.tsmask, task_counter, st) : launch_scatter_ring<4>(s, L.tsmask, task_counter, st);
     return geo.G == 32 ? launch_scatter_cols<32>(s, L.tsmask, task_counter, st) : launch_scatter_cols<16>(s, L.tsmask, task_counter, st);

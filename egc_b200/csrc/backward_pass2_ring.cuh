@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kAggThreads, 3) k_scatter_ring(const __grid_co
   const bool hinted = p.near_rows > 0;
   const uint64_t pol_near = hinted ? l2_policy_keep() : l2_policy_normal();
   const uint64_t pol_far = hinted ? l2_policy_stream() : pol_near;
-  float a_sym[4], a_lin[4], a_sq[4];
+  float a_sym[4] = {0.f, 0.f, 0.f, 0.f}, a_lin[4] = {0.f, 0.f, 0.f, 0.f}, a_sq[4] = {0.f, 0.f, 0.f, 0.f};
   int slot_w = 0, slot_r = 0;                                    // ring slot of the next entry to issue / to consume
 
   auto stage = [&](int wb, int we) {                             // entries [wb, we) -> shared memory (no ring group pending)
