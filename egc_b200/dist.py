@@ -339,6 +339,8 @@ class PartitionedGraph:
     def uses_t_exchange(self, aggrs) -> bool:
         if self.tpart is None or self.t_exchange == "0" or any(a in ("max", "min") for a in aggrs):
             return False
+        if self.part.val_lin is not None and self.t_exchange != "1":     # per-entry weights: the partial-sum exchange (tested)
+            return False
         return self.t_exchange == "1" or n_target_streams(aggrs) == 1
 
     def peer_context(self, key, bd: int, n_flat: int, t_width: int = 0):
