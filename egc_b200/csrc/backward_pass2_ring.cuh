@@ -9,7 +9,7 @@
 //     in flight) into slot (q mod R) of the ring, one commit group per entry;
 //   * the warp runs R entries ahead of the one it consumes, ACROSS the columns of its block (and across the batches of
 //     a column): consuming entry q = wait_group(R - 1), three LDS.128 of the lane's own pieces, the same fp32 operations
-//     in the same order as k_scatter_cols (bit-identical sums), then the freed slot takes entry q + R;
+//     in the same order as k_scatter_cols, then the freed slot takes entry q + R;
 //   * a lane only ever reads what it wrote itself: no barrier, no bank conflict (lane l owns bytes [16 l, 16 l + 16)).
 // Task model, chunk partials of long columns, the ordered merge and the epilogue are those of k_scatter_cols.
 #pragma once
