@@ -434,3 +434,28 @@ def paper_forward(x: Tensor, graph_in, bases_weights: Sequence[Tensor], comb_wei
     y = torch.stack(cols, dim=2)                                                 # [N, B, A, D]  layers.py:108
     z = (w.unsqueeze(-1) * y.unsqueeze(1)).sum(dim=(2, 3)).reshape(n, -1)        # layers.py:131-135
     return z + bias if bias is not None else z
+
+
+def arxivnet_forward(x: Tensor, edge_index: Tensor, state: dict, num_layers: int, heads: int, bases: int,
+                     aggrs: Sequence[str], residual: bool, training: bool = False, eps: float = 1e-5,
+                     graph_dtype=torch.float32) -> Tensor:
+    """CPU restatement of the reference's normalised full-graph model (dropout 0):
+    /root/reference/experiments/arxiv/norm_models.py:31-43 - embed (one Linear: experiments/utils.py:33-43 with two sizes)
+    -> per layer [paper conv -> BatchNorm1d -> ReLU -> (+ identity)] -> Linear -> log_softmax.  `state` = the reference's
+    state_dict (any float dtype).  training=True uses the batch statistics (biased variance, as BatchNorm1d normalises).
+    graph_dtype: gcn_norm of an edge_index input materialises its unit edge weights in the default dtype (fp32) whatever
+    the model's dtype, so the reference's symnorm weights are fp32 values even in an fp64 run."""
+    h = x @ state["embed.0.weight"].t() + state["embed.0.bias"]                                 # norm_models.py:32
+    for i in range(num_layers):
+        identity = h
+        w_b = [state[f"convs.{i}.bases_weight.{b}"] for b in range(bases)]
+        y = paper_forward(h, edge_index, w_b, state[f"convs.{i}.comb_weights.weight"], state[f"convs.{i}.comb_weights.bias"],
+                          state.get(f"convs.{i}.bias"), aggrs, heads, graph_dtype=graph_dtype)  # :35
+        if training:
+            mean, var = y.mean(0), y.var(0, unbiased=False)
+        else:
+            mean, var = state[f"bns.{i}.running_mean"], state[f"bns.{i}.running_var"]
+        y = (y - mean) / torch.sqrt(var + eps) * state[f"bns.{i}.weight"] + state[f"bns.{i}.bias"]   # :36
+        y = torch.relu(y)                                                                      # :37 (dropout 0: identity)
+        h = y + identity if residual else y                                                    # :39-40
+    return (h @ state["out.weight"].t() + state["out.bias"]).log_softmax(dim=-1)               # :42-43

@@ -36,6 +36,24 @@ def test_state_dict_layout_and_parameter_count_match_the_reference(name):
     assert m.eval()._fusable() == (rec["aggrs"] == ["symadd"])
 
 
+@pytest.mark.parametrize("mode", ["eval", "train"])
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_restatement_matches_reference_golden(name, mode):
+    """The CPU restatement of the model (oracle/restatement.py::arxivnet_forward) against the unmodified reference's
+    output, loss and input gradient in fp64: pins what the goldens mean independently of the CUDA path."""
+    from oracle import restatement as R
+    rec = load_golden(name)
+    state = {k: (v.double() if v.is_floating_point() else v) for k, v in rec["state_dict"].items()}
+    x = rec["x"].double().requires_grad_(True)
+    out = R.arxivnet_forward(x, rec["edge_index"], state, rec["layers"], rec["heads"], rec["bases"], rec["aggrs"],
+                             rec["residual"], training=(mode == "train"))
+    loss = F.nll_loss(out[rec["train_idx"]], rec["y"][rec["train_idx"]])
+    (gx,) = torch.autograd.grad(loss, [x])
+    assert rel_err(out, rec[f"{mode}_out_f64"]) < 1e-11
+    assert abs(float(loss) - float(rec[f"{mode}_loss_f64"])) < 1e-11
+    assert rel_err(gx, rec[f"{mode}_grad_x_f64"]) < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["eval", "train"])
 @pytest.mark.parametrize("name", CASES)
